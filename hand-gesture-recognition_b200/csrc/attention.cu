@@ -1,0 +1,215 @@
+// Fused short-sequence attention core for the ViT
+// (reference model/transformer.py:66-74):
+//     q,k,v = split(to_qkv(LN(x)));  P = softmax(q k^T * d^-0.5);  out = P v
+// with 8 heads of width 32 and T = 145 (192x192) or 257 (256x256) tokens.
+//
+// One CTA owns one (image, head): its Q, K and V slices (T x 32 bf16 each)
+// live in shared memory for the whole kernel, the score matrix never leaves
+// registers, and the result is written already in the 'b n (h d)' layout the
+// output projection consumes, so the reference's three rearrange copies and
+// the HBM round trip of the (B, 8, T, T) score tensor disappear.  The last
+// layer optionally writes the normalised probabilities, because
+// Transformer.forward returns them (transformer.py:90-96).
+//
+// The contraction runs on mma.sync m16n8k16 (bf16 in, fp32 accumulate): the
+// whole attention core is 2 % of the network's FLOPs and a (145 x 145 x 32)
+// problem does not fill a 128-row tcgen05 tile.  Softmax is two-pass: pass 1
+// keeps only the running row max / sum, pass 2 recomputes the (bitwise
+// identical) scores, normalises, and feeds P straight back into the P.V MMAs
+// from registers.
+#include "hgr_internal.h"
+#include "ptx.cuh"
+
+namespace hgr {
+
+namespace {
+
+constexpr int kHeads = 8;
+constexpr int kHd = 32;        // head width
+constexpr int kPitch = 40;     // smem row pitch in bf16 (80 B): conflict-free ldmatrix
+constexpr int kWarps = 5;
+constexpr int kKeyBlock = 32;
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+template <typename TP>
+__device__ __forceinline__ void store_prob(TP* p, float v);
+template <>
+__device__ __forceinline__ void store_prob<float>(float* p, float v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void store_prob<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// Scores of a 16-query x 32-key block: s[nt][0..1] = row g, keys nt*8+2t,+1; s[nt][2..3] = row g+8.
+__device__ __forceinline__ void score_block(const uint32_t (&qa)[2][4], uint32_t k_addr_lane, float (&s)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    uint32_t kb[4];
+    ldmatrix_x4(kb, k_addr_lane + nt * 8 * kPitch * 2);
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    mma_bf16_16816(s[nt], qa[0], kb[0], kb[1]);
+    mma_bf16_16816(s[nt], qa[1], kb[2], kb[3]);
+  }
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(kWarps * 32)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, TP* __restrict__ probs, int T,
+                 int Tp, float scale_log2e) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sk = sq + Tp * kPitch;
+  __nv_bfloat16* sv = sk + Tp * kPitch;
+
+  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage Q, K, V (zero rows beyond T) --------------------------------
+  const __nv_bfloat16* base = qkv + (size_t)b * T * (3 * kHeads * kHd) + h * kHd;
+  for (int i = tid; i < 3 * Tp * 4; i += kWarps * 32) {
+    const int c = i & 3;
+    const int row = (i >> 2) % Tp;
+    const int part = (i >> 2) / Tp;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < T) v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * kHeads * kHd) + part * kHeads * kHd) + c);
+    *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v;
+  }
+  __syncthreads();
+
+  const int mtiles = (T + 15) >> 4;
+  const int kblocks = Tp / kKeyBlock;
+  // ldmatrix lane addresses
+  const uint32_t q_lane = smem_u32(sq) + ((lane & 15) * kPitch + (lane >> 4) * 8) * 2;
+  const uint32_t k_lane = smem_u32(sk) + ((lane & 7) * kPitch + (lane >> 3) * 8) * 2;
+  const uint32_t v_lane = smem_u32(sv) + ((((lane >> 3) & 1) * 8 + (lane & 7)) * kPitch + (lane >> 4) * 8) * 2;
+
+  for (int mt = warp; mt < mtiles; mt += kWarps) {
+    uint32_t qa[2][4];
+    ldmatrix_x4(qa[0], q_lane + mt * 16 * kPitch * 2);
+    ldmatrix_x4(qa[1], q_lane + mt * 16 * kPitch * 2 + 32);
+
+    // ---- pass 1: row max and sum of exponentials ----
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      float s[4][4];
+      score_block(qa, k_lane + kb * kKeyBlock * kPitch * 2, s);
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+        if (key >= T) s[nt][0] = s[nt][2] = -INFINITY;
+        if (key + 1 >= T) s[nt][1] = s[nt][3] = -INFINITY;
+        bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+        bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      // key 0 is always valid, so the running max is finite from the first block on
+      const float n0 = fmaxf(m0, quad_max(bm0)), n1 = fmaxf(m1, quad_max(bm1));
+      l0 *= exp2f((m0 - n0) * scale_log2e);
+      l1 *= exp2f((m1 - n1) * scale_log2e);
+      m0 = n0;
+      m1 = n1;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        l0 += exp2f((s[nt][0] - m0) * scale_log2e) + exp2f((s[nt][1] - m0) * scale_log2e);
+        l1 += exp2f((s[nt][2] - m1) * scale_log2e) + exp2f((s[nt][3] - m1) * scale_log2e);
+      }
+    }
+    const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
+
+    // ---- pass 2: normalised probabilities and P.V ----
+    float o[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    const int row0 = mt * 16 + g, row1 = row0 + 8;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      float s[4][4];
+      score_block(qa, k_lane + kb * kKeyBlock * kPitch * 2, s);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+        s[nt][0] = key < T ? exp2f((s[nt][0] - m0) * scale_log2e) * inv0 : 0.f;
+        s[nt][1] = key + 1 < T ? exp2f((s[nt][1] - m0) * scale_log2e) * inv0 : 0.f;
+        s[nt][2] = key < T ? exp2f((s[nt][2] - m1) * scale_log2e) * inv1 : 0.f;
+        s[nt][3] = key + 1 < T ? exp2f((s[nt][3] - m1) * scale_log2e) * inv1 : 0.f;
+        if (probs != nullptr) {
+          TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
+          if (row0 < T) {
+            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[nt][0]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[nt][1]);
+          }
+          if (row1 < T) {
+            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[nt][2]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[nt][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {  // two 16-key k-steps per block
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * j][0], s[2 * j][1]);
+        pa[1] = pack_bf16x2(s[2 * j][2], s[2 * j][3]);
+        pa[2] = pack_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3]);
+        const uint32_t vaddr = v_lane + (kb * kKeyBlock + j * 16) * kPitch * 2;
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {  // two pairs of 8-wide d tiles
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, vaddr + np * 32);
+          mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    // ---- write 'b n (h d)' ----
+    __nv_bfloat16* orow0 = out + ((size_t)b * T + row0) * (kHeads * kHd) + h * kHd + 2 * t;
+    __nv_bfloat16* orow1 = out + ((size_t)b * T + row1) * (kHeads * kHd) + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      if (row0 < T) *reinterpret_cast<uint32_t*>(orow0 + nd * 8) = pack_bf16x2(o[nd][0], o[nd][1]);
+      if (row1 < T) *reinterpret_cast<uint32_t*>(orow1 + nd * 8) = pack_bf16x2(o[nd][2], o[nd][3]);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
+                     cudaStream_t stream) {
+  const int Tp = (T + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
+  const size_t smem = (size_t)3 * Tp * kPitch * 2;
+  if (smem > 227 * 1024) {
+    set_error("attention: %d tokens do not fit one CTA's shared memory", T);
+    return -1;
+  }
+  // softmax(x * d^-0.5) evaluated as exp2((x - max) * d^-0.5 * log2(e))
+  const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
+  const unsigned grid = (unsigned)B * kHeads;
+  if (attn_probs != nullptr && probs_dtype == DT_BF16) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    attention_kernel<__nv_bfloat16><<<grid, kWarps * 32, smem, stream>>>(
+        qkv, out, static_cast<__nv_bfloat16*>(attn_probs), T, Tp, scale_log2e);
+  } else {
+    HGR_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attention_kernel<float>
+        <<<grid, kWarps * 32, smem, stream>>>(qkv, out, static_cast<float*>(attn_probs), T, Tp, scale_log2e);
+  }
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hgr

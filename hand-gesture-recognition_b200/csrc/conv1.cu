@@ -1,0 +1,167 @@
+// Stem convolution: encoder.conv1 = Conv(3, 64, k=3, s=2) + BN + SiLU
+// (reference model/gelan.py:155 via Conv.forward :55-56).
+//
+// K = 27 is too thin for the tcgen05 pipeline (one 64-wide k-step would be
+// 58 % zero padding and the layer is bound by its 1.18 MB/image output
+// anyway), so this kernel reads the NCHW fp32/bf16 crop directly, stages a
+// 9-row input patch in shared memory as bf16, and runs the contraction with
+// register-resident weights on mma.sync m16n8k16 (K padded 27 -> 32).  The
+// output is written as NHWC bf16 in full 128-byte pixel rows, which is the
+// layout every later TMA box load expects.
+#include "hgr_internal.h"
+#include "ptx.cuh"
+
+namespace hgr {
+
+namespace {
+
+constexpr int kRowsOut = 4;                 // output rows per CTA
+constexpr int kRowsIn = 2 * kRowsOut + 1;   // 9 input rows
+constexpr int kWarps = 8;
+
+template <typename TIn>
+__device__ __forceinline__ __nv_bfloat16 to_bf16(TIn v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_bf16<float>(float v) {
+  return __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_bf16<__nv_bfloat16>(__nv_bfloat16 v) {
+  return v;
+}
+
+// w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale already folded in, k>=27 zero.
+template <typename TIn>
+__global__ void __launch_bounds__(kWarps * 32)
+conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
+             const float* __restrict__ shift, int S) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int So = S >> 1;
+  const int pitch = S + 8;  // x index 0 is input column -1
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(smem_raw);               // [3][9][pitch]
+  __nv_bfloat16* stage = patch + 3 * kRowsIn * pitch;  // [warps][16][64]; 54*pitch bytes is a multiple of 16
+
+  const int b = blockIdx.y;
+  const int oh0 = blockIdx.x * kRowsOut;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage the input patch (zero padded) ------------------------------
+  const TIn* xb = x + (size_t)b * 3 * S * S;
+  const int ih0 = 2 * oh0 - 1;
+  for (int i = tid; i < 3 * kRowsIn * pitch; i += kWarps * 32) {
+    const int xi = i % pitch;
+    const int r = (i / pitch) % kRowsIn;
+    const int c = i / (pitch * kRowsIn);
+    const int ih = ih0 + r, iw = xi - 1;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.0f);
+    if (ih >= 0 && ih < S && iw >= 0 && iw < S) v = to_bf16<TIn>(xb[((size_t)c * S + ih) * S + iw]);
+    patch[i] = v;
+  }
+
+  // ---- weights -> B fragments (registers, loaded once) ------------------
+  uint32_t bfrag[8][2][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const __nv_bfloat16* wr = w + (nt * 8 + g) * 32 + s * 16 + 2 * t;
+      bfrag[nt][s][0] = *reinterpret_cast<const uint32_t*>(wr);
+      bfrag[nt][s][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+    }
+  float sh[8][2];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    sh[nt][0] = shift[nt * 8 + 2 * t];
+    sh[nt][1] = shift[nt * 8 + 2 * t + 1];
+  }
+  // per-thread gather offsets of its 8 k values: k = 16*s + 2*t + {0,1,8,9}
+  int koff[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = 16 * (i >> 2) + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
+    if (k < 27) {
+      const int c = k % 3, kw = (k / 3) % 3, kh = k / 9;
+      koff[i] = (c * kRowsIn + kh) * pitch + kw;
+    } else {
+      koff[i] = -1;
+    }
+  }
+  __syncthreads();
+
+  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
+  __nv_bfloat16* st = stage + warp * 16 * 64;
+  const int mtiles_per_row = So >> 4;
+  const int mtiles = kRowsOut * mtiles_per_row;
+  for (int mt = warp; mt < mtiles; mt += kWarps) {
+    const int orow = mt / mtiles_per_row;
+    const int ow0 = (mt % mtiles_per_row) << 4;
+    // pixel (orow, ow0+g) and (orow, ow0+g+8): patch offset of tap (0,0), channel 0
+    const int base0 = (2 * orow) * pitch + 2 * (ow0 + g);
+    const int base1 = base0 + 16;
+    uint32_t a[2][4];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      unsigned short e[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ko = koff[s * 4 + i];
+        e[i] = ko >= 0 ? pu[base0 + ko] : (unsigned short)0;
+        e[4 + i] = ko >= 0 ? pu[base1 + ko] : (unsigned short)0;
+      }
+      a[s][0] = (uint32_t)e[0] | ((uint32_t)e[1] << 16);  // row g,   k 2t,2t+1
+      a[s][1] = (uint32_t)e[4] | ((uint32_t)e[5] << 16);  // row g+8, k 2t,2t+1
+      a[s][2] = (uint32_t)e[2] | ((uint32_t)e[3] << 16);  // row g,   k 2t+8,2t+9
+      a[s][3] = (uint32_t)e[6] | ((uint32_t)e[7] << 16);  // row g+8, k 2t+8,2t+9
+    }
+    __syncwarp();  // previous tile's staging reads are done
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(d, a[0], bfrag[nt][0][0], bfrag[nt][0][1]);
+      mma_bf16_16816(d, a[1], bfrag[nt][1][0], bfrag[nt][1][1]);
+      const uint32_t lo = pack_bf16x2(silu_f(d[0] + sh[nt][0]), silu_f(d[1] + sh[nt][1]));
+      const uint32_t hi = pack_bf16x2(silu_f(d[2] + sh[nt][0]), silu_f(d[3] + sh[nt][1]));
+      // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
+      const int ch = nt * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(st + g * 64 + ((((ch >> 3) ^ g) & 7) << 3) + (ch & 7)) = lo;
+      *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + ((((ch >> 3) ^ (g + 8)) & 7) << 3) + (ch & 7)) = hi;
+    }
+    __syncwarp();
+    // 16 pixels x 128 B are contiguous in NHWC: 4 fully coalesced 512-byte stores
+    __nv_bfloat16* orow_ptr = out + (((size_t)b * So + (oh0 + orow)) * So + ow0) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane;      // 16-byte chunk index in the 2 KB tile
+      const int px = idx >> 3, chunk = idx & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(st + px * 64 + (((chunk ^ px) & 7) << 3));
+      *reinterpret_cast<uint4*>(orow_ptr + px * 64 + chunk * 8) = v;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
+                 int S, cudaStream_t stream) {
+  if (S % 32 != 0 || S < 32 || S > 1024) {
+    set_error("conv1: image side %d must be a multiple of 32 in [32, 1024]", S);
+    return -1;
+  }
+  const int pitch = S + 8;
+  const size_t smem = (size_t)3 * kRowsIn * pitch * 2 + (size_t)kWarps * 16 * 64 * 2;
+  dim3 grid((S / 2) / kRowsOut, B);
+  if (x_dtype == DT_F32) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv1_kernel<float><<<grid, kWarps * 32, smem, stream>>>(static_cast<const float*>(x), out, w, shift, S);
+  } else {
+    HGR_CHECK_CUDA(
+        cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv1_kernel<__nv_bfloat16>
+        <<<grid, kWarps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), out, w, shift, S);
+  }
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hgr

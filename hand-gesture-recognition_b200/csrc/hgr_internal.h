@@ -1,0 +1,92 @@
+// Internal declarations shared by the CUDA translation units of libhgr_b200.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace hgr {
+
+// ----------------------------------------------------------- errors ----
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define HGR_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::hgr::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------- implicit-GEMM conv / linear ----
+//
+// One launch computes   OUT[pix, n] = act( scale[n] * sum_k A[pix, k] W[n, k] + shift[n] (+ RES[pix, n]) )
+// for a tile grid of 128-pixel x BN-channel tiles.  A is never materialised:
+// K runs over (tap, 64-channel chunk) and every k-step is one TMA box load of
+// the NHWC activation tensor at tap-shifted coordinates (out-of-bounds rows
+// come back as zeros, which is the convolution's zero padding).
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+
+struct GemmParams {
+  int num_taps;        // 1 (1x1 / linear) or 9 (3x3)
+  int chunks_per_tap;  // Cin / 64
+  int a_c_off;         // first input channel inside the A buffer (concat slices)
+  int tap_dc[9];       // per-tap coordinate deltas into the 5-D A map (c, w, p, h, n)
+  int tap_dw[9];
+  int tap_p[9];
+  int tap_dh[9];
+  int tiles_w, tiles_h, tiles_n, tiles_nout;
+  int bw_log2, bh_log2;  // pixel box = (1<<bw) x (1<<bh) x (128>>(bw+bh)) images
+  int W, H, NIMG;        // output extents, for per-row validity of residual reads
+  int out_c_off;         // first output channel inside the OUT buffer
+  int out_w_off;         // extra w offset of the OUT box (token assembly writes at +1)
+  int cout;              // channels produced by this layer (length of scale/shift)
+  int act;
+  const float* scale;  // nullable: 1
+  const float* shift;  // nullable: 0
+  const __nv_bfloat16* res;  // nullable; element strides below
+  long long res_sn, res_sh, res_sw;
+};
+
+// bn is the N tile (64, 128 or 256) and must divide cout.
+int launch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                int num_sms, cudaStream_t stream);
+int gemm_smem_bytes(int bn);
+
+// ------------------------------------------------------ tensor maps ----
+// rank <= 5; dims innermost first; strides in bytes for dims 1..rank-1.
+int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                         const uint32_t* box);
+
+// --------------------------------------------------- small kernels ----
+// w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale folded in, k >= 27 zero; shift: [64] fp32.
+int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
+                 int S, cudaStream_t stream);
+
+int launch_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamma, const float* beta, long long rows,
+                     cudaStream_t stream);
+
+int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, int B, int T, cudaStream_t stream);
+
+int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
+                     cudaStream_t stream);
+
+int launch_cls_head(const __nv_bfloat16* tokens, const float* gamma, const float* beta, const float* w /*[C][256]*/,
+                    const float* bias, void* logits, int out_dtype, int B, int T, int num_classes,
+                    cudaStream_t stream);
+
+int launch_pose_head(const __nv_bfloat16* tokens, const __nv_bfloat16* w /*[Jpad][256]*/, const float* bias,
+                     void* heatmaps, int out_dtype, int B, int F, int J, cudaStream_t stream);
+
+int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw, int width, float* preds,
+                         float* maxvals, cudaStream_t stream);
+
+int launch_crop_normalize(const uint8_t* hwc, void* chw, int out_dtype, int B, int H, int W, cudaStream_t stream);
+
+enum : int { DT_F32 = 0, DT_BF16 = 1 };
+
+}  // namespace hgr

@@ -1,0 +1,789 @@
+// Host side of libhgr_b200: parameter-block layout, workspace layout, the
+// per-layer tensor maps, and the launch sequence that realises
+// MultiTaskNet.forward (reference model/multitasknet.py:24-29 ->
+// model/gelan.py:165-176 -> model/transformer.py:129-152).
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hgr_b200.h"
+#include "hgr_internal.h"
+
+namespace hgr {
+
+namespace {
+
+constexpr int kDim = 256;
+constexpr int kHeads = 8;
+constexpr int kDepth = 4;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------
+// One implicit-GEMM launch: maps + params + N tile.
+// ------------------------------------------------------------------------
+struct GemmOp {
+  CUtensorMap a, w, o;
+  GemmParams p;
+  int bn;
+};
+
+int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// Pixel box (bw x bh x bi = 128 pixels) for a W x H feature map.
+void pick_box(int W, int H, int& bw, int& bh, int& bi) {
+  bw = 16;
+  while (bw > 1 && W % bw != 0) bw >>= 1;
+  bh = 128 / bw;
+  if (bh > 8 && W >= 16) bh = 8;  // keep boxes squarish on large maps
+  while (bh > 1 && H % bh != 0) bh >>= 1;
+  bi = 128 / (bw * bh);
+}
+
+// Conv / 1x1 / stride-2 layer over NHWC bf16 buffers.
+int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, int in_coff, int cin, const void* wgt,
+                  const float* scale, const float* shift, int k, int s, int act, const void* res, int res_ctot,
+                  int res_coff, void* out, int out_ctot, int out_coff, int cout) {
+  if (!((k == 1 && s == 1) || (k == 3 && (s == 1 || s == 2)))) {
+    set_error("conv: unsupported kernel %d stride %d", k, s);
+    return -1;
+  }
+  if (cin % 64 != 0 || cout % 64 != 0 || in_coff % 64 != 0 || out_coff % 64 != 0 || in_ctot % 8 != 0 ||
+      out_ctot % 8 != 0) {
+    set_error("conv: channel counts must be multiples of 64 (cin %d cout %d)", cin, cout);
+    return -1;
+  }
+  if (s == 2 && ((H & 1) || (W & 1))) {
+    set_error("conv: stride 2 needs even H and W (%d x %d)", H, W);
+    return -1;
+  }
+  const int Ho = H / s, Wo = W / s;
+  int bw, bh, bi;
+  pick_box(Wo, Ho, bw, bh, bi);
+  memset(&op, 0, sizeof(op));
+  op.bn = pick_bn(cout);
+  GemmParams& p = op.p;
+  p.num_taps = k * k;
+  p.chunks_per_tap = cin / 64;
+  p.a_c_off = in_coff;
+  if (s == 1) {
+    // A map: (c, w, 1, h, n)
+    const uint64_t dims[5] = {(uint64_t)in_ctot, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
+    const uint64_t row = (uint64_t)in_ctot * 2;
+    const uint64_t strides[4] = {row, row * W, row * W, row * W * H};
+    const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bi};
+    if (int r = make_tensor_map_bf16(&op.a, in, 5, dims, strides, box)) return r;
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const int t = kh * k + kw;
+        p.tap_dc[t] = 0;
+        p.tap_dw[t] = kw - k / 2;
+        p.tap_p[t] = 0;
+        p.tap_dh[t] = kh - k / 2;
+      }
+  } else {
+    // Stride 2 as a space-to-depth VIEW of the same NHWC buffer:
+    // (c2 = pw*C + c, bw = W/2, ph = 2, bh = H/2, n); input column 2*ow + kw - 1
+    // is block ow + (kw==0 ? -1 : 0) with parity (kw==1 ? 0 : 1).
+    if (in_coff != 0 || in_ctot != cin) {
+      set_error("conv: stride-2 layers read a whole buffer (no channel slice)");
+      return -1;
+    }
+    const uint64_t dims[5] = {(uint64_t)(2 * cin), (uint64_t)(W / 2), 2, (uint64_t)(H / 2), (uint64_t)B};
+    const uint64_t pix = (uint64_t)cin * 2;
+    const uint64_t strides[4] = {2 * pix, pix * W, 2 * pix * W, pix * W * H};
+    const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bi};
+    if (int r = make_tensor_map_bf16(&op.a, in, 5, dims, strides, box)) return r;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int t = kh * 3 + kw;
+        p.tap_dc[t] = (kw == 1 ? 0 : 1) * cin;
+        p.tap_dw[t] = kw == 0 ? -1 : 0;
+        p.tap_p[t] = kh == 1 ? 0 : 1;
+        p.tap_dh[t] = kh == 0 ? -1 : 0;
+      }
+  }
+  {
+    const uint64_t K = (uint64_t)k * k * cin;
+    const uint64_t dims[2] = {K, (uint64_t)cout};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)out_ctot, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t row = (uint64_t)out_ctot * 2;
+    const uint64_t strides[3] = {row, row * Wo, row * Wo * Ho};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bi};
+    if (int r = make_tensor_map_bf16(&op.o, out, 4, dims, strides, box)) return r;
+  }
+  p.tiles_w = (Wo + bw - 1) / bw;
+  p.tiles_h = (Ho + bh - 1) / bh;
+  p.tiles_n = (B + bi - 1) / bi;
+  p.tiles_nout = cout / op.bn;
+  p.bw_log2 = ilog2(bw);
+  p.bh_log2 = ilog2(bh);
+  p.W = Wo;
+  p.H = Ho;
+  p.NIMG = B;
+  p.out_c_off = out_coff;
+  p.out_w_off = 0;
+  p.cout = cout;
+  p.act = act;
+  p.scale = scale;
+  p.shift = shift;
+  if (res != nullptr) {
+    p.res = static_cast<const __nv_bfloat16*>(res) + res_coff;
+    p.res_sw = res_ctot;
+    p.res_sh = (long long)res_ctot * Wo;
+    p.res_sn = (long long)res_ctot * Wo * Ho;
+  }
+  return 0;
+}
+
+// y = act(x W^T + b) (+ res) over a (rows, cin) matrix.
+int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const void* wgt, const float* bias, int act,
+                    const void* res, void* y, int cout) {
+  if (cin % 64 != 0 || cout % 64 != 0 || rows <= 0 || rows > 0x7fffffffLL) {
+    set_error("linear: unsupported shape rows %lld cin %d cout %d", rows, cin, cout);
+    return -1;
+  }
+  memset(&op, 0, sizeof(op));
+  op.bn = pick_bn(cout);
+  GemmParams& p = op.p;
+  p.num_taps = 1;
+  p.chunks_per_tap = cin / 64;
+  {
+    const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)rows, 1, 1, 1};
+    const uint64_t row = (uint64_t)cin * 2;
+    const uint64_t strides[4] = {row, row * rows, row * rows, row * rows};
+    const uint32_t box[5] = {64, 128, 1, 1, 1};
+    if (int r = make_tensor_map_bf16(&op.a, x, 5, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
+    const uint64_t strides[1] = {(uint64_t)cin * 2};
+    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)rows, 1, 1};
+    const uint64_t row = (uint64_t)cout * 2;
+    const uint64_t strides[3] = {row, row * rows, row * rows};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if (int r = make_tensor_map_bf16(&op.o, y, 4, dims, strides, box)) return r;
+  }
+  p.tiles_w = (int)((rows + 127) / 128);
+  p.tiles_h = 1;
+  p.tiles_n = 1;
+  p.tiles_nout = cout / op.bn;
+  p.bw_log2 = 7;
+  p.bh_log2 = 0;
+  p.W = (int)rows;
+  p.H = 1;
+  p.NIMG = 1;
+  p.cout = cout;
+  p.act = act;
+  p.scale = nullptr;
+  p.shift = bias;
+  if (res != nullptr) {
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.res_sw = cout;
+    p.res_sh = 0;
+    p.res_sn = 0;
+  }
+  return 0;
+}
+
+// proj (1x1 conv 512->256, no bias) fused with the token assembly of
+// ViT.forward (transformer.py:132-139): rows are written at token index 1+p
+// and the sin-cos table is added as a batch-broadcast residual.
+int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const void* wgt, const void* pe, void* tokens,
+                  int T) {
+  if (P % 16 != 0) {
+    set_error("proj: %d positions per image is not a multiple of 16", P);
+    return -1;
+  }
+  memset(&op, 0, sizeof(op));
+  op.bn = 256;
+  GemmParams& p = op.p;
+  p.num_taps = 1;
+  p.chunks_per_tap = cin / 64;
+  {
+    const uint64_t dims[5] = {(uint64_t)cin, (uint64_t)P, 1, 1, (uint64_t)B};
+    const uint64_t row = (uint64_t)cin * 2;
+    const uint64_t strides[4] = {row, row * P, row * P, row * P};
+    const uint32_t box[5] = {64, 16, 1, 1, 8};
+    if (int r = make_tensor_map_bf16(&op.a, feat, 5, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)kDim};
+    const uint64_t strides[1] = {(uint64_t)cin * 2};
+    const uint32_t box[2] = {64, 256};
+    if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)kDim, (uint64_t)T, 1, (uint64_t)B};
+    const uint64_t row = (uint64_t)kDim * 2;
+    const uint64_t strides[3] = {row, row * T, row * T};
+    const uint32_t box[4] = {64, 16, 1, 8};
+    if (int r = make_tensor_map_bf16(&op.o, tokens, 4, dims, strides, box)) return r;
+  }
+  p.tiles_w = P / 16;
+  p.tiles_h = 1;
+  p.tiles_n = (B + 7) / 8;
+  p.tiles_nout = 1;
+  p.bw_log2 = 4;
+  p.bh_log2 = 0;
+  p.W = P;
+  p.H = 1;
+  p.NIMG = B;
+  p.out_w_off = 1;
+  p.cout = kDim;
+  p.act = ACT_NONE;
+  p.res = static_cast<const __nv_bfloat16*>(pe);
+  p.res_sw = kDim;
+  p.res_sh = 0;
+  p.res_sn = 0;
+  return 0;
+}
+
+int run_op(const GemmOp& op, cudaStream_t stream) {
+  return launch_gemm(op.bn, op.a, op.w, op.o, op.p, device_sm_count(), stream);
+}
+
+// ------------------------------------------------------------------------
+// Parameter block layout
+// ------------------------------------------------------------------------
+struct ParamEntry {
+  std::string name;
+  size_t offset, nbytes;
+  int dtype;
+  int64_t dims[3];
+};
+
+struct ConvSpec {
+  const char* name;
+  int cin, cout, k, s;
+};
+
+// The 21 tensor-core convolutions of GELANNet('small') (gelan.py:155-160 and
+// GELANBlock :127-135) in execution order; conv1 is handled separately.
+const ConvSpec kConvs[] = {
+    {"encoder.conv2", 64, 128, 3, 2},
+    {"encoder.cspelan1.cv1", 128, 128, 1, 1},
+    {"encoder.cspelan1.cv2.0.cv1", 64, 64, 3, 1},
+    {"encoder.cspelan1.cv2.0.cv2", 64, 64, 3, 1},
+    {"encoder.cspelan1.cv3.0.cv1", 64, 64, 3, 1},
+    {"encoder.cspelan1.cv3.0.cv2", 64, 64, 3, 1},
+    {"encoder.cspelan1.cv4", 256, 128, 1, 1},
+    {"encoder.down1", 128, 256, 3, 2},
+    {"encoder.cspelan2.cv1", 256, 256, 1, 1},
+    {"encoder.cspelan2.cv2.0.cv1", 128, 128, 3, 1},
+    {"encoder.cspelan2.cv2.0.cv2", 128, 128, 3, 1},
+    {"encoder.cspelan2.cv3.0.cv1", 128, 128, 3, 1},
+    {"encoder.cspelan2.cv3.0.cv2", 128, 128, 3, 1},
+    {"encoder.cspelan2.cv4", 512, 256, 1, 1},
+    {"encoder.down2", 256, 512, 3, 2},
+    {"encoder.cspelan3.cv1", 512, 512, 1, 1},
+    {"encoder.cspelan3.cv2.0.cv1", 256, 256, 3, 1},
+    {"encoder.cspelan3.cv2.0.cv2", 256, 256, 3, 1},
+    {"encoder.cspelan3.cv3.0.cv1", 256, 256, 3, 1},
+    {"encoder.cspelan3.cv3.0.cv2", 256, 256, 3, 1},
+    {"encoder.cspelan3.cv4", 1024, 512, 1, 1},
+};
+constexpr int kNumConvs = sizeof(kConvs) / sizeof(kConvs[0]);
+
+std::vector<ParamEntry> param_layout(int S, int J, int C) {
+  std::vector<ParamEntry> v;
+  size_t off = 0;
+  auto add = [&](const std::string& name, int dtype, int64_t d0, int64_t d1 = 1, int64_t d2 = 1) {
+    ParamEntry e;
+    e.name = name;
+    e.dtype = dtype;
+    e.dims[0] = d0;
+    e.dims[1] = d1;
+    e.dims[2] = d2;
+    e.nbytes = (size_t)(d0 * d1 * d2) * (dtype == DT_F32 ? 4 : 2);
+    e.offset = off;
+    off = align_up(off + e.nbytes, 1024);
+    v.push_back(e);
+  };
+  add("encoder.conv1.w", DT_BF16, 64, 32);
+  add("encoder.conv1.shift", DT_F32, 64);
+  for (int i = 0; i < kNumConvs; ++i) {
+    const ConvSpec& c = kConvs[i];
+    add(std::string(c.name) + ".w", DT_BF16, c.cout, c.k * c.k, c.cin);
+    add(std::string(c.name) + ".scale", DT_F32, c.cout);
+    add(std::string(c.name) + ".shift", DT_F32, c.cout);
+  }
+  const int F = S / 16;
+  add("proj.w", DT_BF16, kDim, 512);
+  add("decoder.pos_embedding", DT_BF16, (int64_t)F * F, kDim);
+  add("decoder.cls_token", DT_F32, kDim);
+  for (int l = 0; l < kDepth; ++l) {
+    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
+    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
+    add(a + "norm.weight", DT_F32, kDim);
+    add(a + "norm.bias", DT_F32, kDim);
+    add(a + "to_qkv.w", DT_BF16, 3 * kDim, kDim);
+    add(a + "to_out.w", DT_BF16, kDim, kDim);
+    add(f + "0.weight", DT_F32, kDim);
+    add(f + "0.bias", DT_F32, kDim);
+    add(f + "1.w", DT_BF16, kDim, kDim);
+    add(f + "1.bias", DT_F32, kDim);
+    add(f + "4.w", DT_BF16, kDim, kDim);
+    add(f + "4.bias", DT_F32, kDim);
+  }
+  add("decoder.mlp_head.0.weight", DT_F32, kDim);
+  add("decoder.mlp_head.0.bias", DT_F32, kDim);
+  add("decoder.mlp_head.1.weight", DT_F32, C, kDim);
+  add("decoder.mlp_head.1.bias", DT_F32, C);
+  add("decoder.simple_decoder.1.w", DT_BF16, J, kDim);
+  add("decoder.simple_decoder.1.bias", DT_F32, J);
+  return v;
+}
+
+size_t param_total(const std::vector<ParamEntry>& v) {
+  return v.empty() ? 0 : align_up(v.back().offset + v.back().nbytes, 1024);
+}
+
+// ------------------------------------------------------------------------
+// Workspace layout (all NHWC bf16)
+// ------------------------------------------------------------------------
+struct Buf {
+  std::string name;
+  size_t offset;
+  int64_t dims[4];  // N, H, W, C
+};
+
+std::vector<Buf> workspace_layout(int S, int B, size_t* total) {
+  std::vector<Buf> v;
+  size_t off = 0;
+  auto add = [&](const char* name, int64_t h, int64_t w, int64_t c) {
+    Buf b;
+    b.name = name;
+    b.offset = off;
+    b.dims[0] = B;
+    b.dims[1] = h;
+    b.dims[2] = w;
+    b.dims[3] = c;
+    off = align_up(off + (size_t)B * h * w * c * 2, 1024);
+    v.push_back(b);
+  };
+  const int H1 = S / 2, H2 = S / 4, H3 = S / 8, H4 = S / 16, T = H4 * H4 + 1;
+  add("a1", H1, H1, 64);
+  add("a2", H2, H2, 128);
+  add("g1", H2, H2, 256);
+  add("t1", H2, H2, 64);
+  add("o1", H2, H2, 128);
+  add("d1", H3, H3, 256);
+  add("g2", H3, H3, 512);
+  add("t2", H3, H3, 128);
+  add("o2", H3, H3, 256);
+  add("d2", H4, H4, 512);
+  add("g3", H4, H4, 1024);
+  add("t3", H4, H4, 256);
+  add("o3", H4, H4, 512);
+  add("tokens", 1, T, kDim);
+  add("tokens_b", 1, T, kDim);
+  add("ln", 1, T, kDim);
+  add("qkv", 1, T, 3 * kDim);
+  add("attn_out", 1, T, kDim);
+  add("hidden", 1, T, kDim);
+  *total = off;
+  return v;
+}
+
+}  // namespace
+
+}  // namespace hgr
+
+// ==========================================================================
+// C ABI
+// ==========================================================================
+using namespace hgr;
+
+struct hgr_plan {
+  int S, F, T, B, J, C;
+  uint8_t* params;
+  uint8_t* ws;
+  std::vector<ParamEntry> playout;
+  std::vector<Buf> bufs;
+  std::vector<GemmOp> convs;        // kNumConvs backbone layers
+  GemmOp proj;
+  GemmOp qkv[kDepth], out[kDepth], ff1[kDepth], ff2[kDepth];
+  // host-path staging
+  void* d_x = nullptr;
+  void* d_logits = nullptr;
+  void* d_heat = nullptr;
+  size_t d_x_bytes = 0, d_logits_bytes = 0, d_heat_bytes = 0;
+
+  const ParamEntry* param(const std::string& n) const {
+    for (auto& e : playout)
+      if (e.name == n) return &e;
+    return nullptr;
+  }
+  const Buf* buf(const std::string& n) const {
+    for (auto& b : bufs)
+      if (b.name == n) return &b;
+    return nullptr;
+  }
+  template <typename T>
+  T* pp(const std::string& n) const {
+    const ParamEntry* e = param(n);
+    return e ? reinterpret_cast<T*>(params + e->offset) : nullptr;
+  }
+  __nv_bfloat16* bp(const std::string& n) const {
+    const Buf* b = buf(n);
+    return b ? reinterpret_cast<__nv_bfloat16*>(ws + b->offset) : nullptr;
+  }
+};
+
+namespace {
+
+int check_config(int S, int J, int C) {
+  if (S < 64 || S > 1024 || S % 64 != 0) {
+    set_error("image_size %d unsupported: must be a multiple of 64 in [64, 1024]", S);
+    return -1;
+  }
+  if (J < 1 || J > 24 || C < 1 || C > 4096) {
+    set_error("num_joints %d / num_classes %d unsupported", J, C);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hgr_version(void) { return 100; }
+
+const char* hgr_last_error(void) { return last_error(); }
+
+int hgr_param_count(int S, int J, int C) {
+  if (check_config(S, J, C)) return -1;
+  return (int)param_layout(S, J, C).size();
+}
+
+int hgr_param_info(int S, int J, int C, int index, const char** name, size_t* offset, size_t* nbytes, int* dtype,
+                   int64_t dims[3]) {
+  if (check_config(S, J, C)) return -1;
+  static thread_local std::vector<ParamEntry> cache;
+  static thread_local int cs = 0, cj = 0, cc = 0;
+  if (cs != S || cj != J || cc != C) {
+    cache = param_layout(S, J, C);
+    cs = S;
+    cj = J;
+    cc = C;
+  }
+  if (index < 0 || index >= (int)cache.size()) {
+    set_error("param index %d out of range", index);
+    return -1;
+  }
+  const ParamEntry& e = cache[index];
+  *name = e.name.c_str();
+  *offset = e.offset;
+  *nbytes = e.nbytes;
+  *dtype = e.dtype;
+  dims[0] = e.dims[0];
+  dims[1] = e.dims[1];
+  dims[2] = e.dims[2];
+  return 0;
+}
+
+size_t hgr_param_bytes(int S, int J, int C) {
+  if (check_config(S, J, C)) return 0;
+  return param_total(param_layout(S, J, C));
+}
+
+size_t hgr_workspace_bytes(int S, int batch) {
+  if (check_config(S, 21, 19) || batch < 1) return 0;
+  size_t total = 0;
+  workspace_layout(S, batch, &total);
+  return total;
+}
+
+int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_params, void* d_workspace,
+                    size_t workspace_bytes) {
+  if (!out) return -1;
+  *out = nullptr;
+  if (check_config(S, J, C)) return -1;
+  if (batch < 1) {
+    set_error("batch %d", batch);
+    return -1;
+  }
+  if (!d_params || !d_workspace || (reinterpret_cast<uintptr_t>(d_params) & 1023) ||
+      (reinterpret_cast<uintptr_t>(d_workspace) & 1023)) {
+    set_error("params/workspace must be non-null, 1024-byte aligned device pointers");
+    return -1;
+  }
+  hgr_plan* pl = new hgr_plan();
+  pl->S = S;
+  pl->F = S / 16;
+  pl->T = pl->F * pl->F + 1;
+  pl->B = batch;
+  pl->J = J;
+  pl->C = C;
+  pl->params = static_cast<uint8_t*>(d_params);
+  pl->ws = static_cast<uint8_t*>(d_workspace);
+  pl->playout = param_layout(S, J, C);
+  size_t need = 0;
+  pl->bufs = workspace_layout(S, batch, &need);
+  if (workspace_bytes < need) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    delete pl;
+    return -1;
+  }
+  const int B = batch;
+  const int H1 = S / 2, H2 = S / 4, H3 = S / 8, H4 = S / 16;
+  pl->convs.resize(kNumConvs);
+  int ci = 0;
+  int rc = 0;
+  auto conv = [&](const char* in, int H, int in_ctot, int in_coff, const char* res, int res_ctot, int res_coff,
+                  const char* outb, int out_ctot, int out_coff, int act) {
+    if (rc) return;
+    const ConvSpec& c = kConvs[ci];
+    const std::string n = c.name;
+    rc = build_conv_op(pl->convs[ci], pl->bp(in), B, H, H, in_ctot, in_coff, c.cin, pl->pp<void>(n + ".w"),
+                       pl->pp<float>(n + ".scale"), pl->pp<float>(n + ".shift"), c.k, c.s, act,
+                       res ? pl->bp(res) : nullptr, res_ctot, res_coff, pl->bp(outb), out_ctot, out_coff, c.cout);
+    ++ci;
+  };
+  // GELANNet.forward (gelan.py:165-176); GELANBlock.forward (:137-142) with the
+  // chunk/cat realised as channel slices of one buffer; ResBasicBlock (:78-87).
+  conv("a1", H1, 64, 0, nullptr, 0, 0, "a2", 128, 0, ACT_SILU);          // conv2
+  auto gelan = [&](const char* in, int H, int cin, const char* g, const char* t, const char* o, int hid1, int hid2) {
+    const int gtot = hid1 + 2 * hid2;
+    conv(in, H, cin, 0, nullptr, 0, 0, g, gtot, 0, ACT_SILU);                        // cv1
+    conv(g, H, gtot, hid1 / 2, nullptr, 0, 0, t, hid2, 0, ACT_SILU);                 // cv2.0.cv1
+    conv(t, H, hid2, 0, g, gtot, hid1 / 2, g, gtot, hid1, ACT_SILU);                 // cv2.0.cv2 + x, SiLU
+    conv(g, H, gtot, hid1, nullptr, 0, 0, t, hid2, 0, ACT_SILU);                     // cv3.0.cv1
+    conv(t, H, hid2, 0, g, gtot, hid1, g, gtot, hid1 + hid2, ACT_SILU);              // cv3.0.cv2 + x, SiLU
+    conv(g, H, gtot, 0, nullptr, 0, 0, o, cin, 0, ACT_SILU);                         // cv4
+  };
+  gelan("a2", H2, 128, "g1", "t1", "o1", 128, 64);
+  conv("o1", H2, 128, 0, nullptr, 0, 0, "d1", 256, 0, ACT_SILU);         // down1
+  gelan("d1", H3, 256, "g2", "t2", "o2", 256, 128);
+  conv("o2", H3, 256, 0, nullptr, 0, 0, "d2", 512, 0, ACT_SILU);         // down2
+  gelan("d2", H4, 512, "g3", "t3", "o3", 512, 256);
+  if (!rc)
+    rc = build_proj_op(pl->proj, pl->bp("o3"), B, H4 * H4, 512, pl->pp<void>("proj.w"),
+                       pl->pp<void>("decoder.pos_embedding"), pl->bp("tokens"), pl->T);
+  const long long rows = (long long)B * pl->T;
+  for (int l = 0; l < kDepth && !rc; ++l) {
+    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
+    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
+    rc = build_linear_op(pl->qkv[l], pl->bp("ln"), rows, kDim, pl->pp<void>(a + "to_qkv.w"), nullptr, ACT_NONE,
+                         nullptr, pl->bp("qkv"), 3 * kDim);
+    if (!rc)
+      rc = build_linear_op(pl->out[l], pl->bp("attn_out"), rows, kDim, pl->pp<void>(a + "to_out.w"), nullptr,
+                           ACT_NONE, pl->bp("tokens"), pl->bp("tokens_b"), kDim);
+    if (!rc)
+      rc = build_linear_op(pl->ff1[l], pl->bp("ln"), rows, kDim, pl->pp<void>(f + "1.w"), pl->pp<float>(f + "1.bias"),
+                           ACT_GELU, nullptr, pl->bp("hidden"), kDim);
+    if (!rc)
+      rc = build_linear_op(pl->ff2[l], pl->bp("hidden"), rows, kDim, pl->pp<void>(f + "4.w"),
+                           pl->pp<float>(f + "4.bias"), ACT_NONE, pl->bp("tokens_b"), pl->bp("tokens"), kDim);
+  }
+  if (rc) {
+    delete pl;
+    return rc;
+  }
+  *out = pl;
+  return 0;
+}
+
+void hgr_plan_destroy(hgr_plan_t* plan) {
+  if (!plan) return;
+  if (plan->d_x) cudaFree(plan->d_x);
+  if (plan->d_logits) cudaFree(plan->d_logits);
+  if (plan->d_heat) cudaFree(plan->d_heat);
+  delete plan;
+}
+
+int hgr_plan_launches(hgr_plan_t* plan, int with_attn) {
+  (void)with_attn;
+  if (!plan) return -1;
+  // conv1 + 21 convs + cls fill + proj + 4 x (ln, qkv, attn, out, ln, ff1, ff2) + cls head + pose head
+  return 1 + kNumConvs + 2 + kDepth * 7 + 2;
+}
+
+int hgr_forward(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                void* d_attn, int out_dtype, void* stream_v) {
+  if (!pl || !d_x || !d_logits || !d_heatmaps) {
+    set_error("hgr_forward: null argument");
+    return -1;
+  }
+  if (batch != pl->B) {
+    // tensor maps and tile grids are built for the plan's batch; smaller
+    // batches would need re-encoded maps, so the host mirror keeps one plan per batch size.
+    set_error("hgr_forward: batch %d != plan batch %d", batch, pl->B);
+    return -1;
+  }
+  if ((x_dtype != DT_F32 && x_dtype != DT_BF16) || (out_dtype != DT_F32 && out_dtype != DT_BF16)) {
+    set_error("hgr_forward: bad dtype code");
+    return -1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  const int B = pl->B, T = pl->T;
+  const long long rows = (long long)B * T;
+  int rc = launch_conv1(d_x, x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
+                        pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
+  for (int i = 0; i < kNumConvs && !rc; ++i) rc = run_op(pl->convs[i], st);
+  if (!rc) rc = launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"), B, T, st);
+  if (!rc) rc = run_op(pl->proj, st);
+  for (int l = 0; l < kDepth && !rc; ++l) {
+    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
+    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
+    // Attention (transformer.py:62-77) + residual (:93)
+    rc = launch_layernorm(pl->bp("tokens"), pl->bp("ln"), pl->pp<float>(a + "norm.weight"),
+                          pl->pp<float>(a + "norm.bias"), rows, st);
+    if (!rc) rc = run_op(pl->qkv[l], st);
+    if (!rc)
+      rc = launch_attention(pl->bp("qkv"), pl->bp("attn_out"), l == kDepth - 1 ? d_attn : nullptr, out_dtype, B, T, st);
+    if (!rc) rc = run_op(pl->out[l], st);
+    // FeedForward (transformer.py:32-42) + residual (:94)
+    if (!rc)
+      rc = launch_layernorm(pl->bp("tokens_b"), pl->bp("ln"), pl->pp<float>(f + "0.weight"),
+                            pl->pp<float>(f + "0.bias"), rows, st);
+    if (!rc) rc = run_op(pl->ff1[l], st);
+    if (!rc) rc = run_op(pl->ff2[l], st);
+  }
+  if (!rc)
+    rc = launch_cls_head(pl->bp("tokens"), pl->pp<float>("decoder.mlp_head.0.weight"),
+                         pl->pp<float>("decoder.mlp_head.0.bias"), pl->pp<float>("decoder.mlp_head.1.weight"),
+                         pl->pp<float>("decoder.mlp_head.1.bias"), d_logits, out_dtype, B, T, pl->C, st);
+  if (!rc)
+    rc = launch_pose_head(pl->bp("tokens"), pl->pp<__nv_bfloat16>("decoder.simple_decoder.1.w"),
+                          pl->pp<float>("decoder.simple_decoder.1.bias"), d_heatmaps, out_dtype, B, pl->F, pl->J, st);
+  return rc;
+}
+
+int hgr_forward_host(hgr_plan_t* pl, const void* h_x, int x_dtype, int batch, void* h_logits, void* h_heatmaps,
+                     int out_dtype, void* stream_v) {
+  if (!pl || !h_x || !h_logits || !h_heatmaps) {
+    set_error("hgr_forward_host: null argument");
+    return -1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  const size_t xin = (size_t)pl->B * 3 * pl->S * pl->S * (x_dtype == DT_F32 ? 4 : 2);
+  const size_t osz = out_dtype == DT_F32 ? 4 : 2;
+  const size_t lb = (size_t)pl->B * pl->C * osz;
+  const size_t hb = (size_t)pl->B * pl->J * (pl->S / 4) * (pl->S / 4) * osz;
+  if (pl->d_x_bytes < xin) {
+    if (pl->d_x) cudaFree(pl->d_x);
+    HGR_CHECK_CUDA(cudaMalloc(&pl->d_x, xin));
+    pl->d_x_bytes = xin;
+  }
+  if (pl->d_logits_bytes < lb) {
+    if (pl->d_logits) cudaFree(pl->d_logits);
+    HGR_CHECK_CUDA(cudaMalloc(&pl->d_logits, lb));
+    pl->d_logits_bytes = lb;
+  }
+  if (pl->d_heat_bytes < hb) {
+    if (pl->d_heat) cudaFree(pl->d_heat);
+    HGR_CHECK_CUDA(cudaMalloc(&pl->d_heat, hb));
+    pl->d_heat_bytes = hb;
+  }
+  HGR_CHECK_CUDA(cudaMemcpyAsync(pl->d_x, h_x, xin, cudaMemcpyHostToDevice, st));
+  if (int rc = hgr_forward(pl, pl->d_x, x_dtype, batch, pl->d_logits, pl->d_heat, nullptr, out_dtype, stream_v))
+    return rc;
+  HGR_CHECK_CUDA(cudaMemcpyAsync(h_logits, pl->d_logits, lb, cudaMemcpyDeviceToHost, st));
+  HGR_CHECK_CUDA(cudaMemcpyAsync(h_heatmaps, pl->d_heat, hb, cudaMemcpyDeviceToHost, st));
+  HGR_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int hgr_plan_buffer(hgr_plan_t* pl, const char* name, void** d_ptr, int64_t dims[4]) {
+  if (!pl || !name) return -1;
+  const Buf* b = pl->buf(name);
+  if (!b) {
+    set_error("no workspace buffer named '%s'", name);
+    return -1;
+  }
+  *d_ptr = pl->ws + b->offset;
+  for (int i = 0; i < 4; ++i) dims[i] = b->dims[i];
+  return 0;
+}
+
+// ---------------------------------------------------------- single ops ----
+
+int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, int in_coff, int cin, const void* d_w,
+                    const float* d_scale, const float* d_shift, int k, int s, int act, const void* d_res,
+                    int res_ctot, int res_coff, void* d_out, int out_ctot, int out_coff, int cout, void* stream) {
+  GemmOp op;
+  if (int rc = build_conv_op(op, d_in, B, H, W, in_ctot, in_coff, cin, d_w, d_scale, d_shift, k, s, act, d_res,
+                             res_ctot, res_coff, d_out, out_ctot, out_coff, cout))
+    return rc;
+  return run_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_bias, int act,
+               const void* d_res, void* d_y, int cout, void* stream) {
+  GemmOp op;
+  if (int rc = build_linear_op(op, d_x, rows, cin, d_w, d_bias, act, d_res, d_y, cout)) return rc;
+  return run_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_conv1(const void* d_x, int x_dtype, int B, int S, const void* d_w, const float* d_shift, void* d_out,
+              void* stream) {
+  return launch_conv1(d_x, x_dtype, static_cast<__nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(d_w),
+                      d_shift, B, S, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_layernorm(const void* d_x, void* d_y, const float* d_gamma, const float* d_beta, long long rows,
+                  void* stream) {
+  return launch_layernorm(static_cast<const __nv_bfloat16*>(d_x), static_cast<__nv_bfloat16*>(d_y), d_gamma, d_beta,
+                          rows, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_attention(const void* d_qkv, void* d_out, void* d_probs, int probs_dtype, int B, int T, void* stream) {
+  return launch_attention(static_cast<const __nv_bfloat16*>(d_qkv), static_cast<__nv_bfloat16*>(d_out), d_probs,
+                          probs_dtype, B, T, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
+                 const float* d_bias, void* d_logits, int out_dtype, int B, int T, int num_classes, void* stream) {
+  return launch_cls_head(static_cast<const __nv_bfloat16*>(d_tokens), d_gamma, d_beta, d_w, d_bias, d_logits,
+                         out_dtype, B, T, num_classes, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_pose_head(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps, int out_dtype, int B,
+                  int F, int J, void* stream) {
+  return launch_pose_head(static_cast<const __nv_bfloat16*>(d_tokens), static_cast<const __nv_bfloat16*>(d_w), d_bias,
+                          d_heatmaps, out_dtype, B, F, J, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_get_max_preds(const void* d_heatmaps, int dtype, int B, int J, int H, int W, float* d_preds,
+                      float* d_maxvals, void* stream) {
+  if (B < 0 || J < 0 || H <= 0 || W <= 0) {
+    set_error("get_max_preds: bad shape (%d, %d, %d, %d)", B, J, H, W);
+    return -1;
+  }
+  return launch_get_max_preds(d_heatmaps, dtype, (long long)B * J, H * W, W, d_preds, d_maxvals,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, int H, int W, void* stream) {
+  return launch_crop_normalize(d_hwc, d_chw, out_dtype, B, H, W, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Memory-bound tail of the hot path.
+//
+// get_max_preds  - reference libs/utils.py:4-32 (numpy on the host, after a
+//                  device->host copy of every heatmap).  Bit-exact contract:
+//                  first index on ties, NaN wins and masks the prediction to
+//                  (0, 0), x = idx % W and y = floor(idx / W) evaluated in
+//                  fp32 like the reference does, zeroed where max <= 0.
+// crop_normalize - reference detect.py:106-112 (and its training twin
+//                  libs/load.py:46-50): HWC uint8 -> CHW float,
+//                  ((v / 255) - mean[c]) / std[c] in fp32 with the ImageNet
+//                  constants applied by channel INDEX (the frames are BGR).
+//
+// Both use 128-bit loads; the arg-max reduces through warp shuffles.
+#include "hgr_internal.h"
+#include "ptx.cuh"
+
+namespace hgr {
+
+namespace {
+
+// "a beats b" under numpy's argmax order: NaN is maximal, otherwise larger
+// value; equal values keep the smaller index.
+__device__ __forceinline__ bool beats(float av, int ai, float bv, int bi) {
+  const bool an = av != av, bn = bv != bv;
+  if (an || bn) {
+    if (an && bn) return ai < bi;
+    return an;
+  }
+  if (av > bv) return true;
+  if (av < bv) return false;
+  return ai < bi;
+}
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<float> {
+  static constexpr int kN = 4;
+  __device__ static void load(const float* p, float (&v)[8]) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+  __device__ static float one(const float* p) { return __ldg(p); }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = bf16_lo(w[i]);
+      v[2 * i + 1] = bf16_hi(w[i]);
+    }
+  }
+  __device__ static float one(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+max_preds_kernel(const T* __restrict__ heat, long long rows, int hw, int width, float* __restrict__ preds,
+                 float* __restrict__ maxvals) {
+  constexpr int N = Vec<T>::kN;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* p = heat + row * hw;
+
+  float best = 0.f;
+  int besti = 0x7fffffff;  // "nothing yet": any real element beats it through the index rule below
+  bool have = false;
+  const bool vec_ok = (hw % N == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+  if (vec_ok) {
+    for (int i = lane * N; i < hw; i += 32 * N) {
+      float v[8];
+      Vec<T>::load(p + i, v);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        if (!have || beats(v[k], i + k, best, besti)) {
+          best = v[k];
+          besti = i + k;
+          have = true;
+        }
+      }
+    }
+  } else {
+    for (int i = lane; i < hw; i += 32) {
+      const float v = Vec<T>::one(p + i);
+      if (!have || beats(v, i, best, besti)) {
+        best = v;
+        besti = i;
+        have = true;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    const bool oh = __shfl_xor_sync(0xffffffffu, (int)have, o) != 0;
+    if (oh && (!have || beats(ov, oi, best, besti))) {
+      best = ov;
+      besti = oi;
+      have = true;
+    }
+  }
+  if (lane == 0) {
+    const float fi = (float)besti, fw = (float)width;
+    float x = fmodf(fi, fw);
+    float y = floorf(__fdiv_rn(fi, fw));
+    const float mask = best > 0.0f ? 1.0f : 0.0f;  // NaN > 0 is false, as in numpy
+    x = __fmul_rn(x, mask);
+    y = __fmul_rn(y, mask);
+    preds[row * 2] = x;
+    preds[row * 2 + 1] = y;
+    maxvals[row] = best;
+  }
+}
+
+template <typename TOut>
+__device__ __forceinline__ void store4(TOut* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+template <typename TOut>
+__device__ __forceinline__ void store1(TOut* p, float a);
+template <>
+__device__ __forceinline__ void store1<float>(float* p, float a) {
+  *p = a;
+}
+template <>
+__device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16* p, float a) {
+  *p = __float2bfloat16_rn(a);
+}
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+crop_normalize_kernel(const uint8_t* __restrict__ hwc, TOut* __restrict__ chw, long long npix_total, int hw) {
+  // 256-entry table per channel, built with the reference's operation order in IEEE fp32.
+  __shared__ float lut[3][256];
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, v = i & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean[c]), stdv[c]);
+  }
+  __syncthreads();
+  const bool vec_ok = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(hwc) & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(chw) & 15) == 0);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec_ok) {
+    const long long nquads = npix_total >> 2;
+    for (long long qd = (long long)blockIdx.x * blockDim.x + threadIdx.x; qd < nquads; qd += stride) {
+      const long long pix = qd << 2;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(hwc + pix * 3);
+      const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      uint8_t by[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        by[k] = (w0 >> (8 * k)) & 0xff;
+        by[4 + k] = (w1 >> (8 * k)) & 0xff;
+        by[8 + k] = (w2 >> (8 * k)) & 0xff;
+      }
+      const long long img = pix / hw;
+      const long long off = pix - img * hw;
+      TOut* dst = chw + img * 3 * hw + off;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        store4<TOut>(dst + (long long)c * hw, lut[c][by[c]], lut[c][by[3 + c]], lut[c][by[6 + c]], lut[c][by[9 + c]]);
+    }
+  } else {
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix_total; pix += stride) {
+      const long long img = pix / hw;
+      const long long off = pix - img * hw;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) store1<TOut>(chw + img * 3 * hw + (long long)c * hw + off, lut[c][hwc[pix * 3 + c]]);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw, int width, float* preds,
+                         float* maxvals, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (hw <= 0 || width <= 0) {
+    set_error("get_max_preds: empty heatmap (hw=%d width=%d)", hw, width);
+    return -1;
+  }
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  if (dtype == DT_F32)
+    max_preds_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(heatmaps), rows, hw, width, preds,
+                                                         maxvals);
+  else
+    max_preds_kernel<__nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(heatmaps), rows, hw, width, preds, maxvals);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_crop_normalize(const uint8_t* hwc, void* chw, int out_dtype, int B, int H, int W, cudaStream_t stream) {
+  const long long npix = (long long)B * H * W;
+  if (npix <= 0) return 0;
+  long long want = (npix / 4 + 255) / 256;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  if (out_dtype == DT_F32)
+    crop_normalize_kernel<float><<<blocks, 256, 0, stream>>>(hwc, static_cast<float*>(chw), npix, H * W);
+  else
+    crop_normalize_kernel<__nv_bfloat16>
+        <<<blocks, 256, 0, stream>>>(hwc, static_cast<__nv_bfloat16*>(chw), npix, H * W);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hgr

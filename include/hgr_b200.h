@@ -1,0 +1,154 @@
+/*
+ * hgr_b200 - C ABI of the B200-native MultiTaskNet forward path.
+ *
+ * The reference (yingkunwu/hand-gesture-recognition) is pure Python: there is
+ * no FFI in it to bind against.  The boundary this library sits behind is the
+ * Python class model.multitasknet.MultiTaskNet (reference
+ * model/multitasknet.py:8-29) plus libs.utils.get_max_preds (libs/utils.py:4-32)
+ * and the crop normalisation of detect.py:106-112.  The host-side mirror of
+ * those interfaces lives in hand-gesture-recognition_b200/hgr_b200/ and calls
+ * the entry points below through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer, h_* a HOST pointer;
+ *   - the caller owns every buffer; nothing here allocates device memory
+ *     except hgr_forward_host's internal staging (allocated once per plan);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *     unless stated otherwise;
+ *   - return 0 on success, negative on error; hgr_last_error() describes the
+ *     last failure of the calling thread;
+ *   - dtype codes: HGR_F32 = 0, HGR_BF16 = 1;
+ *   - activations between kernels are NHWC bf16; module inputs are NCHW
+ *     (fp32 or bf16) and module outputs NCHW / row-major like the reference's.
+ */
+#ifndef HGR_B200_H_
+#define HGR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HGR_API __attribute__((visibility("default")))
+#else
+#define HGR_API
+#endif
+
+#define HGR_F32 0
+#define HGR_BF16 1
+
+#define HGR_ACT_NONE 0
+#define HGR_ACT_SILU 1
+#define HGR_ACT_GELU 2
+
+HGR_API int hgr_version(void);
+HGR_API const char* hgr_last_error(void);
+
+/* ------------------------------------------------------------------------
+ * Whole-network plan: MultiTaskNet(num_joints, num_classes, [S, S]).forward
+ * (reference model/multitasknet.py:24-29).
+ * ---------------------------------------------------------------------- */
+typedef struct hgr_plan hgr_plan_t;
+
+/* Packed-parameter block: BN-folded bf16 weights in [Cout][tap][Cin] order,
+ * fp32 scale/shift/bias vectors, the bf16 sin-cos position table.  The layout
+ * is owned by the library; the host packs a state_dict into it entry by entry. */
+HGR_API int hgr_param_count(int image_size, int num_joints, int num_classes);
+/* Entry i: name (e.g. "encoder.cspelan1.cv2.0.cv1.w"), byte offset, byte size,
+ * dtype code and up to 3 dims (unused dims = 1). */
+HGR_API int hgr_param_info(int image_size, int num_joints, int num_classes, int index, const char** name, size_t* offset,
+                   size_t* nbytes, int* dtype, int64_t dims[3]);
+HGR_API size_t hgr_param_bytes(int image_size, int num_joints, int num_classes);
+
+HGR_API size_t hgr_workspace_bytes(int image_size, int batch);
+
+/* Binds a plan to a packed-parameter block and a workspace (both device
+ * memory, 1024-byte aligned, owned by the caller, alive as long as the plan). */
+HGR_API int hgr_plan_create(hgr_plan_t** out, int image_size, int num_joints, int num_classes, int batch, void* d_params,
+                    void* d_workspace, size_t workspace_bytes);
+HGR_API void hgr_plan_destroy(hgr_plan_t* plan);
+
+/* forward(x) -> (class logits, pose heatmaps, last-layer attention).
+ *   d_x        (B, 3, S, S) NCHW, x_dtype
+ *   d_logits   (B, num_classes)            out_dtype
+ *   d_heatmaps (B, num_joints, S/4, S/4)   out_dtype
+ *   d_attn     (B, 8, T, T) out_dtype or NULL to skip materialising it
+ *   batch      <= the plan's batch */
+HGR_API int hgr_forward(hgr_plan_t* plan, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                void* d_attn, int out_dtype, void* stream);
+
+/* Same call with HOST buffers: pinned or pageable input is copied to the
+ * device, the forward runs, logits and heatmaps are copied back; returns after
+ * the results are in host memory.  This is the end-to-end path bench.py times. */
+HGR_API int hgr_forward_host(hgr_plan_t* plan, const void* h_x, int x_dtype, int batch, void* h_logits, void* h_heatmaps,
+                     int out_dtype, void* stream);
+
+/* Device address and NHWC dims of a named intermediate ("a1", "a2", "g1",
+ * "o1", "d1", "g2", "o2", "d2", "g3", "o3", "tokens", "qkv", ...), for the
+ * per-stage parity tests.  dims = (N, H, W, C). */
+HGR_API int hgr_plan_buffer(hgr_plan_t* plan, const char* name, void** d_ptr, int64_t dims[4]);
+
+/* Number of kernel launches one hgr_forward issues (for bench.py's gpu_launches). */
+HGR_API int hgr_plan_launches(hgr_plan_t* plan, int with_attn);
+
+/* ------------------------------------------------------------------------
+ * Single operators (the building blocks the plan chains; exported so the
+ * parity tests can exercise every kernel against the oracle in isolation).
+ * ---------------------------------------------------------------------- */
+
+/* Conv(c1, c2, k, s) + folded BatchNorm + activation (+ residual before the
+ * activation) - reference model/gelan.py:18-56 and ResBasicBlock :78-87.
+ *   d_in   NHWC bf16 (B, H, W, in_ctot); channels [in_coff, in_coff+cin) are read
+ *   d_w    bf16 [cout][k*k][cin]
+ *   d_out  NHWC bf16 (B, H/s, W/s, out_ctot); channels [out_coff, out_coff+cout) written
+ *   d_res  NHWC bf16 (B, H/s, W/s, res_ctot) or NULL; channels [res_coff, ..+cout)
+ * k in {1, 3}; s in {1, 2} (s = 2 needs k = 3, even H and W); cin % 64 == 0;
+ * cout % 64 == 0. */
+HGR_API int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, int in_coff, int cin, const void* d_w,
+                    const float* d_scale, const float* d_shift, int k, int s, int act, const void* d_res,
+                    int res_ctot, int res_coff, void* d_out, int out_ctot, int out_coff, int cout, void* stream);
+
+/* y = act(x W^T + bias) (+ residual): nn.Linear of the ViT
+ * (reference model/transformer.py:34,37,65,75).  x (rows, cin) bf16,
+ * W (cout, cin) bf16, y (rows, cout) bf16. */
+HGR_API int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_bias, int act,
+               const void* d_res, void* d_y, int cout, void* stream);
+
+/* encoder.conv1: NCHW (fp32|bf16) -> NHWC bf16 (B, S/2, S/2, 64).
+ * d_w bf16 [64][32] (k = (kh*3+kw)*3+c, BN scale folded, zero padded). */
+HGR_API int hgr_conv1(const void* d_x, int x_dtype, int B, int S, const void* d_w, const float* d_shift, void* d_out,
+              void* stream);
+
+/* nn.LayerNorm(256), eps 1e-5: (rows, 256) bf16 -> bf16. */
+HGR_API int hgr_layernorm(const void* d_x, void* d_y, const float* d_gamma, const float* d_beta, long long rows, void* stream);
+
+/* softmax(q k^T / sqrt(32)) v over 8 heads of 32: d_qkv (B, T, 768) bf16 ->
+ * d_out (B, T, 256) bf16; d_probs (B, 8, T, T) probs_dtype or NULL. */
+HGR_API int hgr_attention(const void* d_qkv, void* d_out, void* d_probs, int probs_dtype, int B, int T, void* stream);
+
+/* mlp_head: Linear(256, C)(LayerNorm(tokens[:, 0])). */
+HGR_API int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
+                 const float* d_bias, void* d_logits, int out_dtype, int B, int T, int num_classes, void* stream);
+
+/* bilinear x4 (align_corners) + ReLU + 1x1 conv + bias on tokens[:, 1:]:
+ * d_tokens (B, F*F+1, 256) bf16, d_w bf16 [J][256] -> (B, J, 4F, 4F). */
+HGR_API int hgr_pose_head(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps, int out_dtype, int B,
+                  int F, int J, void* stream);
+
+/* libs.utils.get_max_preds (reference libs/utils.py:4-32):
+ * heatmaps (B, J, H, W) -> preds (B, J, 2) fp32 [x, y], maxvals (B, J, 1) fp32. */
+HGR_API int hgr_get_max_preds(const void* d_heatmaps, int dtype, int B, int J, int H, int W, float* d_preds,
+                      float* d_maxvals, void* stream);
+
+/* detect.py:106-112: (B, H, W, 3) uint8 -> (B, 3, H, W) out_dtype,
+ * ((v / 255) - mean[c]) / std[c], ImageNet constants by channel index. */
+HGR_API int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HGR_B200_H_ */
