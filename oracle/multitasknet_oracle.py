@@ -1,0 +1,254 @@
+"""ORACLE - test infrastructure, not product code.
+
+A plain fp32 restatement of the reference's MultiTaskNet forward pass and of the
+two host helpers around it, written as pure functions over a state_dict so that
+it can run where /root/reference does not exist (the GPU box).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs
+may import this module; the product path (hgr_b200) never does.
+
+Parity pin: tests/golden/*.npz were produced by running the REAL reference
+(imported from /root/reference by tests/golden/make_golden.py) on seeded
+weights and inputs; tests/test_oracle.py checks this restatement against those
+vectors (fp32 tolerance), and the CUDA path is then checked against this
+restatement (bf16 tolerance).  Arithmetic lives in torch.nn.functional, the
+same ATen operators the reference dispatches to.
+
+Every function cites the reference file:line it restates.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, model/gelan.py:46
+LN_EPS = 1e-5  # nn.LayerNorm default, model/transformer.py:33,63,114
+HEADS, HEAD_DIM, DEPTH = 8, 32, 4  # model/multitasknet.py:14-22
+
+
+# --------------------------------------------------------------------------
+# GELAN backbone
+# --------------------------------------------------------------------------
+def conv_bn_act(sd, prefix, x, k, s, act=True):
+    """Conv.forward: act(bn(conv(x))), conv bias-free, padding k//2 (model/gelan.py:5-15, 37-56); eval-mode BN."""
+    y = F.conv2d(x, sd[prefix + ".conv.weight"], None, stride=s, padding=k // 2)
+    y = F.batch_norm(y, sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"], sd[prefix + ".bn.weight"],
+                     sd[prefix + ".bn.bias"], training=False, eps=BN_EPS)
+    return F.silu(y) if act else y
+
+
+def res_basic_block(sd, prefix, x):
+    """ResBasicBlock.forward with c1 == c2 (no downsample): SiLU(x + cv2(cv1(x))) (model/gelan.py:78-87)."""
+    y = conv_bn_act(sd, prefix + ".cv1", x, 3, 1, act=True)
+    y = conv_bn_act(sd, prefix + ".cv2", y, 3, 1, act=False)
+    return F.silu(x + y)
+
+
+def gelan_block(sd, prefix, x):
+    """GELANBlock.forward: cv1 -> chunk(2) -> cv2 -> cv3 -> cat(4) -> cv4 (model/gelan.py:137-142)."""
+    y = list(conv_bn_act(sd, prefix + ".cv1", x, 1, 1).chunk(2, 1))
+    y.append(res_basic_block(sd, prefix + ".cv2.0", y[-1]))
+    y.append(res_basic_block(sd, prefix + ".cv3.0", y[-1]))
+    return conv_bn_act(sd, prefix + ".cv4", torch.cat(y, 1), 1, 1)
+
+
+def gelan_net(sd, x, taps=None):
+    """GELANNet('small').forward (model/gelan.py:165-176); `taps` collects per-stage outputs (NCHW)."""
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+    x = tap("a1", conv_bn_act(sd, "encoder.conv1", x, 3, 2))
+    x = tap("a2", conv_bn_act(sd, "encoder.conv2", x, 3, 2))
+    x = tap("o1", gelan_block(sd, "encoder.cspelan1", x))
+    x = tap("d1", conv_bn_act(sd, "encoder.down1", x, 3, 2))
+    x = tap("o2", gelan_block(sd, "encoder.cspelan2", x))
+    x = tap("d2", conv_bn_act(sd, "encoder.down2", x, 3, 2))
+    x = tap("o3", gelan_block(sd, "encoder.cspelan3", x))
+    return x
+
+
+# --------------------------------------------------------------------------
+# ViT
+# --------------------------------------------------------------------------
+def pos_emb_sincos_2d(h, w, dim, temperature=10000.0):
+    """model/transformer.py:9-26, including its raw-integer exponent (omega = 1 / temperature**k)."""
+    y, x = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    omega = 1.0 / (temperature ** torch.arange(dim // 4, dtype=torch.float32))
+    y = y.flatten()[:, None] * omega[None, :]
+    x = x.flatten()[:, None] * omega[None, :]
+    return torch.cat((x.sin(), x.cos(), y.sin(), y.cos()), dim=1).type(torch.float32)
+
+
+def attention(sd, prefix, x):
+    """Attention.forward (model/transformer.py:62-77): pre-norm, bias-free qkv/out, softmax(q k^T d^-0.5) v."""
+    b, n, _ = x.shape
+    xn = F.layer_norm(x, (x.shape[-1],), sd[prefix + ".norm.weight"], sd[prefix + ".norm.bias"], LN_EPS)
+    q, k, v = F.linear(xn, sd[prefix + ".to_qkv.weight"]).chunk(3, dim=-1)
+    split = lambda t: t.reshape(b, n, HEADS, HEAD_DIM).permute(0, 2, 1, 3)  # 'b n (h d) -> b h n d'
+    q, k, v = split(q), split(k), split(v)
+    attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * HEAD_DIM ** -0.5, dim=-1)
+    out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(b, n, HEADS * HEAD_DIM)  # 'b h n d -> b n (h d)'
+    return F.linear(out, sd[prefix + ".to_out.weight"]), attn
+
+
+def feed_forward(sd, prefix, x):
+    """FeedForward.forward (model/transformer.py:32-42): LN -> Linear -> GELU(erf) -> Linear; dropout p=0."""
+    y = F.layer_norm(x, (x.shape[-1],), sd[prefix + ".net.0.weight"], sd[prefix + ".net.0.bias"], LN_EPS)
+    y = F.gelu(F.linear(y, sd[prefix + ".net.1.weight"], sd[prefix + ".net.1.bias"]))
+    return F.linear(y, sd[prefix + ".net.4.weight"], sd[prefix + ".net.4.bias"])
+
+
+def vit(sd, feat, taps=None):
+    """ViT.forward (model/transformer.py:129-152) on the projected feature map (B, 256, F, F)."""
+    b, c, h, w = feat.shape
+    x = feat.permute(0, 2, 3, 1).reshape(b, h * w, c)  # 'b c h w -> b (h w) c'
+    x = x + pos_emb_sincos_2d(h, w, c).to(x.device)
+    x = torch.cat([sd["decoder.cls_token"].expand(b, -1, -1), x], dim=1)
+    if taps is not None:
+        taps["tokens_in"] = x
+    attn = None
+    for l in range(DEPTH):  # Transformer.forward, :90-96
+        p = f"decoder.transformer.layers.{l}"
+        msg, attn = attention(sd, p + ".0", x)
+        x = msg + x
+        x = feed_forward(sd, p + ".1", x) + x
+        if taps is not None:
+            taps[f"tokens_l{l}"] = x
+    cls_feat, hmap_feat = x[:, 0], x[:, 1:]
+    cls_out = F.linear(F.layer_norm(cls_feat, (c,), sd["decoder.mlp_head.0.weight"], sd["decoder.mlp_head.0.bias"],
+                                    LN_EPS), sd["decoder.mlp_head.1.weight"], sd["decoder.mlp_head.1.bias"])
+    hmap_feat = hmap_feat.reshape(b, h, w, c).permute(0, 3, 1, 2)  # 'b (h w) c -> b c h w'
+    hmap_feat = F.interpolate(hmap_feat, scale_factor=(4, 4), mode="bilinear", align_corners=True)
+    hmap_out = F.conv2d(F.relu(hmap_feat), sd["decoder.simple_decoder.1.weight"], sd["decoder.simple_decoder.1.bias"])
+    return cls_out, hmap_out, attn
+
+
+def multitasknet_forward(sd, x, taps=None):
+    """MultiTaskNet.forward (model/multitasknet.py:24-29) in eval mode, fp32. Returns (cls, hmap, attn)."""
+    sd = {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+    with torch.no_grad():
+        feat = gelan_net(sd, x.float(), taps)
+        feat = F.conv2d(feat, sd["proj.weight"])  # proj, :13,26
+        if taps is not None:
+            taps["proj"] = feat
+        return vit(sd, feat, taps)
+
+
+# --------------------------------------------------------------------------
+# host helpers around the model
+# --------------------------------------------------------------------------
+def get_max_preds(batch_heatmaps):
+    """libs/utils.py:4-32 restated with the same numpy calls (argmax/amax, float32 mod/floor, mask)."""
+    assert isinstance(batch_heatmaps, np.ndarray), "batch_heatmaps should be numpy.ndarray"
+    assert batch_heatmaps.ndim == 4, "batch_images should be 4-ndim"
+    b, j, _, width = batch_heatmaps.shape
+    flat = batch_heatmaps.reshape((b, j, -1))
+    idx = np.argmax(flat, 2).reshape((b, j, 1))
+    maxvals = np.amax(flat, 2).reshape((b, j, 1))
+    preds = np.tile(idx, (1, 1, 2)).astype(np.float32)
+    preds[:, :, 0] = preds[:, :, 0] % width
+    preds[:, :, 1] = np.floor(preds[:, :, 1] / width)
+    mask = np.tile(np.greater(maxvals, 0.0), (1, 1, 2)).astype(np.float32)
+    preds *= mask
+    return preds, maxvals
+
+
+def crop_normalize(img_hwc_u8):
+    """detect.py:106-112: HWC uint8 -> (1, 3, H, W) float32, /255 then ImageNet mean/std by channel index."""
+    im = img_hwc_u8.transpose((2, 0, 1)).astype(np.float32)
+    im /= 255
+    mean = np.array([0.485, 0.456, 0.406], dtype=np.float32)
+    std = np.array([0.229, 0.224, 0.225], dtype=np.float32)
+    im = (im - mean.reshape(3, 1, 1)) / std.reshape(3, 1, 1)
+    return np.ascontiguousarray(np.expand_dims(im, 0))
+
+
+# --------------------------------------------------------------------------
+# seeded weight recipes (no module construction needed)
+# --------------------------------------------------------------------------
+def state_dict_spec(num_joints=21, num_classes=19):
+    """[(key, shape)] of the reference's 180 state_dict entries, in its own order."""
+    spec = []
+
+    def conv(p, c1, c2, k):
+        spec.extend([(p + ".conv.weight", (c2, c1, k, k)), (p + ".bn.weight", (c2,)), (p + ".bn.bias", (c2,)),
+                     (p + ".bn.running_mean", (c2,)), (p + ".bn.running_var", (c2,)),
+                     (p + ".bn.num_batches_tracked", ())])
+
+    def block(p, cin, cout, h1, h2):
+        conv(p + ".cv1", cin, h1, 1)
+        conv(p + ".cv2.0.cv1", h1 // 2, h2, 3)
+        conv(p + ".cv2.0.cv2", h2, h2, 3)
+        conv(p + ".cv3.0.cv1", h2, h2, 3)
+        conv(p + ".cv3.0.cv2", h2, h2, 3)
+        conv(p + ".cv4", h1 + 2 * h2, cout, 1)
+
+    conv("encoder.conv1", 3, 64, 3)
+    conv("encoder.conv2", 64, 128, 3)
+    block("encoder.cspelan1", 128, 128, 128, 64)
+    conv("encoder.down1", 128, 256, 3)
+    block("encoder.cspelan2", 256, 256, 256, 128)
+    conv("encoder.down2", 256, 512, 3)
+    block("encoder.cspelan3", 512, 512, 512, 256)
+    spec.append(("proj.weight", (256, 512, 1, 1)))
+    spec.append(("decoder.cls_token", (1, 1, 256)))
+    for l in range(DEPTH):
+        a, f = f"decoder.transformer.layers.{l}.0", f"decoder.transformer.layers.{l}.1.net"
+        spec.extend([(a + ".norm.weight", (256,)), (a + ".norm.bias", (256,)), (a + ".to_qkv.weight", (768, 256)),
+                     (a + ".to_out.weight", (256, 256)), (f + ".0.weight", (256,)), (f + ".0.bias", (256,)),
+                     (f + ".1.weight", (256, 256)), (f + ".1.bias", (256,)), (f + ".4.weight", (256, 256)),
+                     (f + ".4.bias", (256,))])
+    spec.extend([("decoder.mlp_head.0.weight", (256,)), ("decoder.mlp_head.0.bias", (256,)),
+                 ("decoder.mlp_head.1.weight", (num_classes, 256)), ("decoder.mlp_head.1.bias", (num_classes,)),
+                 ("decoder.simple_decoder.1.weight", (num_joints, 256, 1, 1)),
+                 ("decoder.simple_decoder.1.bias", (num_joints,))])
+    return spec
+
+
+def synthetic_state_dict(seed=0, num_joints=21, num_classes=19, gain=1.0):
+    """'Trained-like' seeded weights that keep every stage's activations O(1).
+
+    With PyTorch's default init the backbone shrinks the signal ~10x per stage
+    and every image yields the same outputs (degeneracy warning),
+    so parity on default-init weights would not exercise the backbone at all.
+    This recipe draws conv / linear weights ~ N(0, gain^2 * 2 / fan_in), BN
+    gamma ~ U(0.5, 1.5), beta ~ N(0, 0.2), running_mean ~ N(0, 0.2),
+    running_var ~ U(0.5, 1.5), LayerNorm gamma ~ U(0.5, 1.5), beta ~ N(0, 0.1):
+    every BN statistic differs, so a folding mix-up is visible.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in state_dict_spec(num_joints, num_classes):
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(100, dtype=torch.int64)
+        elif key.endswith("running_var"):
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        elif key.endswith("running_mean"):
+            sd[key] = torch.randn(shape, generator=g) * 0.2
+        elif ".bn.weight" in key or "norm.weight" in key or key.endswith("net.0.weight") \
+                or key == "decoder.mlp_head.0.weight":
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        elif ".bn.bias" in key:
+            sd[key] = torch.randn(shape, generator=g) * 0.2
+        elif key.endswith("bias"):
+            sd[key] = torch.randn(shape, generator=g) * 0.1
+        elif key == "decoder.cls_token":
+            sd[key] = torch.randn(shape, generator=g)
+        else:  # conv / linear weight
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            sd[key] = torch.randn(shape, generator=g) * (gain * (2.0 / fan_in) ** 0.5)
+    return sd
+
+
+def synthetic_images(batch, size, seed=1):
+    """Low-frequency random fields with per-sample contrast and offset, roughly normalised-image statistics."""
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.randn(batch, 3, size // 8, size // 8, generator=g)
+    x = F.interpolate(coarse, size=(size, size), mode="bilinear", align_corners=False)
+    x = x + 0.3 * torch.randn(batch, 3, size, size, generator=g)
+    contrast = 0.5 + torch.rand(batch, 1, 1, 1, generator=g)
+    offset = 0.5 * torch.randn(batch, 1, 1, 1, generator=g)
+    return (x * contrast + offset).contiguous()

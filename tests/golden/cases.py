@@ -1,0 +1,33 @@
+"""Seeded inputs shared by make_golden.py (which runs the reference on them) and the tests."""
+import numpy as np
+
+
+def heatmap_cases():
+    """Crafted get_max_preds inputs: ties, all-negative, zeros, NaN, +-inf, 48x48, 64x64, non-square."""
+    rng = np.random.default_rng(0)
+    maps = rng.standard_normal((3, 21, 48, 48)).astype(np.float32)
+    maps[0, 0] = -np.abs(maps[0, 0])            # all negative -> (0, 0)
+    maps[0, 1] = 0.0                            # all zero -> (0, 0), maxval 0
+    maps[0, 2] = 0.25                           # all tied positive -> index 0
+    maps[0, 3, 10, 7] = 9.0
+    maps[0, 3, 30, 40] = 9.0                    # two-way tie -> first
+    maps[0, 4, 5, 5] = np.nan                   # NaN wins, masked to (0, 0)
+    maps[0, 5, 47, 47] = 100.0                  # last element
+    maps[0, 6, 0, 0] = 100.0                    # first element
+    maps[0, 7] = -0.0
+    maps[0, 8, 3, 3] = np.inf
+    maps[0, 9] = -np.inf
+    maps[0, 10, 1, 1] = np.nan
+    maps[0, 10, 40, 2] = np.nan                 # two NaNs -> first
+    maps64 = rng.standard_normal((2, 21, 64, 64)).astype(np.float32)
+    maps64[1, 0, 63, 0] = 50.0
+    rect = rng.standard_normal((2, 3, 5, 9)).astype(np.float32)   # non-square, odd sizes
+    return {"maps48": maps, "maps64": maps64, "rect": rect}
+
+
+def crop_image():
+    """(16, 16, 3) uint8 holding every byte value in every channel."""
+    img = np.stack([np.arange(256, dtype=np.uint8).reshape(16, 16)] * 3, axis=-1)
+    img[..., 1] = img[..., 1][::-1]
+    img[..., 2] = np.roll(img[..., 2], 7)
+    return img

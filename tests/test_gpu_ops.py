@@ -1,0 +1,259 @@
+"""Per-kernel parity against the oracle's operators, through the C ABI.
+
+Inputs and weights are rounded to bf16 first, so the oracle (fp32 on those
+rounded values) and the kernels (bf16 operands, fp32 accumulation, one bf16
+rounding of the output) differ only by accumulation order, the activation's
+approximation and the final rounding.  Stated tolerance for bf16 outputs:
+rel-L2 <= 4e-3 and max-abs <= 2^-7 * max|ref| (two bf16 ulps at the top of the
+range); fp32 outputs of the heads: rel-L2 <= 2e-3.
+"""
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import bf16_round, nchw_f32, nhwc_bf16, report
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 4e-3
+MAX_TOL = 2.0 ** -7
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hgr_b200 import _lib
+    return _lib.load()
+
+
+def _chk(rc, what):
+    from hgr_b200 import _lib
+    _lib.check(rc, what)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _act(v, act):
+    return F.silu(v) if act == 1 else (F.gelu(v) if act == 2 else v)
+
+
+def run_conv(lib, x, w, scale, shift, k, s, act, res=None, in_pad=(0, 0), out_pad=(0, 0), res_pad=(0, 0)):
+    """x NCHW fp32 (already bf16-rounded) on CPU.  *_pad = (channels before, channels after) of garbage
+    around the slice inside its NHWC buffer, to exercise the concat-slice addressing."""
+    dev = torch.device("cuda")
+    b, cin, h, wd = x.shape
+    cout = w.shape[0]
+
+    def embed(t, pad):
+        full = torch.randn(t.shape[0], pad[0] + t.shape[1] + pad[1], t.shape[2], t.shape[3])
+        full[:, pad[0]: pad[0] + t.shape[1]] = t
+        return nhwc_bf16(full, dev)
+
+    xin = embed(x, in_pad)
+    ho, wo = h // s, wd // s
+    out_ctot = out_pad[0] + cout + out_pad[1]
+    out = torch.full((b, ho, wo, out_ctot), 7.0, dtype=torch.bfloat16, device=dev)
+    wp = w.permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    sc = None if scale is None else scale.to(dev).float().contiguous()
+    sh = None if shift is None else shift.to(dev).float().contiguous()
+    rbuf = None if res is None else embed(res, res_pad)
+    _chk(lib.hgr_conv_bn_act(xin.data_ptr(), b, h, wd, xin.shape[-1], in_pad[0], cin, wp.data_ptr(), _ptr(sc), _ptr(sh),
+                             k, s, act, _ptr(rbuf), 0 if res is None else rbuf.shape[-1], res_pad[0], out.data_ptr(),
+                             out_ctot, out_pad[0], cout, _stream()), "hgr_conv_bn_act")
+    torch.cuda.synchronize()
+    got = nchw_f32(out)
+    # untouched channels must still hold the fill value
+    if out_pad[0]:
+        assert torch.all(got[:, : out_pad[0]] == 7.0)
+    if out_pad[1]:
+        assert torch.all(got[:, out_pad[0] + cout:] == 7.0)
+    y = F.conv2d(x, bf16_round(w), None, stride=s, padding=k // 2)
+    if scale is not None:
+        y = y * scale.view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res
+    return got[:, out_pad[0]: out_pad[0] + cout], _act(y, act)
+
+
+CONV_CASES = [
+    # name, B, H, cin, cout, k, s, act, res, in_pad, out_pad
+    ("1x1_128_128_48", 2, 48, 128, 128, 1, 1, 1, False, (0, 0), (0, 128)),
+    ("3x3_64_64_48_slice_res", 2, 48, 64, 64, 3, 1, 1, True, (64, 128), (128, 64)),
+    ("3x3_128_128_24_ragged_batch", 3, 24, 128, 128, 3, 1, 1, True, (128, 256), (256, 128)),
+    ("3x3_256_256_12_ragged_batch", 5, 12, 256, 256, 3, 1, 1, False, (0, 0), (0, 0)),
+    ("1x1_1024_512_12", 9, 12, 1024, 512, 1, 1, 1, False, (0, 0), (0, 0)),
+    ("3x3s2_64_128_96", 2, 96, 64, 128, 3, 2, 1, False, (0, 0), (0, 0)),
+    ("3x3s2_128_256_48", 3, 48, 128, 256, 3, 2, 1, False, (0, 0), (0, 0)),
+    ("3x3s2_256_512_24", 9, 24, 256, 512, 3, 2, 1, False, (0, 0), (0, 0)),
+    ("3x3_64_64_64_noact", 1, 64, 64, 64, 3, 1, 0, False, (0, 0), (0, 0)),
+    ("3x3_128_128_32", 2, 32, 128, 128, 3, 1, 1, True, (0, 0), (0, 0)),
+    ("3x3_256_256_16", 3, 16, 256, 256, 3, 1, 1, True, (0, 0), (0, 0)),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_bn_act(lib, case):
+    name, b, h, cin, cout, k, s, act, use_res, in_pad, out_pad = case
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    x = bf16_round(torch.randn(b, cin, h, h, generator=g))
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.3
+    res = bf16_round(torch.randn(b, cout, h // s, h // s, generator=g)) if use_res else None
+    got, ref = run_conv(lib, x, w, scale, shift, k, s, act, res, in_pad, out_pad, res_pad=(64, 0))
+    r, m = report("conv " + name, got, ref)
+    assert r <= REL_TOL and m <= MAX_TOL
+
+
+LINEAR_CASES = [
+    ("qkv_300", 300, 256, 768, 0, False, False),
+    ("out_res_1160", 1160, 256, 256, 0, False, True),
+    ("ff1_gelu_bias_77", 77, 256, 256, 2, True, False),
+    ("ff2_bias_res_4096", 4096, 256, 256, 0, True, True),
+    ("wide_k_512_129", 129, 512, 256, 0, True, False),
+]
+
+
+@pytest.mark.parametrize("case", LINEAR_CASES, ids=[c[0] for c in LINEAR_CASES])
+def test_linear(lib, case):
+    name, rows, cin, cout, act, use_bias, use_res = case
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    x = bf16_round(torch.randn(rows, cin, generator=g))
+    w = bf16_round(torch.randn(cout, cin, generator=g) * cin ** -0.5)
+    bias = torch.randn(cout, generator=g) * 0.2 if use_bias else None
+    res = bf16_round(torch.randn(rows, cout, generator=g)) if use_res else None
+    xd, wd = x.to(dev, torch.bfloat16), w.to(dev, torch.bfloat16)
+    bd = None if bias is None else bias.to(dev)
+    rd = None if res is None else res.to(dev, torch.bfloat16)
+    y = torch.full((rows, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_linear(xd.data_ptr(), rows, cin, wd.data_ptr(), _ptr(bd), act, _ptr(rd), y.data_ptr(), cout,
+                        _stream()), "hgr_linear")
+    torch.cuda.synchronize()
+    ref = F.linear(x, w, bias)
+    if res is not None:
+        ref = ref + res
+    ref = _act(ref, act)
+    r, m = report("linear " + name, y, ref)
+    assert r <= REL_TOL and m <= MAX_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("size", [64, 192])
+def test_conv1(lib, dtype, size):
+    from hgr_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(size)
+    b = 3
+    x = torch.randn(b, 3, size, size, generator=g)
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    w = torch.randn(64, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    scale = torch.rand(64, generator=g) + 0.5
+    shift = torch.randn(64, generator=g) * 0.3
+    wk = torch.zeros(64, 32)
+    wk[:, :27] = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 27)
+    wk = wk.to(dev, torch.bfloat16)
+    out = torch.full((b, size // 2, size // 2, 64), 7.0, dtype=torch.bfloat16, device=dev)
+    xd = x.to(dev, dtype).contiguous()
+    shd = shift.to(dev)
+    _chk(lib.hgr_conv1(xd.data_ptr(), _lib.F32 if dtype == torch.float32 else _lib.BF16, b, size, wk.data_ptr(),
+                       shd.data_ptr(), out.data_ptr(), _stream()), "hgr_conv1")
+    torch.cuda.synchronize()
+    wref = wk.float().cpu()[:, :27].reshape(64, 3, 3, 3).permute(0, 3, 1, 2)  # the bf16-rounded folded weights
+    ref = F.silu(F.conv2d(bf16_round(x), wref, None, stride=2, padding=1) + shift.view(1, -1, 1, 1))
+    r, m = report(f"conv1 {size} {dtype}", nchw_f32(out), ref)
+    assert r <= REL_TOL and m <= MAX_TOL
+
+
+def test_layernorm(lib):
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    rows = 1237
+    x = bf16_round(torch.randn(rows, 256, generator=g) * 3 + 0.5)
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    xd = x.to(dev, torch.bfloat16)
+    y = torch.empty_like(xd)
+    gd, bd = gamma.to(dev), beta.to(dev)
+    _chk(lib.hgr_layernorm(xd.data_ptr(), y.data_ptr(), gd.data_ptr(), bd.data_ptr(), rows, _stream()), "hgr_layernorm")
+    torch.cuda.synchronize()
+    r, m = report("layernorm", y, F.layer_norm(x, (256,), gamma, beta, 1e-5))
+    assert r <= REL_TOL and m <= MAX_TOL
+
+
+@pytest.mark.parametrize("tokens", [145, 257, 17])
+@pytest.mark.parametrize("probs", [None, torch.float32, torch.bfloat16], ids=["noprobs", "p32", "pbf16"])
+def test_attention(lib, tokens, probs):
+    from hgr_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(tokens)
+    b = 3
+    qkv = bf16_round(torch.randn(b, tokens, 768, generator=g) * 1.5)
+    qd = qkv.to(dev, torch.bfloat16)
+    out = torch.full((b, tokens, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    pd = None if probs is None else torch.full((b, 8, tokens, tokens), 7.0, dtype=probs, device=dev)
+    _chk(lib.hgr_attention(qd.data_ptr(), out.data_ptr(), _ptr(pd), _lib.BF16 if probs == torch.bfloat16 else _lib.F32,
+                           b, tokens, _stream()), "hgr_attention")
+    torch.cuda.synchronize()
+    q, k, v = qkv.chunk(3, dim=-1)
+    sp = lambda t: t.reshape(b, tokens, 8, 32).permute(0, 2, 1, 3)
+    attn = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) * 32 ** -0.5, dim=-1)
+    ref = (attn @ sp(v)).permute(0, 2, 1, 3).reshape(b, tokens, 256)
+    r, m = report(f"attention T={tokens}", out, ref)
+    assert r <= 6e-3 and m <= 2 * MAX_TOL  # P is rounded to bf16 before P.V, like the reference's bf16 path
+    if pd is not None:
+        r2, m2 = report(f"attention probs T={tokens} {probs}", pd, attn)
+        assert r2 <= (REL_TOL if probs == torch.bfloat16 else 1e-4) and m2 <= MAX_TOL
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_cls_head(lib, out_dtype):
+    from hgr_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    b, t, c = 13, 145, 19
+    tok = bf16_round(torch.randn(b, t, 256, generator=g) * 2)
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    w, bias = torch.randn(c, 256, generator=g) * 0.1, torch.randn(c, generator=g)
+    td = tok.to(dev, torch.bfloat16)
+    out = torch.empty(b, c, dtype=out_dtype, device=dev)
+    args = [x.to(dev) for x in (gamma, beta, w, bias)]
+    _chk(lib.hgr_cls_head(td.data_ptr(), *[a.data_ptr() for a in args], out.data_ptr(),
+                          _lib.F32 if out_dtype == torch.float32 else _lib.BF16, b, t, c, _stream()), "hgr_cls_head")
+    torch.cuda.synchronize()
+    ref = F.linear(F.layer_norm(tok[:, 0], (256,), gamma, beta, 1e-5), w, bias)
+    r, m = report(f"cls_head {out_dtype}", out, ref)
+    assert r <= (1e-5 if out_dtype == torch.float32 else REL_TOL)
+
+
+@pytest.mark.parametrize("feat", [12, 16])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_pose_head(lib, feat, out_dtype):
+    from hgr_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(feat)
+    b, j = 3, 21
+    tok = bf16_round(torch.randn(b, feat * feat + 1, 256, generator=g) * 2)
+    w = bf16_round(torch.randn(j, 256, generator=g) * 0.1)
+    bias = torch.randn(j, generator=g)
+    td, wd, bd = tok.to(dev, torch.bfloat16), w.to(dev, torch.bfloat16), bias.to(dev)
+    out = torch.full((b, j, 4 * feat, 4 * feat), 7.0, dtype=out_dtype, device=dev)
+    _chk(lib.hgr_pose_head(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                           _lib.F32 if out_dtype == torch.float32 else _lib.BF16, b, feat, j, _stream()),
+         "hgr_pose_head")
+    torch.cuda.synchronize()
+    fmap = tok[:, 1:].reshape(b, feat, feat, 256).permute(0, 3, 1, 2)
+    up = F.relu(F.interpolate(fmap, scale_factor=(4, 4), mode="bilinear", align_corners=True))
+    ref = F.conv2d(bf16_round(up), w.view(j, 256, 1, 1), bias)
+    r, m = report(f"pose_head F={feat} {out_dtype}", out, ref)
+    assert r <= REL_TOL and m <= MAX_TOL

@@ -1,0 +1,156 @@
+"""Host-side logic that needs no GPU: C-ABI export, parameter layout, packing, module contract, sharding."""
+import os
+import re
+import socket
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import multitasknet_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from hgr_b200 import _lib
+    header = (ROOT / "include" / "hgr_b200.h").read_text()
+    declared = set(re.findall(r"HGR_API[^;(]*?\b(hgr_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/hgr_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes prototypes and header disagree"
+    assert lib.hgr_version() >= 100
+
+
+def test_param_layout_is_dense_and_complete():
+    from hgr_b200 import _lib, packing
+    lay = _lib.param_layout(192, 21, 19)
+    total = _lib.load().hgr_param_bytes(192, 21, 19)
+    end = 0
+    for name, off, nbytes, dt, dims in lay:
+        assert off >= end and off % 1024 == 0, name
+        assert nbytes == int(np.prod(dims)) * (4 if dt == _lib.F32 else 2), name
+        end = off + nbytes
+    assert end <= total
+    sd = O.synthetic_state_dict(0)
+    tensors = packing.packed_tensors(sd, 192, "cpu")
+    assert {l[0] for l in lay} == set(tensors)
+    block = packing.pack(sd, 192, 21, 19, torch.device("cpu"))
+    assert block.numel() == total
+    # workspace grows linearly with the batch and is non-trivial
+    w1, w8 = _lib.load().hgr_workspace_bytes(192, 1), _lib.load().hgr_workspace_bytes(192, 8)
+    assert w1 > 5_000_000 and 7.5 * w1 < w8 <= 8 * w1
+    assert _lib.load().hgr_workspace_bytes(100, 1) == 0  # unsupported size is refused
+    assert b"multiple of 64" in _lib.load().hgr_last_error()
+
+
+def test_bn_folding_and_weight_order():
+    """Packed [Cout][kh][kw][Cin] weights + scale/shift reproduce conv+BN of the oracle (fp32 on the packed values)."""
+    from hgr_b200 import packing
+    sd = O.synthetic_state_dict(3)
+    t = packing.packed_tensors(sd, 192, "cpu")
+    x = torch.randn(2, 64, 10, 10)
+    p = "encoder.cspelan1.cv2.0.cv1"
+    w = t[p + ".w"].float().permute(0, 3, 1, 2)  # back to (Cout, Cin, kh, kw)
+    y = F.conv2d(x, w, None, 1, 1) * t[p + ".scale"].view(1, -1, 1, 1) + t[p + ".shift"].view(1, -1, 1, 1)
+    sd_r = dict(sd)
+    sd_r[p + ".conv.weight"] = sd[p + ".conv.weight"].to(torch.bfloat16).float()
+    ref = O.conv_bn_act(sd_r, p, x, 3, 1, act=False)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    # conv1: scale folded into the weights, K padded 27 -> 32, k = (kh*3+kw)*3 + c
+    w1 = t["encoder.conv1.w"].float()
+    assert w1.shape == (64, 32) and torch.all(w1[:, 27:] == 0)
+    scale, shift = packing.fold_bn(sd, "encoder.conv1")
+    ref1 = (sd["encoder.conv1.conv.weight"] * scale.view(-1, 1, 1, 1))[5, 2, 1, 0]  # co=5, c=2, kh=1, kw=0
+    assert abs(float(w1[5, (1 * 3 + 0) * 3 + 2]) - float(ref1)) <= abs(float(ref1)) * 2 ** -8
+    torch.testing.assert_close(t["encoder.conv1.shift"], shift)
+    torch.testing.assert_close(packing.sincos_table(12, 12), O.pos_emb_sincos_2d(12, 12, 256))
+    assert t["decoder.pos_embedding"].shape == (144, 256)
+
+
+def test_module_tree_and_contract():
+    from hgr_b200 import MultiTaskNet
+    m = MultiTaskNet(21, 19, [192, 192])
+    sd = m.state_dict()
+    spec = O.state_dict_spec()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    for k, shape in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sd["encoder.conv1.bn.num_batches_tracked"].dtype == torch.int64
+    assert "decoder.pos_embedding" not in sd and m.decoder.pos_embedding.shape == (144, 256)
+    m.load_state_dict(O.synthetic_state_dict(1), strict=True)
+    # Lightning checkpoints prefix keys with "model." and export.py strips it (reference export.py:37-40)
+    ckpt = {"model." + k: v for k, v in sd.items()}
+    m.load_state_dict({k[len("model."):]: v for k, v in ckpt.items()}, strict=True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m.eval()(torch.zeros(1, 3, 192, 192))
+    with pytest.raises(TypeError):
+        m("not a tensor")
+    with pytest.raises(ValueError):
+        MultiTaskNet(21, 19, [192, 256])
+    with pytest.raises(RuntimeError, match="parameter container"):
+        m.encoder(torch.zeros(1, 3, 192, 192))
+    assert MultiTaskNet(21, 19, [256, 256]).decoder.pos_embedding.shape == (256, 256)
+
+
+def test_ops_refuse_cpu_inputs():
+    from hgr_b200 import crop_normalize, get_max_preds
+    with pytest.raises(RuntimeError):
+        get_max_preds(torch.zeros(1, 1, 4, 4))
+    with pytest.raises(AssertionError):
+        get_max_preds(torch.zeros(1, 4, 4))
+    with pytest.raises(RuntimeError):
+        crop_normalize(torch.zeros(4, 4, 3, dtype=torch.uint8))
+
+
+def test_shard_range_partitions_exactly():
+    from hgr_b200.sharding import shard_range
+    for total in [0, 1, 7, 8, 1024, 8192, 8191]:
+        for world in [1, 2, 3, 4, 8]:
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from hgr_b200.sharding import max_over_ranks, shard_range, sum_over_ranks
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(101, rank, world)
+    dist.barrier()
+    slowest = max_over_ranks(10.0 + rank)
+    units = sum_over_ranks(float(hi - lo))
+    q.put((rank, lo, hi, slowest, units))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo():
+    """The N>1 plumbing of bench.py (shard, barrier, max-over-ranks time, summed units) on 2 CPU ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 51), (51, 101)]
+    assert all(r[3] == 11.0 and r[4] == 101.0 for r in res)
