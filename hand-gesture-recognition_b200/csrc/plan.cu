@@ -3,6 +3,7 @@
 // MultiTaskNet.forward (reference model/multitasknet.py:24-29 ->
 // model/gelan.py:165-176 -> model/transformer.py:129-152).
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,8 @@ struct GemmOp {
   CUtensorMap a, w, o;
   GemmParams p;
   int bn;
+  double flops;  // algorithmic: 2 * M * N * K, unpadded
+  double bytes;  // algorithmic: A + W + OUT (+ RES) in bf16
 };
 
 int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
@@ -154,6 +157,9 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
     p.res_sh = (long long)res_ctot * Wo;
     p.res_sn = (long long)res_ctot * Wo * Ho;
   }
+  const double M = (double)B * Ho * Wo;
+  op.flops = 2.0 * M * cout * k * k * cin;
+  op.bytes = 2.0 * ((double)B * H * W * cin + (double)cout * k * k * cin + M * cout * (res ? 2 : 1));
   return 0;
 }
 
@@ -208,6 +214,8 @@ int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const vo
     p.res_sh = 0;
     p.res_sn = 0;
   }
+  op.flops = 2.0 * (double)rows * cin * cout;
+  op.bytes = 2.0 * ((double)rows * cin + (double)cin * cout + (double)rows * cout * (res ? 2 : 1));
   return 0;
 }
 
@@ -261,6 +269,8 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
   p.res_sw = kDim;
   p.res_sh = 0;
   p.res_sn = 0;
+  op.flops = 2.0 * (double)B * P * cin * kDim;
+  op.bytes = 2.0 * ((double)B * P * cin + (double)cin * kDim + (double)B * P * kDim + (double)P * kDim);
   return 0;
 }
 
@@ -429,6 +439,25 @@ struct hgr_plan {
   std::vector<GemmOp> convs;        // kNumConvs backbone layers
   GemmOp proj;
   GemmOp qkv[kDepth], out[kDepth], ff1[kDepth], ff2[kDepth];
+  // launch sequence of one forward pass
+  struct Io {
+    const void* x;
+    int x_dtype;
+    void* logits;
+    void* heat;
+    void* attn;
+    int out_dtype;
+  };
+  struct Step {
+    std::string name;
+    int kind;      // 0 = tcgen05 implicit GEMM, 1 = mma.sync kernel, 2 = memory-bound kernel
+    double flops;  // algorithmic
+    double bytes;  // algorithmic
+    std::function<int(cudaStream_t, const Io&)> run;
+  };
+  std::vector<Step> steps;
+  cudaEvent_t* events = nullptr;
+  int num_events = 0;
   // host-path staging
   void* d_x = nullptr;
   void* d_logits = nullptr;
@@ -607,6 +636,62 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
     delete pl;
     return rc;
   }
+  // ---- the launch sequence -------------------------------------------------
+  using Io = hgr_plan::Io;
+  auto add = [&](const std::string& name, int kind, double flops, double bytes,
+                 std::function<int(cudaStream_t, const Io&)> fn) {
+    pl->steps.push_back({name, kind, flops, bytes, std::move(fn)});
+  };
+  auto add_gemm = [&](const std::string& name, const GemmOp* op) {
+    add(name, 0, op->flops, op->bytes, [op](cudaStream_t st, const Io&) { return run_op(*op, st); });
+  };
+  const int T = pl->T;
+  const double dB = B, dS = S;
+  add("encoder.conv1", 1, 2.0 * dB * (dS / 2) * (dS / 2) * 64 * 27,
+      dB * 3 * dS * dS * 2 + dB * (dS / 2) * (dS / 2) * 64 * 2, [pl, B](cudaStream_t st, const Io& io) {
+        return launch_conv1(io.x, io.x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
+                            pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
+      });
+  for (int i = 0; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
+  add("decoder.cls_token", 2, 0, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io&) {
+    return launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"), B, T, st);
+  });
+  add_gemm("proj+pos_embedding", &pl->proj);
+  for (int l = 0; l < kDepth; ++l) {
+    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
+    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
+    const double ln_bytes = 2.0 * (double)rows * kDim * 2;
+    // Attention (transformer.py:62-77) + residual (:93)
+    add(a + "norm", 2, 0, ln_bytes, [pl, a, rows](cudaStream_t st, const Io&) {
+      return launch_layernorm(pl->bp("tokens"), pl->bp("ln"), pl->pp<float>(a + "norm.weight"),
+                              pl->pp<float>(a + "norm.bias"), rows, st);
+    });
+    add_gemm(a + "to_qkv", &pl->qkv[l]);
+    const bool last = l == kDepth - 1;
+    add(a + "attention", 1, 4.0 * dB * kHeads * T * T * 32, (double)rows * kDim * 2 * 4,
+        [pl, B, T, last](cudaStream_t st, const Io& io) {
+          return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st);
+        });
+    add_gemm(a + "to_out+residual", &pl->out[l]);
+    // FeedForward (transformer.py:32-42) + residual (:94)
+    add(f + "0", 2, 0, ln_bytes, [pl, f, rows](cudaStream_t st, const Io&) {
+      return launch_layernorm(pl->bp("tokens_b"), pl->bp("ln"), pl->pp<float>(f + "0.weight"),
+                              pl->pp<float>(f + "0.bias"), rows, st);
+    });
+    add_gemm(f + "1+gelu", &pl->ff1[l]);
+    add_gemm(f + "4+residual", &pl->ff2[l]);
+  }
+  add("decoder.mlp_head", 2, 2.0 * dB * kDim * C, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io& io) {
+    return launch_cls_head(pl->bp("tokens"), pl->pp<float>("decoder.mlp_head.0.weight"),
+                           pl->pp<float>("decoder.mlp_head.0.bias"), pl->pp<float>("decoder.mlp_head.1.weight"),
+                           pl->pp<float>("decoder.mlp_head.1.bias"), io.logits, io.out_dtype, B, T, pl->C, st);
+  });
+  add("decoder.simple_decoder", 1, 2.0 * dB * (dS / 4) * (dS / 4) * kDim * J,
+      (double)rows * kDim * 2 + dB * J * (dS / 4) * (dS / 4) * 2, [pl, B](cudaStream_t st, const Io& io) {
+        return launch_pose_head(pl->bp("tokens"), pl->pp<__nv_bfloat16>("decoder.simple_decoder.1.w"),
+                                pl->pp<float>("decoder.simple_decoder.1.bias"), io.heat, io.out_dtype, B, pl->F, pl->J,
+                                st);
+      });
   *out = pl;
   return 0;
 }
@@ -616,25 +701,38 @@ void hgr_plan_destroy(hgr_plan_t* plan) {
   if (plan->d_x) cudaFree(plan->d_x);
   if (plan->d_logits) cudaFree(plan->d_logits);
   if (plan->d_heat) cudaFree(plan->d_heat);
+  for (int i = 0; i < plan->num_events; ++i) cudaEventDestroy(plan->events[i]);
+  free(plan->events);
   delete plan;
 }
 
 int hgr_plan_launches(hgr_plan_t* plan, int with_attn) {
   (void)with_attn;
   if (!plan) return -1;
-  // conv1 + 21 convs + cls fill + proj + 4 x (ln, qkv, attn, out, ln, ff1, ff2) + cls head + pose head
-  return 1 + kNumConvs + 2 + kDepth * 7 + 2;
+  return (int)plan->steps.size();
 }
 
-int hgr_forward(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
-                void* d_attn, int out_dtype, void* stream_v) {
+int hgr_plan_launch_info(hgr_plan_t* plan, int index, const char** name, int* kind, double* flops, double* bytes) {
+  if (!plan || index < 0 || index >= (int)plan->steps.size()) {
+    set_error("launch index %d out of range", index);
+    return -1;
+  }
+  const hgr_plan::Step& s = plan->steps[index];
+  *name = s.name.c_str();
+  *kind = s.kind;
+  *flops = s.flops;
+  *bytes = s.bytes;
+  return 0;
+}
+
+static int check_forward_args(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits,
+                              void* d_heatmaps, int out_dtype) {
   if (!pl || !d_x || !d_logits || !d_heatmaps) {
     set_error("hgr_forward: null argument");
     return -1;
   }
   if (batch != pl->B) {
-    // tensor maps and tile grids are built for the plan's batch; smaller
-    // batches would need re-encoded maps, so the host mirror keeps one plan per batch size.
+    // tensor maps and tile grids are built for the plan's batch; the host mirror keeps one plan per batch size.
     set_error("hgr_forward: batch %d != plan batch %d", batch, pl->B);
     return -1;
   }
@@ -642,39 +740,42 @@ int hgr_forward(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d
     set_error("hgr_forward: bad dtype code");
     return -1;
   }
+  return 0;
+}
+
+int hgr_forward(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                void* d_attn, int out_dtype, void* stream_v) {
+  if (int rc = check_forward_args(pl, d_x, x_dtype, batch, d_logits, d_heatmaps, out_dtype)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
-  const int B = pl->B, T = pl->T;
-  const long long rows = (long long)B * T;
-  int rc = launch_conv1(d_x, x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
-                        pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
-  for (int i = 0; i < kNumConvs && !rc; ++i) rc = run_op(pl->convs[i], st);
-  if (!rc) rc = launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"), B, T, st);
-  if (!rc) rc = run_op(pl->proj, st);
-  for (int l = 0; l < kDepth && !rc; ++l) {
-    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
-    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
-    // Attention (transformer.py:62-77) + residual (:93)
-    rc = launch_layernorm(pl->bp("tokens"), pl->bp("ln"), pl->pp<float>(a + "norm.weight"),
-                          pl->pp<float>(a + "norm.bias"), rows, st);
-    if (!rc) rc = run_op(pl->qkv[l], st);
-    if (!rc)
-      rc = launch_attention(pl->bp("qkv"), pl->bp("attn_out"), l == kDepth - 1 ? d_attn : nullptr, out_dtype, B, T, st);
-    if (!rc) rc = run_op(pl->out[l], st);
-    // FeedForward (transformer.py:32-42) + residual (:94)
-    if (!rc)
-      rc = launch_layernorm(pl->bp("tokens_b"), pl->bp("ln"), pl->pp<float>(f + "0.weight"),
-                            pl->pp<float>(f + "0.bias"), rows, st);
-    if (!rc) rc = run_op(pl->ff1[l], st);
-    if (!rc) rc = run_op(pl->ff2[l], st);
+  const hgr_plan::Io io{d_x, x_dtype, d_logits, d_heatmaps, d_attn, out_dtype};
+  for (const auto& step : pl->steps)
+    if (int rc = step.run(st, io)) return rc;
+  return 0;
+}
+
+int hgr_forward_profile(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                        void* d_attn, int out_dtype, void* stream_v, float* h_ms, int capacity) {
+  if (int rc = check_forward_args(pl, d_x, x_dtype, batch, d_logits, d_heatmaps, out_dtype)) return rc;
+  const int n = (int)pl->steps.size();
+  if (!h_ms || capacity < n) {
+    set_error("hgr_forward_profile: need room for %d launch times", n);
+    return -1;
   }
-  if (!rc)
-    rc = launch_cls_head(pl->bp("tokens"), pl->pp<float>("decoder.mlp_head.0.weight"),
-                         pl->pp<float>("decoder.mlp_head.0.bias"), pl->pp<float>("decoder.mlp_head.1.weight"),
-                         pl->pp<float>("decoder.mlp_head.1.bias"), d_logits, out_dtype, B, T, pl->C, st);
-  if (!rc)
-    rc = launch_pose_head(pl->bp("tokens"), pl->pp<__nv_bfloat16>("decoder.simple_decoder.1.w"),
-                          pl->pp<float>("decoder.simple_decoder.1.bias"), d_heatmaps, out_dtype, B, pl->F, pl->J, st);
-  return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  if (pl->num_events < n + 1) {
+    pl->events = static_cast<cudaEvent_t*>(realloc(pl->events, sizeof(cudaEvent_t) * (n + 1)));
+    for (int i = pl->num_events; i < n + 1; ++i) HGR_CHECK_CUDA(cudaEventCreate(&pl->events[i]));
+    pl->num_events = n + 1;
+  }
+  const hgr_plan::Io io{d_x, x_dtype, d_logits, d_heatmaps, d_attn, out_dtype};
+  HGR_CHECK_CUDA(cudaEventRecord(pl->events[0], st));
+  for (int i = 0; i < n; ++i) {
+    if (int rc = pl->steps[i].run(st, io)) return rc;
+    HGR_CHECK_CUDA(cudaEventRecord(pl->events[i + 1], st));
+  }
+  HGR_CHECK_CUDA(cudaEventSynchronize(pl->events[n]));
+  for (int i = 0; i < n; ++i) HGR_CHECK_CUDA(cudaEventElapsedTime(&h_ms[i], pl->events[i], pl->events[i + 1]));
+  return n;
 }
 
 int hgr_forward_host(hgr_plan_t* pl, const void* h_x, int x_dtype, int batch, void* h_logits, void* h_heatmaps,

@@ -33,6 +33,9 @@ SIGNATURES = {
     "hgr_forward_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "hgr_plan_buffer": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "hgr_plan_launches": (_i, [_vp, _i]),
+    "hgr_plan_launch_info": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double)]),
+    "hgr_forward_profile": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, C.POINTER(C.c_float), _i]),
     "hgr_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _fp, _fp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i,
                              _vp]),
     "hgr_linear": (_i, [_vp, _ll, _i, _vp, _fp, _i, _vp, _vp, _i, _vp]),

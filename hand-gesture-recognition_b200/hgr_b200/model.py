@@ -141,6 +141,33 @@ class _Plan:
     def launches(self) -> int:
         return _lib.load().hgr_plan_launches(self.handle, 0)
 
+    def launch_table(self):
+        """[(layer name, kind, algorithmic flops, algorithmic bytes)] of one forward pass."""
+        lib = _lib.load()
+        out = []
+        for i in range(self.launches()):
+            name = C.c_char_p()
+            kind = C.c_int()
+            fl, by = C.c_double(), C.c_double()
+            _lib.check(lib.hgr_plan_launch_info(self.handle, i, C.byref(name), C.byref(kind), C.byref(fl),
+                                                C.byref(by)), "hgr_plan_launch_info")
+            out.append((name.value.decode(), kind.value, fl.value, by.value))
+        return out
+
+    def profile(self, x, logits, heat, attn=None):
+        """Per-launch milliseconds of one forward (CUDA events between launches)."""
+        n = self.launches()
+        ms = (C.c_float * n)()
+        dt = _lib.F32 if x.dtype == torch.float32 else _lib.BF16
+        odt = _lib.F32 if logits.dtype == torch.float32 else _lib.BF16
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib.load().hgr_forward_profile(self.handle, x.data_ptr(), dt, x.shape[0], logits.data_ptr(),
+                                             heat.data_ptr(), attn.data_ptr() if attn is not None else None, odt,
+                                             stream, ms, n)
+        if rc != n:
+            _lib.check(rc if rc < 0 else -1, "hgr_forward_profile")
+        return list(ms)
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):

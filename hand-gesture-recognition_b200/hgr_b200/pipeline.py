@@ -1,0 +1,104 @@
+"""Batched, host-facing version of the classifier stage of the reference's inference app.
+
+reference detect.py:92-117,140-155 does, per frame and per hand:
+    uint8 BGR crop -> /255, mean/std, CHW -> classifier -> argmax(label), get_max_preds(heatmap)
+This class does the same for a whole batch of crops that live in HOST memory:
+pinned uint8 crops are copied to the device, normalised (crop_normalize
+kernel), run through the MultiTaskNet plan, decoded on the device
+(get_max_preds kernel) and only the logits, keypoints and their confidences
+travel back - 19*4 + 21*3*4 bytes per hand instead of a 194 KB heatmap.
+
+Two lanes (stream + buffers + plan each) are used alternately so that the
+host->device copy of batch i+1 overlaps the kernels of batch i.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .model import MultiTaskNet, _Plan
+
+
+class _Lane:
+    def __init__(self, model: MultiTaskNet, batch: int, device, dtype):
+        s = model.image_size[0]
+        self.stream = torch.cuda.Stream(device)
+        self.plan = _Plan(s, model.num_joints, model.num_classes, batch, model._packed_params(device))
+        self.h_crops = torch.empty(batch, s, s, 3, dtype=torch.uint8).pin_memory()
+        self.d_crops = torch.empty(batch, s, s, 3, dtype=torch.uint8, device=device)
+        self.d_x = torch.empty(batch, 3, s, s, dtype=dtype, device=device)
+        self.d_logits = torch.empty(batch, model.num_classes, dtype=torch.float32, device=device)
+        self.d_heat = torch.empty(batch, model.num_joints, s // 4, s // 4, dtype=torch.float32, device=device)
+        self.d_preds = torch.empty(batch, model.num_joints, 2, dtype=torch.float32, device=device)
+        self.d_maxvals = torch.empty(batch, model.num_joints, 1, dtype=torch.float32, device=device)
+        self.h_logits = torch.empty(batch, model.num_classes, dtype=torch.float32).pin_memory()
+        self.h_preds = torch.empty(batch, model.num_joints, 2, dtype=torch.float32).pin_memory()
+        self.h_maxvals = torch.empty(batch, model.num_joints, 1, dtype=torch.float32).pin_memory()
+        self.done = torch.cuda.Event()
+        self.busy = False
+
+
+class HandPipeline:
+    def __init__(self, model: MultiTaskNet, batch: int, compute_dtype=torch.bfloat16, lanes: int = 2):
+        if model.training:
+            raise RuntimeError("HandPipeline needs model.eval()")
+        p = next(model.parameters())
+        if not p.is_cuda:
+            raise RuntimeError("HandPipeline needs the model on a CUDA device; there is no CPU path")
+        self.model, self.batch, self.device, self.dtype = model, batch, p.device, compute_dtype
+        with torch.cuda.device(self.device):
+            self.lanes = [_Lane(model, batch, self.device, compute_dtype) for _ in range(lanes)]
+        self._next = 0
+        self.h2d_bytes = self.lanes[0].h_crops.numel()
+        self.d2h_bytes = 4 * (self.lanes[0].h_logits.numel() + self.lanes[0].h_preds.numel()
+                              + self.lanes[0].h_maxvals.numel())
+        # crop_normalize + the plan's launches + get_max_preds
+        self.launches_per_batch = self.lanes[0].plan.launches() + 2
+
+    def submit(self, crops_u8: torch.Tensor, after: torch.cuda.Event | None = None) -> int:
+        """Queue one batch of (B, S, S, 3) uint8 host crops; returns the lane to collect from."""
+        lib = _lib.load()
+        i = self._next
+        self._next = (self._next + 1) % len(self.lanes)
+        ln = self.lanes[i]
+        if ln.busy:
+            raise RuntimeError("lane still holds an uncollected batch; call collect() first")
+        if tuple(crops_u8.shape) != tuple(ln.h_crops.shape) or crops_u8.dtype != torch.uint8 or crops_u8.is_cuda:
+            raise ValueError(f"expected host uint8 crops of shape {tuple(ln.h_crops.shape)}")
+        dt = _lib.F32 if self.dtype == torch.float32 else _lib.BF16
+        m = self.model
+        s = m.image_size[0]
+        with torch.cuda.device(self.device), torch.cuda.stream(ln.stream):
+            if after is not None:
+                ln.stream.wait_event(after)
+            src = crops_u8 if crops_u8.is_pinned() else ln.h_crops.copy_(crops_u8)
+            ln.d_crops.copy_(src, non_blocking=True)
+            st = ln.stream.cuda_stream
+            _lib.check(lib.hgr_crop_normalize(ln.d_crops.data_ptr(), ln.d_x.data_ptr(), dt, self.batch, s, s, st),
+                       "hgr_crop_normalize")
+            _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
+                                       ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
+            _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
+                                             ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
+            ln.h_logits.copy_(ln.d_logits, non_blocking=True)
+            ln.h_preds.copy_(ln.d_preds, non_blocking=True)
+            ln.h_maxvals.copy_(ln.d_maxvals, non_blocking=True)
+            ln.done.record(ln.stream)
+        ln.busy = True
+        return i
+
+    def collect(self, lane: int):
+        """Wait for a submitted batch; returns host tensors (logits, preds, maxvals) valid until the lane is reused."""
+        ln = self.lanes[lane]
+        if not ln.busy:
+            raise RuntimeError("nothing submitted on this lane")
+        ln.done.synchronize()
+        ln.busy = False
+        return ln.h_logits, ln.h_preds, ln.h_maxvals
+
+    def infer(self, crops_u8: torch.Tensor):
+        """One batch, synchronously: (logits (B, C), keypoints (B, J, 2), confidences (B, J, 1)) on the host."""
+        a, b, c = self.collect(self.submit(crops_u8))
+        return a.clone(), b.clone(), c.clone()

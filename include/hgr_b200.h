@@ -76,7 +76,7 @@ HGR_API void hgr_plan_destroy(hgr_plan_t* plan);
  *   d_logits   (B, num_classes)            out_dtype
  *   d_heatmaps (B, num_joints, S/4, S/4)   out_dtype
  *   d_attn     (B, 8, T, T) out_dtype or NULL to skip materialising it
- *   batch      <= the plan's batch */
+ *   batch      must equal the plan's batch (tile grids and tensor maps are built for it) */
 HGR_API int hgr_forward(hgr_plan_t* plan, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
                 void* d_attn, int out_dtype, void* stream);
 
@@ -93,6 +93,15 @@ HGR_API int hgr_plan_buffer(hgr_plan_t* plan, const char* name, void** d_ptr, in
 
 /* Number of kernel launches one hgr_forward issues (for bench.py's gpu_launches). */
 HGR_API int hgr_plan_launches(hgr_plan_t* plan, int with_attn);
+
+/* Launch i of the sequence: layer name, kind (0 = tcgen05 implicit GEMM, 1 = mma.sync kernel,
+ * 2 = memory-bound kernel) and its algorithmic FLOPs / bytes (unpadded, bf16 activations). */
+HGR_API int hgr_plan_launch_info(hgr_plan_t* plan, int index, const char** name, int* kind, double* flops, double* bytes);
+
+/* hgr_forward with a CUDA event between consecutive launches: h_ms[i] receives launch i's
+ * duration in milliseconds (capacity >= hgr_plan_launches).  Synchronises; returns the count. */
+HGR_API int hgr_forward_profile(hgr_plan_t* plan, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                        void* d_attn, int out_dtype, void* stream, float* h_ms, int capacity);
 
 /* ------------------------------------------------------------------------
  * Single operators (the building blocks the plan chains; exported so the
