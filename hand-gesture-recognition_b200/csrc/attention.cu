@@ -41,6 +41,12 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <typename TP>
 __device__ __forceinline__ void store_prob(TP* p, float v);
 template <>
@@ -117,14 +123,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       }
       // key 0 is always valid, so the running max is finite from the first block on
       const float n0 = fmaxf(m0, quad_max(bm0)), n1 = fmaxf(m1, quad_max(bm1));
-      l0 *= exp2f((m0 - n0) * scale_log2e);
-      l1 *= exp2f((m1 - n1) * scale_log2e);
+      l0 *= ex2((m0 - n0) * scale_log2e);
+      l1 *= ex2((m1 - n1) * scale_log2e);
       m0 = n0;
       m1 = n1;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        l0 += exp2f((s[nt][0] - m0) * scale_log2e) + exp2f((s[nt][1] - m0) * scale_log2e);
-        l1 += exp2f((s[nt][2] - m1) * scale_log2e) + exp2f((s[nt][3] - m1) * scale_log2e);
+        l0 += ex2((s[nt][0] - m0) * scale_log2e) + ex2((s[nt][1] - m0) * scale_log2e);
+        l1 += ex2((s[nt][2] - m1) * scale_log2e) + ex2((s[nt][3] - m1) * scale_log2e);
       }
     }
     const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
@@ -140,10 +146,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int key = kb * kKeyBlock + nt * 8 + 2 * t;
-        s[nt][0] = key < T ? exp2f((s[nt][0] - m0) * scale_log2e) * inv0 : 0.f;
-        s[nt][1] = key + 1 < T ? exp2f((s[nt][1] - m0) * scale_log2e) * inv0 : 0.f;
-        s[nt][2] = key < T ? exp2f((s[nt][2] - m1) * scale_log2e) * inv1 : 0.f;
-        s[nt][3] = key + 1 < T ? exp2f((s[nt][3] - m1) * scale_log2e) * inv1 : 0.f;
+        s[nt][0] = key < T ? ex2((s[nt][0] - m0) * scale_log2e) * inv0 : 0.f;
+        s[nt][1] = key + 1 < T ? ex2((s[nt][1] - m0) * scale_log2e) * inv0 : 0.f;
+        s[nt][2] = key < T ? ex2((s[nt][2] - m1) * scale_log2e) * inv1 : 0.f;
+        s[nt][3] = key + 1 < T ? ex2((s[nt][3] - m1) * scale_log2e) * inv1 : 0.f;
         if (probs != nullptr) {
           TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
           if (row0 < T) {
@@ -184,6 +190,138 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }
 }
 
+// Single-pass variant for T <= 32 * NKB keys: the whole 16 x T score strip of a
+// warp stays in registers (NKB * 16 fp32), so Q.K^T and the exponentials are
+// evaluated once instead of twice.  Used for the 145-token (192x192) case.
+template <typename TP, int NKB>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, TP* __restrict__ probs,
+                       int T, float scale_log2e) {
+  constexpr int Tp = NKB * kKeyBlock;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sk = sq + Tp * kPitch;
+  __nv_bfloat16* sv = sk + Tp * kPitch;
+
+  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const __nv_bfloat16* base = qkv + (size_t)b * T * (3 * kHeads * kHd) + h * kHd;
+  {
+    // all 16-byte requests of this thread are issued before the first one is consumed
+    constexpr int kPer = 3 * Tp * 4 / (kWarps * 32);
+    static_assert(kPer * kWarps * 32 == 3 * Tp * 4, "chunk count must divide evenly");
+    uint4 v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * kWarps * 32;
+      const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (row < T)
+        v[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * kHeads * kHd) + part * kHeads * kHd) + c);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int i = tid + k * kWarps * 32;
+      const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+      *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v[k];
+    }
+  }
+  __syncthreads();
+
+  const int mtiles = (T + 15) >> 4;
+  const uint32_t q_lane = smem_u32(sq) + ((lane & 15) * kPitch + (lane >> 4) * 8) * 2;
+  const uint32_t k_lane = smem_u32(sk) + ((lane & 7) * kPitch + (lane >> 3) * 8) * 2;
+  const uint32_t v_lane = smem_u32(sv) + ((((lane >> 3) & 1) * 8 + (lane & 7)) * kPitch + (lane >> 4) * 8) * 2;
+
+  for (int mt = warp; mt < mtiles; mt += kWarps) {
+    uint32_t qa[2][4];
+    ldmatrix_x4(qa[0], q_lane + mt * 16 * kPitch * 2);
+    ldmatrix_x4(qa[1], q_lane + mt * 16 * kPitch * 2 + 32);
+
+    float s[NKB][4][4];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      score_block(qa, k_lane + kb * kKeyBlock * kPitch * 2, s[kb]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+        if (key >= T) s[kb][nt][0] = s[kb][nt][2] = -INFINITY;
+        if (key + 1 >= T) s[kb][nt][1] = s[kb][nt][3] = -INFINITY;
+        m0 = fmaxf(m0, fmaxf(s[kb][nt][0], s[kb][nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[kb][nt][2], s[kb][nt][3]));
+      }
+    }
+    m0 = quad_max(m0) * scale_log2e;
+    m1 = quad_max(m1) * scale_log2e;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s[kb][nt][0] = ex2(fmaf(s[kb][nt][0], scale_log2e, -m0));
+        s[kb][nt][1] = ex2(fmaf(s[kb][nt][1], scale_log2e, -m0));
+        s[kb][nt][2] = ex2(fmaf(s[kb][nt][2], scale_log2e, -m1));
+        s[kb][nt][3] = ex2(fmaf(s[kb][nt][3], scale_log2e, -m1));
+        l0 += s[kb][nt][0] + s[kb][nt][1];
+        l1 += s[kb][nt][2] + s[kb][nt][3];
+      }
+    const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
+
+    float o[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+    const int row0 = mt * 16 + g, row1 = row0 + 8;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        s[kb][nt][0] *= inv0;
+        s[kb][nt][1] *= inv0;
+        s[kb][nt][2] *= inv1;
+        s[kb][nt][3] *= inv1;
+        if (probs != nullptr) {
+          const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+          TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
+          if (row0 < T) {
+            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[kb][nt][0]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[kb][nt][1]);
+          }
+          if (row1 < T) {
+            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[kb][nt][2]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[kb][nt][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[kb][2 * j][0], s[kb][2 * j][1]);
+        pa[1] = pack_bf16x2(s[kb][2 * j][2], s[kb][2 * j][3]);
+        pa[2] = pack_bf16x2(s[kb][2 * j + 1][0], s[kb][2 * j + 1][1]);
+        pa[3] = pack_bf16x2(s[kb][2 * j + 1][2], s[kb][2 * j + 1][3]);
+        const uint32_t vaddr = v_lane + (kb * kKeyBlock + j * 16) * kPitch * 2;
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, vaddr + np * 32);
+          mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    __nv_bfloat16* orow0 = out + ((size_t)b * T + row0) * (kHeads * kHd) + h * kHd + 2 * t;
+    __nv_bfloat16* orow1 = out + ((size_t)b * T + row1) * (kHeads * kHd) + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      if (row0 < T) *reinterpret_cast<uint32_t*>(orow0 + nd * 8) = pack_bf16x2(o[nd][0], o[nd][1]);
+      if (row1 < T) *reinterpret_cast<uint32_t*>(orow1 + nd * 8) = pack_bf16x2(o[nd][2], o[nd][3]);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
@@ -197,6 +335,17 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   // softmax(x * d^-0.5) evaluated as exp2((x - max) * d^-0.5 * log2(e))
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
   const unsigned grid = (unsigned)B * kHeads;
+  if (T <= 5 * kKeyBlock) {
+    const size_t smem1 = (size_t)3 * 5 * kKeyBlock * kPitch * 2;
+    if (attn_probs != nullptr && probs_dtype == DT_BF16)
+      attention_kernel_1pass<__nv_bfloat16, 5><<<grid, kWarps * 32, smem1, stream>>>(
+          qkv, out, static_cast<__nv_bfloat16*>(attn_probs), T, scale_log2e);
+    else
+      attention_kernel_1pass<float, 5>
+          <<<grid, kWarps * 32, smem1, stream>>>(qkv, out, static_cast<float*>(attn_probs), T, scale_log2e);
+    HGR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (attn_probs != nullptr && probs_dtype == DT_BF16) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));

@@ -4,7 +4,7 @@
 // K = 27 is too thin for the tcgen05 pipeline (one 64-wide k-step would be
 // 58 % zero padding and the layer is bound by its 1.18 MB/image output
 // anyway), so this kernel reads the NCHW fp32/bf16 crop directly, stages a
-// 9-row input patch in shared memory as bf16, and runs the contraction with
+// 17-row input patch (8 output rows) in shared memory as bf16 with 128-bit loads, and runs the contraction with
 // register-resident weights on mma.sync m16n8k16 (K padded 27 -> 32).  The
 // output is written as NHWC bf16 in full 128-byte pixel rows, which is the
 // layout every later TMA box load expects.
@@ -15,48 +15,59 @@ namespace hgr {
 
 namespace {
 
-constexpr int kRowsOut = 4;                 // output rows per CTA
-constexpr int kRowsIn = 2 * kRowsOut + 1;   // 9 input rows
+constexpr int kRowsOut = 8;                // output rows per CTA
+constexpr int kRowsIn = 2 * kRowsOut + 1;  // 17 input rows
 constexpr int kWarps = 8;
+constexpr int kLeft = 8;                   // patch x index of input column 0 (index 7 is the zero padding column)
 
-template <typename TIn>
-__device__ __forceinline__ __nv_bfloat16 to_bf16(TIn v);
-template <>
-__device__ __forceinline__ __nv_bfloat16 to_bf16<float>(float v) {
-  return __float2bfloat16_rn(v);
+// 8 consecutive input elements as packed bf16 (one 16-byte smem store).
+__device__ __forceinline__ uint4 load8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
-template <>
-__device__ __forceinline__ __nv_bfloat16 to_bf16<__nv_bfloat16>(__nv_bfloat16 v) {
-  return v;
-}
+__device__ __forceinline__ uint4 load8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale already folded in, k>=27 zero.
 template <typename TIn>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
              const float* __restrict__ shift, int S) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int So = S >> 1;
-  const int pitch = S + 8;  // x index 0 is input column -1
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(smem_raw);               // [3][9][pitch]
-  __nv_bfloat16* stage = patch + 3 * kRowsIn * pitch;  // [warps][16][64]; 54*pitch bytes is a multiple of 16
+  const int pitch = S + 16;  // [0,8): left padding (index 7 = column -1), [8, 8+S): the row, then right padding
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [3][17][pitch]
+  __nv_bfloat16* stage = patch + 3 * kRowsIn * pitch;                 // [warps][16][64]
 
   const int b = blockIdx.y;
   const int oh0 = blockIdx.x * kRowsOut;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  // ---- stage the input patch (zero padded) ------------------------------
+  // ---- stage the input patch: 16-byte chunks of 8 pixels, zero rows/columns outside the image ----
   const TIn* xb = x + (size_t)b * 3 * S * S;
   const int ih0 = 2 * oh0 - 1;
-  for (int i = tid; i < 3 * kRowsIn * pitch; i += kWarps * 32) {
-    const int xi = i % pitch;
-    const int r = (i / pitch) % kRowsIn;
-    const int c = i / (pitch * kRowsIn);
-    const int ih = ih0 + r, iw = xi - 1;
-    __nv_bfloat16 v = __float2bfloat16_rn(0.0f);
-    if (ih >= 0 && ih < S && iw >= 0 && iw < S) v = to_bf16<TIn>(xb[((size_t)c * S + ih) * S + iw]);
-    patch[i] = v;
+  const int cpr = pitch >> 3;  // chunks per patch row, including one padding chunk on each side
+  const int nchunks = 3 * kRowsIn * cpr;
+  for (int i0 = tid; i0 < nchunks; i0 += 4 * kWarps * 32) {
+    // four requests in flight per thread before the first shared-memory store
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32;
+      const int ck = i % cpr;
+      const int rr = i / cpr;  // c * kRowsIn + r
+      const int r = rr % kRowsIn, c = rr / kRowsIn;
+      const int ih = ih0 + r;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < nchunks && ck >= 1 && ck <= (S >> 3) && ih >= 0 && ih < S)
+        v[u] = load8(xb + ((size_t)c * S + ih) * S + (ck - 1) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32;
+      if (i < nchunks) *reinterpret_cast<uint4*>(patch + (i / cpr) * pitch + (i % cpr) * 8) = v[u];
+    }
   }
 
   // ---- weights -> B fragments (registers, loaded once) ------------------
@@ -66,14 +77,15 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       const __nv_bfloat16* wr = w + (nt * 8 + g) * 32 + s * 16 + 2 * t;
-      bfrag[nt][s][0] = *reinterpret_cast<const uint32_t*>(wr);
-      bfrag[nt][s][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+      bfrag[nt][s][0] = __ldg(reinterpret_cast<const uint32_t*>(wr));
+      bfrag[nt][s][1] = __ldg(reinterpret_cast<const uint32_t*>(wr + 8));
     }
+  // SiLU is evaluated on h = x/2 (x*sigmoid(x) = h + h*tanh(h)): keep shift/2, halve the accumulator with one FMA
   float sh[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    sh[nt][0] = shift[nt * 8 + 2 * t];
-    sh[nt][1] = shift[nt * 8 + 2 * t + 1];
+    sh[nt][0] = 0.5f * __ldg(shift + nt * 8 + 2 * t);
+    sh[nt][1] = 0.5f * __ldg(shift + nt * 8 + 2 * t + 1);
   }
   // per-thread gather offsets of its 8 k values: k = 16*s + 2*t + {0,1,8,9}
   int koff[8];
@@ -82,7 +94,7 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
     const int k = 16 * (i >> 2) + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
     if (k < 27) {
       const int c = k % 3, kw = (k / 3) % 3, kh = k / 9;
-      koff[i] = (c * kRowsIn + kh) * pitch + kw;
+      koff[i] = (c * kRowsIn + kh) * pitch + kw + (kLeft - 1);
     } else {
       koff[i] = -1;
     }
@@ -120,19 +132,23 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
       float d[4] = {0.f, 0.f, 0.f, 0.f};
       mma_bf16_16816(d, a[0], bfrag[nt][0][0], bfrag[nt][0][1]);
       mma_bf16_16816(d, a[1], bfrag[nt][1][0], bfrag[nt][1][1]);
-      const uint32_t lo = pack_bf16x2(silu_f(d[0] + sh[nt][0]), silu_f(d[1] + sh[nt][1]));
-      const uint32_t hi = pack_bf16x2(silu_f(d[2] + sh[nt][0]), silu_f(d[3] + sh[nt][1]));
+      float h[4];
+      h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
+      h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
+      h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
+      h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
       // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
-      const int ch = nt * 8 + 2 * t;
-      *reinterpret_cast<uint32_t*>(st + g * 64 + ((((ch >> 3) ^ g) & 7) << 3) + (ch & 7)) = lo;
-      *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + ((((ch >> 3) ^ (g + 8)) & 7) << 3) + (ch & 7)) = hi;
+      *reinterpret_cast<uint32_t*>(st + g * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[0], h[1]);
+      *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[2], h[3]);
     }
     __syncwarp();
     // 16 pixels x 128 B are contiguous in NHWC: 4 fully coalesced 512-byte stores
     __nv_bfloat16* orow_ptr = out + (((size_t)b * So + (oh0 + orow)) * So + ow0) * 64;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int idx = i * 32 + lane;      // 16-byte chunk index in the 2 KB tile
+      const int idx = i * 32 + lane;  // 16-byte chunk index in the 2 KB tile
       const int px = idx >> 3, chunk = idx & 7;
       const uint4 v = *reinterpret_cast<const uint4*>(st + px * 64 + (((chunk ^ px) & 7) << 3));
       *reinterpret_cast<uint4*>(orow_ptr + px * 64 + chunk * 8) = v;
@@ -148,7 +164,7 @@ int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bflo
     set_error("conv1: image side %d must be a multiple of 32 in [32, 1024]", S);
     return -1;
   }
-  const int pitch = S + 8;
+  const int pitch = S + 16;
   const size_t smem = (size_t)3 * kRowsIn * pitch * 2 + (size_t)kWarps * 16 * 64 * 2;
   dim3 grid((S / 2) / kRowsOut, B);
   if (x_dtype == DT_F32) {

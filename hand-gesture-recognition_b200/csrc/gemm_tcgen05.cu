@@ -50,7 +50,170 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
 };
 
-template <int BN>
+// Fast activations for the epilogue.  The epilogue runs with ONE warp per SM
+// sub-partition and accumulator stage, so its cost is counted in issue slots:
+// everything that can be decided at compile time (activation, residual) is a
+// template parameter, which also keeps the loop body inside the instruction cache.
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if constexpr (ACT == ACT_SILU) {
+    // v arrives pre-halved (scale and shift are stored * 0.5): x*sigmoid(x) = h + h*tanh(h), h = x/2
+    return fmaf(v, tanh_approx(v), v);
+  } else if constexpr (ACT == ACT_GELU) {
+    // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): two MUFU ops
+    const float ax = fabsf(v) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(t, poly, 1.421413741f);
+    poly = fmaf(t, poly, -0.284496736f);
+    poly = fmaf(t, poly, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    const float hv = 0.5f * v;
+    return fmaf(hv, copysignf(erf_abs, v), hv);
+  } else {
+    return v;
+  }
+}
+
+// tile index -> pixel-box origin and output-channel offset
+struct TileMap {
+  int tiles_w, tiles_h, tiles_nout, bw, bh, bimg, bn;
+  __device__ __forceinline__ void coords(int tile, int& w0, int& h0, int& n0, int& noff) const {
+    const int nt = tile % tiles_nout;
+    int mt = tile / tiles_nout;
+    const int tw = mt % tiles_w;
+    mt /= tiles_w;
+    const int th = mt % tiles_h;
+    const int tn = mt / tiles_h;
+    w0 = tw * bw;
+    h0 = th * bh;
+    n0 = tn * bimg;
+    noff = nt * bn;
+  }
+};
+
+// One epilogue group (4 warps, 128 threads) drains accumulator stage `group` of every other tile:
+// tcgen05.ld -> scale/shift (+ residual) -> activation -> bf16 -> swizzled smem -> TMA store.
+// NBUF = staging buffers per group (each one 64-column chunk, 16 KiB).
+template <int BN, int ACT, bool RES, int NBUF>
+__device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtensorMap* tmO, const TileMap& tm,
+                                               uint8_t* out_bufs, const float* s_scale, const float* s_shift,
+                                               uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t tmem_base,
+                                               int group, int total_tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;         // TMEM lane quarter this warp may touch
+  const int row = q * 32 + lane;  // pixel row inside the tile == TMEM lane
+  const int gtid = threadIdx.x - 128 - group * 128;
+  const uint32_t bar_id = 1 + group;
+  const int wi = row & (tm.bw - 1);
+  const int hi = (row >> p.bw_log2) & (tm.bh - 1);
+  const int ni = row >> (p.bw_log2 + p.bh_log2);
+  const uint32_t sw = static_cast<uint32_t>(row & 7);
+  uint32_t store_count = 0;
+  int iter = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    if ((iter & 1) != group) continue;
+    const uint32_t acc_phase = (iter >> 1) & 1;
+    int w0, h0, n0, noff;
+    tm.coords(tile, w0, h0, n0, noff);
+    const bool valid = (w0 + wi < p.W) && (h0 + hi < p.H) && (n0 + ni < p.NIMG);
+    const uint4* res_row = nullptr;
+    uint4 rnext[8];
+    if constexpr (RES) {
+      if (valid)
+        res_row = reinterpret_cast<const uint4*>(p.res + (long long)(n0 + ni) * p.res_sn +
+                                                 (long long)(h0 + hi) * p.res_sh + (long long)(w0 + wi) * p.res_sw + noff);
+      // the residual of the first 64-column chunk is requested before the accumulator is even ready
+#pragma unroll
+      for (int v = 0; v < 8; ++v) rnext[v] = res_row ? __ldg(res_row + v) : make_uint4(0, 0, 0, 0);
+    }
+
+    mbar_wait(&acc_full_bar[group], acc_phase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * BN;
+
+#pragma unroll 1
+    for (int j = 0; j < BN / 64; ++j, ++store_count) {
+      uint8_t* buf = out_bufs + (NBUF == 1 ? 0 : (store_count & 1)) * kStageBufBytes;
+      uint4 rcur[8];
+      if constexpr (RES) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) rcur[v] = rnext[v];
+        if (j + 1 < BN / 64) {  // next chunk's residual flies while this chunk is computed
+#pragma unroll
+          for (int v = 0; v < 8; ++v) rnext[v] = res_row ? __ldg(res_row + (j + 1) * 8 + v) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      // the TMA store that last read this buffer must be done
+      if (gtid == 0) tma_store_wait_read<NBUF - 1>();
+      bar_sync(bar_id, 128);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = j * 64 + half * 32;  // column inside the tile
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(t_row + c0, acc);
+        tmem_ld_wait();
+        const float4* sc4 = reinterpret_cast<const float4*>(s_scale + noff + c0);
+        const float4* sh4 = reinterpret_cast<const float4*>(s_shift + noff + c0);
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 sc = sc4[e >> 2], sh = sh4[e >> 2];
+          float v0 = fmaf(__uint_as_float(acc[e]), sc.x, sh.x);
+          float v1 = fmaf(__uint_as_float(acc[e + 1]), sc.y, sh.y);
+          float v2 = fmaf(__uint_as_float(acc[e + 2]), sc.z, sh.z);
+          float v3 = fmaf(__uint_as_float(acc[e + 3]), sc.w, sh.w);
+          if constexpr (RES) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rcur) + half * 16 + (e >> 1);
+            constexpr float rs = ACT == ACT_SILU ? 0.5f : 1.0f;
+            v0 = fmaf(bf16_lo(rw[0]), rs, v0);
+            v1 = fmaf(bf16_hi(rw[0]), rs, v1);
+            v2 = fmaf(bf16_lo(rw[1]), rs, v2);
+            v3 = fmaf(bf16_hi(rw[1]), rs, v3);
+          }
+          packed[e >> 1] = pack_bf16x2(apply_act<ACT>(v0), apply_act<ACT>(v1));
+          packed[(e >> 1) + 1] = pack_bf16x2(apply_act<ACT>(v2), apply_act<ACT>(v3));
+        }
+        // row-major 128-byte rows, 16-byte chunks XOR-swizzled by (row % 8):
+        // the layout CU_TENSOR_MAP_SWIZZLE_128B expects on the store side.
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint32_t chunk = static_cast<uint32_t>(half * 4 + v) ^ sw;
+          *reinterpret_cast<uint4*>(buf + row * 128 + chunk * 16) =
+              make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        }
+      }
+      if (j == BN / 64 - 1) {
+        // every TMEM read of this accumulator stage is complete: hand it back
+        tc_fence_before();
+        mbar_arrive(&acc_empty_bar[group]);
+      }
+      fence_proxy_async_smem();
+      bar_sync(bar_id, 128);
+      if (gtid == 0) {
+        tma_store_4d(tmO, buf, p.out_c_off + noff + j * 64, w0 + p.out_w_off, h0, n0);
+        tma_store_commit();
+      }
+    }
+  }
+  if (gtid == 0) tma_store_wait_all();
+}
+
+// SiLU is evaluated on h = x/2, so the 1/2 is folded into the affine that the epilogue applies.
+template <int ACT>
+__device__ __forceinline__ void load_affine(const GemmParams& p, float* s_scale, float* s_shift) {
+  const float pre = ACT == ACT_SILU ? 0.5f : 1.0f;
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) {
+    s_scale[i] = pre * (p.scale ? p.scale[i] : 1.0f);
+    s_shift[i] = pre * (p.shift ? p.shift[i] : 0.0f);
+  }
+}
+
+template <int BN, int ACT, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
@@ -94,10 +257,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(tmem_ptr_smem, C::kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) {
-    s_scale[i] = p.scale ? p.scale[i] : 1.0f;
-    s_shift[i] = p.shift ? p.shift[i] : 0.0f;
-  }
+  load_affine<ACT>(p, s_scale, s_shift);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -109,18 +269,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
   const int bimg = kTileM >> (p.bw_log2 + p.bh_log2);
 
-  auto tile_coords = [&](int tile, int& w0, int& h0, int& n0, int& noff) {
-    const int nt = tile % p.tiles_nout;
-    int mt = tile / p.tiles_nout;
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    const int tn = mt / p.tiles_h;
-    w0 = tw * bw;
-    h0 = th * bh;
-    n0 = tn * bimg;
-    noff = nt * BN;
-  };
+  const TileMap tm{p.tiles_w, p.tiles_h, p.tiles_nout, bw, bh, bimg, BN};
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -129,7 +278,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int w0, h0, n0, noff;
-        tile_coords(tile, w0, h0, n0, noff);
+        tm.coords(tile, w0, h0, n0, noff);
         int ks = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int cw = w0 + p.tap_dw[tap];
@@ -187,92 +336,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ================= epilogue groups =================
     const int group = (warp - 4) >> 2;  // accumulator stage this group drains
-    const int q = warp & 3;             // TMEM lane quarter this warp may touch
-    const int row = q * 32 + lane;      // pixel row inside the tile == TMEM lane
-    const int gtid = threadIdx.x - 128 - group * 128;
-    const uint32_t bar_id = 1 + group;
-    uint8_t* out_bufs = smem + C::kOffOut + group * 2 * kStageBufBytes;
-    const int wi = row & (bw - 1);
-    const int hi = (row >> p.bw_log2) & (bh - 1);
-    const int ni = row >> (p.bw_log2 + p.bh_log2);
-    const uint32_t sw = static_cast<uint32_t>(row & 7);
-    uint32_t store_count = 0;
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-      if ((iter & 1) != group) continue;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      int w0, h0, n0, noff;
-      tile_coords(tile, w0, h0, n0, noff);
-      const bool valid = (w0 + wi < p.W) && (h0 + hi < p.H) && (n0 + ni < p.NIMG);
-      const __nv_bfloat16* res_row = nullptr;
-      if (p.res != nullptr && valid)
-        res_row = p.res + (long long)(n0 + ni) * p.res_sn + (long long)(h0 + hi) * p.res_sh +
-                  (long long)(w0 + wi) * p.res_sw + noff;
-
-      mbar_wait(&acc_full_bar[group], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * BN;
-
-#pragma unroll 1
-      for (int j = 0; j < BN / 64; ++j, ++store_count) {
-        uint8_t* buf = out_bufs + (store_count & 1) * kStageBufBytes;
-        // the TMA store that last read this buffer (two stores ago) must be done
-        if (gtid == 0) tma_store_wait_read<1>();
-        bar_sync(bar_id, 128);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c0 = j * 64 + half * 32;  // column inside the tile
-          uint4 rv[4];
-          if (res_row != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res_row + c0);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) rv[v] = __ldg(rp + v);
-          }
-          uint32_t acc[32];
-          tmem_ld_32x32b_x32(t_row + c0, acc);
-          tmem_ld_wait();
-          uint32_t packed[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float v0 = fmaf(__uint_as_float(acc[e]), s_scale[noff + c0 + e], s_shift[noff + c0 + e]);
-            float v1 = fmaf(__uint_as_float(acc[e + 1]), s_scale[noff + c0 + e + 1], s_shift[noff + c0 + e + 1]);
-            if (res_row != nullptr) {
-              const uint32_t r = reinterpret_cast<const uint32_t*>(rv)[e >> 1];
-              v0 += bf16_lo(r);
-              v1 += bf16_hi(r);
-            }
-            if (p.act == ACT_SILU) {
-              v0 = silu_f(v0);
-              v1 = silu_f(v1);
-            } else if (p.act == ACT_GELU) {
-              v0 = gelu_erf_f(v0);
-              v1 = gelu_erf_f(v1);
-            }
-            packed[e >> 1] = pack_bf16x2(v0, v1);
-          }
-          // row-major 128-byte rows, 16-byte chunks XOR-swizzled by (row % 8):
-          // the layout CU_TENSOR_MAP_SWIZZLE_128B expects on the store side.
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint32_t chunk = static_cast<uint32_t>(half * 4 + v) ^ sw;
-            *reinterpret_cast<uint4*>(buf + row * 128 + chunk * 16) =
-                make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-          }
-        }
-        if (j == BN / 64 - 1) {
-          // every TMEM read of this accumulator stage is complete: hand it back
-          tc_fence_before();
-          mbar_arrive(&acc_empty_bar[group]);
-        }
-        fence_proxy_async_smem();
-        bar_sync(bar_id, 128);
-        if (gtid == 0) {
-          tma_store_4d(&tmO, buf, p.out_c_off + noff + j * 64, w0 + p.out_w_off, h0, n0);
-          tma_store_commit();
-        }
-      }
-    }
-    if (gtid == 0) tma_store_wait_all();
+    epilogue_group<BN, ACT, RES, 2>(p, &tmO, tm, smem + C::kOffOut + group * 2 * kStageBufBytes, s_scale, s_shift,
+                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
   }
 
   // ---- teardown ---------------------------------------------------------
@@ -281,26 +346,228 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-template <int BN>
+// ---------------------------------------------------------------------------------------------
+// 3x3 stride-1 convolution, 64 -> 64 channels, with the input halo staged ONCE per tile.
+//
+// The generic kernel above re-loads the 128-pixel A tile for each of the 9 taps, which makes the
+// 64-channel 3x3 convs of cspelan1 (gelan.py:73-74 at 48x48, 15.5 % of the FLOPs) L2-bandwidth
+// bound.  Here a tile is 8 x 16 output pixels; its (8+2) x (16+2) input halo for 64 channels is
+// ONE TMA box of 180 pixel rows (128 B each, SWIZZLE_128B, out-of-image rows zero-filled), and
+// every tap is the same smem patch addressed through a shifted UMMA descriptor:
+//   start = patch + ((kh * 10 + kw) * 128 B),  8-row groups 10 * 128 B apart (one image row),
+// which works because the tensor core applies the 128B swizzle to absolute smem address bits
+// (tools/umma_probe.cu: any 128 B-aligned start and any stride byte offset with base_offset = 0).
+// All nine 64x64 weight tiles (72 KiB) stay resident in smem for the whole kernel, so the
+// per-tile operand traffic drops from 216 KiB to 22.5 KiB.
+struct HaloCfg {
+  static constexpr int kPatchRows = 10 * 18;
+  static constexpr int kPatchBytes = kPatchRows * 128;     // 23040, what one TMA box delivers
+  static constexpr int kPatchStride = 23 * 1024;           // stage pitch, keeps 1024-byte alignment
+  static constexpr int kStages = 4;
+  static constexpr int kWBytes = 9 * 64 * 128;             // nine [64 x 64] bf16 weight tiles
+  static constexpr int kOffW = 0;
+  static constexpr int kOffA = kWBytes;
+  static constexpr int kOffOut = kOffA + kStages * kPatchStride;  // [2 groups][1 buf][16 KiB]
+  static constexpr int kOffScale = kOffOut + 2 * kStageBufBytes;
+  static constexpr int kOffBars = kOffScale + 2 * kMaxCout * 4;
+  static constexpr int kNumBars = 2 * kStages + 5;
+  static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+  static constexpr int kSmemBytes = kOffTmemPtr + 16;
+  static constexpr int kTmemCols = 128;
+};
+
+template <int ACT, bool RES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+  using C = HaloCfg;
+  constexpr int BN = 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::kStages;
+  uint64_t* acc_full_bar = bars + 2 * C::kStages;
+  uint64_t* acc_empty_bar = bars + 2 * C::kStages + 2;
+  uint64_t* w_bar = bars + 2 * C::kStages + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::kOffTmemPtr);
+  float* s_scale = reinterpret_cast<float*>(smem + C::kOffScale);
+  float* s_shift = s_scale + kMaxCout;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("hgr: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmW);
+    prefetch_tensormap(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full_bar[i], 1);
+      mbar_init(&acc_empty_bar[i], 128);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+    tmem_relinquish();
+  }
+  load_affine<ACT>(p, s_scale, s_shift);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: tap t is rows [0, 64) x K columns [64 t, 64 t + 64)
+      mbar_expect_tx(w_bar, C::kWBytes);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem + C::kOffW + t * 8192, &tmW, w_bar, t * 64, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int w0, h0, n0, noff;
+        tm.coords(tile, w0, h0, n0, noff);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], C::kPatchBytes);
+        tma_load_5d(smem + C::kOffA + stage * C::kPatchStride, &tmA, &full_bar[stage], p.a_c_off, w0 - 1, 0, h0 - 1,
+                    n0);
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t patch = smem_u32(smem + C::kOffA + stage * C::kPatchStride);
+        const uint32_t wres = smem_u32(smem + C::kOffW);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a_addr = patch + ((tap / 3) * 10 + (tap % 3)) * 128;
+          const uint32_t b_addr = wres + tap * 8192;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_d, umma_desc_sw128(a_addr + k * 32, 10 * 128), umma_desc_sw128(b_addr + k * 32, 1024),
+                         idesc, (tap | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&acc_full_bar[acc]);
+      }
+      __syncwarp();
+      if (++stage == C::kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int group = (warp - 4) >> 2;
+    epilogue_group<BN, ACT, RES, 1>(p, &tmO, tm, smem + C::kOffOut + group * kStageBufBytes, s_scale, s_shift,
+                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int ACT, bool RES>
+int launch_halo_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                     int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        HaloCfg::kSmemBytes));
+    configured = true;
+  }
+  const int total = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int grid = total < num_sms ? total : num_sms;
+  conv3x3_halo_kernel<ACT, RES><<<grid, kThreads, HaloCfg::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN, int ACT, bool RES>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::kSmemBytes));
     configured = true;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nout;
   const int grid = total < num_sms ? total : num_sms;
-  gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  gemm_kernel<BN, ACT, RES><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p, int num_sms,
+              cudaStream_t stream) {
+  const bool res = p.res != nullptr;
+  switch (p.act) {
+    case ACT_NONE:
+      return res ? launch_impl<BN, ACT_NONE, true>(tmA, tmW, tmO, p, num_sms, stream)
+                 : launch_impl<BN, ACT_NONE, false>(tmA, tmW, tmO, p, num_sms, stream);
+    case ACT_SILU:
+      return res ? launch_impl<BN, ACT_SILU, true>(tmA, tmW, tmO, p, num_sms, stream)
+                 : launch_impl<BN, ACT_SILU, false>(tmA, tmW, tmO, p, num_sms, stream);
+    case ACT_GELU:
+      return res ? launch_impl<BN, ACT_GELU, true>(tmA, tmW, tmO, p, num_sms, stream)
+                 : launch_impl<BN, ACT_GELU, false>(tmA, tmW, tmO, p, num_sms, stream);
+    default: set_error("launch_gemm: bad activation %d", p.act); return -1;
+  }
 }
 
 }  // namespace
 
 int gemm_smem_bytes(int bn) {
   return bn == 256 ? Cfg<256>::kSmemBytes : (bn == 128 ? Cfg<128>::kSmemBytes : Cfg<64>::kSmemBytes);
+}
+
+int launch_conv3x3_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                        int num_sms, cudaStream_t stream) {
+  if (p.cout != 64 || p.num_taps != 9 || p.chunks_per_tap != 1 || p.bw_log2 != 3 || p.bh_log2 != 4) {
+    set_error("launch_conv3x3_halo: needs a 64->64 3x3 layer tiled 8x16");
+    return -1;
+  }
+  const bool res = p.res != nullptr;
+  switch (p.act) {
+    case ACT_NONE:
+      return res ? launch_halo_impl<ACT_NONE, true>(tmA, tmW, tmO, p, num_sms, stream)
+                 : launch_halo_impl<ACT_NONE, false>(tmA, tmW, tmO, p, num_sms, stream);
+    case ACT_SILU:
+      return res ? launch_halo_impl<ACT_SILU, true>(tmA, tmW, tmO, p, num_sms, stream)
+                 : launch_halo_impl<ACT_SILU, false>(tmA, tmW, tmO, p, num_sms, stream);
+    default: set_error("launch_conv3x3_halo: unsupported activation %d", p.act); return -1;
+  }
 }
 
 int launch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
@@ -314,9 +581,9 @@ int launch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
     return -1;
   }
   switch (bn) {
-    case 64: return launch_impl<64>(tmA, tmW, tmO, p, num_sms, stream);
-    case 128: return launch_impl<128>(tmA, tmW, tmO, p, num_sms, stream);
-    case 256: return launch_impl<256>(tmA, tmW, tmO, p, num_sms, stream);
+    case 64: return launch_bn<64>(tmA, tmW, tmO, p, num_sms, stream);
+    case 128: return launch_bn<128>(tmA, tmW, tmO, p, num_sms, stream);
+    case 256: return launch_bn<256>(tmA, tmW, tmO, p, num_sms, stream);
     default: set_error("launch_gemm: bad bn %d", bn); return -1;
   }
 }

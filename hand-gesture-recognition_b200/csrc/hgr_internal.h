@@ -56,6 +56,9 @@ struct GemmParams {
 int launch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                 int num_sms, cudaStream_t stream);
 int gemm_smem_bytes(int bn);
+// 3x3 s1 64->64 layer with the input halo staged once per 8x16 tile (A map box = (64, 10, 1, 18, 1)).
+int launch_conv3x3_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                        int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------ tensor maps ----
 // rank <= 5; dims innermost first; strides in bytes for dims 1..rank-1.

@@ -37,6 +37,7 @@ struct GemmOp {
   CUtensorMap a, w, o;
   GemmParams p;
   int bn;
+  bool halo;     // 64->64 3x3 s1 layer on the halo-staging kernel
   double flops;  // algorithmic: 2 * M * N * K, unpadded
   double bytes;  // algorithmic: A + W + OUT (+ RES) in bf16
 };
@@ -81,6 +82,13 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
   pick_box(Wo, Ho, bw, bh, bi);
   memset(&op, 0, sizeof(op));
   op.bn = pick_bn(cout);
+  // the halo-staging kernel covers the 64->64 3x3 stride-1 layers whose maps tile exactly into 8 x 16 pixels
+  op.halo = k == 3 && s == 1 && cin == 64 && cout == 64 && W % 8 == 0 && H % 16 == 0 && act != ACT_GELU;
+  if (op.halo) {
+    bw = 8;
+    bh = 16;
+    bi = 1;
+  }
   GemmParams& p = op.p;
   p.num_taps = k * k;
   p.chunks_per_tap = cin / 64;
@@ -90,7 +98,7 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
     const uint64_t dims[5] = {(uint64_t)in_ctot, (uint64_t)W, 1, (uint64_t)H, (uint64_t)B};
     const uint64_t row = (uint64_t)in_ctot * 2;
     const uint64_t strides[4] = {row, row * W, row * W, row * W * H};
-    const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bi};
+    const uint32_t box[5] = {64, (uint32_t)(op.halo ? bw + 2 : bw), 1, (uint32_t)(op.halo ? bh + 2 : bh), (uint32_t)bi};
     if (int r = make_tensor_map_bf16(&op.a, in, 5, dims, strides, box)) return r;
     for (int kh = 0; kh < k; ++kh)
       for (int kw = 0; kw < k; ++kw) {
@@ -275,6 +283,7 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
 }
 
 int run_op(const GemmOp& op, cudaStream_t stream) {
+  if (op.halo) return launch_conv3x3_halo(op.a, op.w, op.o, op.p, device_sm_count(), stream);
   return launch_gemm(op.bn, op.a, op.w, op.o, op.p, device_sm_count(), stream);
 }
 

@@ -62,27 +62,46 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
 
   // ---- vertical interpolation of the 8 output rows -----------------------
   const __nv_bfloat16* tok = tokens + ((size_t)b * (F * F + 1) + 1) * kDim;  // skip the class token
-  for (int i = tid; i < kRows * F * (kDim / 8); i += kWarps * 32) {
-    const int c8 = i % (kDim / 8);
-    const int x = (i / (kDim / 8)) % F;
-    const int r = i / ((kDim / 8) * F);
-    const float sy = scale * (float)(oy0 + r);
-    const int y0 = (int)sy;
-    const int y1 = y0 + (y0 < F - 1 ? 1 : 0);
-    const float l1 = sy - (float)y0, l0 = 1.0f - l1;
-    const uint4 ua = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y0 * F + x) * kDim) + c8);
-    const uint4 ub = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y1 * F + x) * kDim) + c8);
-    const uint32_t a[4] = {ua.x, ua.y, ua.z, ua.w};
-    const uint32_t bb[4] = {ub.x, ub.y, ub.z, ub.w};
-    float o[8];
+  const int nitems = kRows * F * (kDim / 8);
+  for (int i0 = tid; i0 < nitems; i0 += 4 * kWarps * 32) {
+    // eight 16-byte requests in flight per thread before the first one is consumed
+    uint4 ua[4], ub[4];
+    float l1v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      o[2 * k] = l0 * bf16_lo(a[k]) + l1 * bf16_lo(bb[k]);
-      o[2 * k + 1] = l0 * bf16_hi(a[k]) + l1 * bf16_hi(bb[k]);
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32;
+      const int c8 = i % (kDim / 8);
+      const int x = (i / (kDim / 8)) % F;
+      const int r = i / ((kDim / 8) * F);
+      const float sy = scale * (float)(oy0 + r);
+      const int y0 = (int)sy;
+      const int y1 = y0 + (y0 < F - 1 ? 1 : 0);
+      l1v[u] = sy - (float)y0;
+      ua[u] = ub[u] = make_uint4(0, 0, 0, 0);
+      if (i < nitems) {
+        ua[u] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y0 * F + x) * kDim) + c8);
+        ub[u] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y1 * F + x) * kDim) + c8);
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(vbuf + (r * F + x) * kVPitch + c8 * 8);
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kWarps * 32;
+      if (i >= nitems) break;
+      const int c8 = i % (kDim / 8);
+      const int rx = i / (kDim / 8);  // r * F + x
+      const float l1 = l1v[u], l0 = 1.0f - l1;
+      const uint32_t a[4] = {ua[u].x, ua[u].y, ua[u].z, ua[u].w};
+      const uint32_t bb[4] = {ub[u].x, ub[u].y, ub[u].z, ub[u].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[2 * k] = l0 * bf16_lo(a[k]) + l1 * bf16_lo(bb[k]);
+        o[2 * k + 1] = l0 * bf16_hi(a[k]) + l1 * bf16_hi(bb[k]);
+      }
+      float4* dst = reinterpret_cast<float4*>(vbuf + rx * kVPitch + c8 * 8);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
   }
   __syncthreads();
 

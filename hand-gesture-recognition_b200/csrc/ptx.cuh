@@ -58,17 +58,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("hgr: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
+
 // Bounded wait: ~2^31 cycles (about a second) and then trap, so a protocol
 // bug shows up as a launch failure rather than a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      printf("hgr: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar),
-             parity);
-      __trap();
-    }
+    if (clock64() - t0 > (1ll << 31)) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
