@@ -49,7 +49,7 @@ GFLOP_PER_IMG = {192: 4.374, 256: 7.891}  # BASELINE.md section 2 (2 x MAC, unpa
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
@@ -96,7 +96,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region."""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -114,12 +118,13 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        clocks = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        smax = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows[-3:]
+        clocks = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        smax = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
         busy = [c for c in clocks if smax and c > 0.3 * smax[0]] or clocks
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": smax[0] if smax else None,
                 "reasons": reasons, "samples": len(clocks)}
@@ -220,12 +225,14 @@ def main():
     x = torch.randn(B, 3, S, S, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
 
     with torch.no_grad():
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()  # nvidia-smi needs ~0.2 s to deliver its first sample: start before the warm-up
         for _ in range(W):
             out = model(x)
         barrier()
-        sampler = ClockSampler(local_rank)
         if rank == 0:
-            sampler.start()
+            sampler.mark()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()

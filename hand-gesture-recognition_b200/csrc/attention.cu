@@ -247,9 +247,11 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
       score_block(qa, k_lane + kb * kKeyBlock * kPitch * 2, s[kb]);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const int key = kb * kKeyBlock + nt * 8 + 2 * t;
-        if (key >= T) s[kb][nt][0] = s[kb][nt][2] = -INFINITY;
-        if (key + 1 >= T) s[kb][nt][1] = s[kb][nt][3] = -INFINITY;
+        if (kb == NKB - 1) {  // only the last key block can hold padding keys (T > 32 * (NKB - 1) is checked at launch)
+          const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+          if (key >= T) s[kb][nt][0] = s[kb][nt][2] = -INFINITY;
+          if (key + 1 >= T) s[kb][nt][1] = s[kb][nt][3] = -INFINITY;
+        }
         m0 = fmaxf(m0, fmaxf(s[kb][nt][0], s[kb][nt][1]));
         m1 = fmaxf(m1, fmaxf(s[kb][nt][2], s[kb][nt][3]));
       }
@@ -270,28 +272,26 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
       }
     const float inv0 = 1.0f / quad_sum(l0), inv1 = 1.0f / quad_sum(l1);
 
+    // P.V on the un-normalised exponentials (each in (0, 1]); 1/l is applied to the 16 x 32 output instead of
+    // the 16 x T probabilities.  The probabilities themselves are only normalised when they are written out.
     float o[4][4];
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
 #pragma unroll
     for (int kb = 0; kb < NKB; ++kb) {
+      if (probs != nullptr) {
+        TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        s[kb][nt][0] *= inv0;
-        s[kb][nt][1] *= inv0;
-        s[kb][nt][2] *= inv1;
-        s[kb][nt][3] *= inv1;
-        if (probs != nullptr) {
+        for (int nt = 0; nt < 4; ++nt) {
           const int key = kb * kKeyBlock + nt * 8 + 2 * t;
-          TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
           if (row0 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[kb][nt][0]);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[kb][nt][1]);
+            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[kb][nt][0] * inv0);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[kb][nt][1] * inv0);
           }
           if (row1 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[kb][nt][2]);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[kb][nt][3]);
+            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[kb][nt][2] * inv1);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[kb][nt][3] * inv1);
           }
         }
       }
@@ -316,8 +316,8 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
     __nv_bfloat16* orow1 = out + ((size_t)b * T + row1) * (kHeads * kHd) + h * kHd + 2 * t;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
-      if (row0 < T) *reinterpret_cast<uint32_t*>(orow0 + nd * 8) = pack_bf16x2(o[nd][0], o[nd][1]);
-      if (row1 < T) *reinterpret_cast<uint32_t*>(orow1 + nd * 8) = pack_bf16x2(o[nd][2], o[nd][3]);
+      if (row0 < T) *reinterpret_cast<uint32_t*>(orow0 + nd * 8) = pack_bf16x2(o[nd][0] * inv0, o[nd][1] * inv0);
+      if (row1 < T) *reinterpret_cast<uint32_t*>(orow1 + nd * 8) = pack_bf16x2(o[nd][2] * inv1, o[nd][3] * inv1);
     }
   }
 }
@@ -335,7 +335,7 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   // softmax(x * d^-0.5) evaluated as exp2((x - max) * d^-0.5 * log2(e))
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
   const unsigned grid = (unsigned)B * kHeads;
-  if (T <= 5 * kKeyBlock) {
+  if (T <= 5 * kKeyBlock && T > 4 * kKeyBlock) {
     const size_t smem1 = (size_t)3 * 5 * kKeyBlock * kPitch * 2;
     if (attn_probs != nullptr && probs_dtype == DT_BF16)
       attention_kernel_1pass<__nv_bfloat16, 5><<<grid, kWarps * 32, smem1, stream>>>(

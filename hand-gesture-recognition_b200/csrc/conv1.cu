@@ -26,49 +26,69 @@ __device__ __forceinline__ uint4 load8(const float* p) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
-__device__ __forceinline__ uint4 load8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-// w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale already folded in, k>=27 zero.
+// Stages the 17-row input patch of row block `rb` (zero padded) into `patch`.
+// bf16 input: asynchronous 16-byte copies (cp.async, zero-fill for padding); fp32 input: load, convert, store.
 template <typename TIn>
-__global__ void __launch_bounds__(kWarps * 32, 2)
-conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
-             const float* __restrict__ shift, int S) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int So = S >> 1;
-  const int pitch = S + 16;  // [0,8): left padding (index 7 = column -1), [8, 8+S): the row, then right padding
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [3][17][pitch]
-  __nv_bfloat16* stage = patch + 3 * kRowsIn * pitch;                 // [warps][16][64]
-
-  const int b = blockIdx.y;
-  const int oh0 = blockIdx.x * kRowsOut;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-
-  // ---- stage the input patch: 16-byte chunks of 8 pixels, zero rows/columns outside the image ----
-  const TIn* xb = x + (size_t)b * 3 * S * S;
-  const int ih0 = 2 * oh0 - 1;
+__device__ __forceinline__ void stage_patch(__nv_bfloat16* patch, const TIn* xb, int rb, int S, int pitch, int tid) {
+  const int ih0 = 2 * rb * kRowsOut - 1;
   const int cpr = pitch >> 3;  // chunks per patch row, including one padding chunk on each side
   const int nchunks = 3 * kRowsIn * cpr;
-  for (int i0 = tid; i0 < nchunks; i0 += 4 * kWarps * 32) {
-    // four requests in flight per thread before the first shared-memory store
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kWarps * 32;
+  if constexpr (sizeof(TIn) == 2) {
+    for (int i = tid; i < nchunks; i += kWarps * 32) {
       const int ck = i % cpr;
       const int rr = i / cpr;  // c * kRowsIn + r
       const int r = rr % kRowsIn, c = rr / kRowsIn;
       const int ih = ih0 + r;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (i < nchunks && ck >= 1 && ck <= (S >> 3) && ih >= 0 && ih < S)
-        v[u] = load8(xb + ((size_t)c * S + ih) * S + (ck - 1) * 8);
+      const bool inside = ck >= 1 && ck <= (S >> 3) && ih >= 0 && ih < S;
+      const TIn* src = inside ? xb + ((size_t)c * S + ih) * S + (ck - 1) * 8 : xb;
+      cp_async_16(patch + rr * pitch + ck * 8, src, inside ? 16u : 0u);
     }
+  } else {
+    for (int i0 = tid; i0 < nchunks; i0 += 4 * kWarps * 32) {
+      uint4 v[4];  // four requests in flight per thread before the first shared-memory store
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kWarps * 32;
-      if (i < nchunks) *reinterpret_cast<uint4*>(patch + (i / cpr) * pitch + (i % cpr) * 8) = v[u];
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kWarps * 32;
+        const int ck = i % cpr;
+        const int rr = i / cpr;
+        const int r = rr % kRowsIn, c = rr / kRowsIn;
+        const int ih = ih0 + r;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (i < nchunks && ck >= 1 && ck <= (S >> 3) && ih >= 0 && ih < S)
+          v[u] = load8(xb + ((size_t)c * S + ih) * S + (ck - 1) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kWarps * 32;
+        if (i < nchunks) *reinterpret_cast<uint4*>(patch + (i / cpr) * pitch + (i % cpr) * 8) = v[u];
+      }
     }
   }
+}
+
+// w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale already folded in, k>=27 zero.
+// grid = (splits, B): a CTA walks `nrb` consecutive 8-row blocks of one image with two patch buffers, so the
+// copy of block i+1 overlaps the MMAs and the stores of block i.
+template <typename TIn>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
+             const float* __restrict__ shift, int S, int nrb) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int So = S >> 1;
+  const int pitch = S + 16;  // [0,8): left padding (index 7 = column -1), [8, 8+S): the row, then right padding
+  const int patch_elems = 3 * kRowsIn * pitch;
+  __nv_bfloat16* patch0 = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // 2 x [3][17][pitch]
+  __nv_bfloat16* stage = patch0 + 2 * patch_elems;                     // [warps][16][64]
+
+  const int b = blockIdx.y;
+  const int rb0 = blockIdx.x * nrb;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const TIn* xb = x + (size_t)b * 3 * S * S;
+
+  stage_patch<TIn>(patch0, xb, rb0, S, pitch, tid);
+  cp_async_commit();
 
   // ---- weights -> B fragments (registers, loaded once) ------------------
   uint32_t bfrag[8][2][2];
@@ -99,60 +119,71 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
       koff[i] = -1;
     }
   }
-  __syncthreads();
 
-  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
   __nv_bfloat16* st = stage + warp * 16 * 64;
   const int mtiles_per_row = So >> 4;
   const int mtiles = kRowsOut * mtiles_per_row;
-  for (int mt = warp; mt < mtiles; mt += kWarps) {
-    const int orow = mt / mtiles_per_row;
-    const int ow0 = (mt % mtiles_per_row) << 4;
-    // pixel (orow, ow0+g) and (orow, ow0+g+8): patch offset of tap (0,0), channel 0
-    const int base0 = (2 * orow) * pitch + 2 * (ow0 + g);
-    const int base1 = base0 + 16;
-    uint32_t a[2][4];
+  for (int it = 0; it < nrb; ++it) {
+    const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch0 + (it & 1) * patch_elems);
+    if (it + 1 < nrb) {
+      stage_patch<TIn>(patch0 + ((it + 1) & 1) * patch_elems, xb, rb0 + it + 1, S, pitch, tid);
+      cp_async_commit();
+      cp_async_wait<1>();  // block `it` has landed, block `it + 1` may still be in flight
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int oh0 = (rb0 + it) * kRowsOut;
+    for (int mt = warp; mt < mtiles; mt += kWarps) {
+      const int orow = mt / mtiles_per_row;
+      const int ow0 = (mt % mtiles_per_row) << 4;
+      // pixel (orow, ow0+g) and (orow, ow0+g+8): patch offset of tap (0,0), channel 0
+      const int base0 = (2 * orow) * pitch + 2 * (ow0 + g);
+      const int base1 = base0 + 16;
+      uint32_t a[2][4];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      unsigned short e[8];
+      for (int s = 0; s < 2; ++s) {
+        unsigned short e[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ko = koff[s * 4 + i];
+          e[i] = ko >= 0 ? pu[base0 + ko] : (unsigned short)0;
+          e[4 + i] = ko >= 0 ? pu[base1 + ko] : (unsigned short)0;
+        }
+        a[s][0] = (uint32_t)e[0] | ((uint32_t)e[1] << 16);  // row g,   k 2t,2t+1
+        a[s][1] = (uint32_t)e[4] | ((uint32_t)e[5] << 16);  // row g+8, k 2t,2t+1
+        a[s][2] = (uint32_t)e[2] | ((uint32_t)e[3] << 16);  // row g,   k 2t+8,2t+9
+        a[s][3] = (uint32_t)e[6] | ((uint32_t)e[7] << 16);  // row g+8, k 2t+8,2t+9
+      }
+      __syncwarp();  // previous tile's staging reads are done
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(d, a[0], bfrag[nt][0][0], bfrag[nt][0][1]);
+        mma_bf16_16816(d, a[1], bfrag[nt][1][0], bfrag[nt][1][1]);
+        float h[4];
+        h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
+        h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
+        h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
+        h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
+        // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
+        *reinterpret_cast<uint32_t*>(st + g * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[0], h[1]);
+        *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[2], h[3]);
+      }
+      __syncwarp();
+      // 16 pixels x 128 B are contiguous in NHWC: 4 fully coalesced 512-byte stores
+      __nv_bfloat16* orow_ptr = out + (((size_t)b * So + (oh0 + orow)) * So + ow0) * 64;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int ko = koff[s * 4 + i];
-        e[i] = ko >= 0 ? pu[base0 + ko] : (unsigned short)0;
-        e[4 + i] = ko >= 0 ? pu[base1 + ko] : (unsigned short)0;
+        const int idx = i * 32 + lane;  // 16-byte chunk index in the 2 KB tile
+        const int px = idx >> 3, chunk = idx & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(st + px * 64 + (((chunk ^ px) & 7) << 3));
+        *reinterpret_cast<uint4*>(orow_ptr + px * 64 + chunk * 8) = v;
       }
-      a[s][0] = (uint32_t)e[0] | ((uint32_t)e[1] << 16);  // row g,   k 2t,2t+1
-      a[s][1] = (uint32_t)e[4] | ((uint32_t)e[5] << 16);  // row g+8, k 2t,2t+1
-      a[s][2] = (uint32_t)e[2] | ((uint32_t)e[3] << 16);  // row g,   k 2t+8,2t+9
-      a[s][3] = (uint32_t)e[6] | ((uint32_t)e[7] << 16);  // row g+8, k 2t+8,2t+9
     }
-    __syncwarp();  // previous tile's staging reads are done
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816(d, a[0], bfrag[nt][0][0], bfrag[nt][0][1]);
-      mma_bf16_16816(d, a[1], bfrag[nt][1][0], bfrag[nt][1][1]);
-      float h[4];
-      h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
-      h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
-      h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
-      h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
-      // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
-      *reinterpret_cast<uint32_t*>(st + g * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[0], h[1]);
-      *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[2], h[3]);
-    }
-    __syncwarp();
-    // 16 pixels x 128 B are contiguous in NHWC: 4 fully coalesced 512-byte stores
-    __nv_bfloat16* orow_ptr = out + (((size_t)b * So + (oh0 + orow)) * So + ow0) * 64;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = i * 32 + lane;  // 16-byte chunk index in the 2 KB tile
-      const int px = idx >> 3, chunk = idx & 7;
-      const uint4 v = *reinterpret_cast<const uint4*>(st + px * 64 + (((chunk ^ px) & 7) << 3));
-      *reinterpret_cast<uint4*>(orow_ptr + px * 64 + chunk * 8) = v;
-    }
+    __syncthreads();  // everyone is done with this patch buffer before block it+2 is copied into it
   }
 }
 
@@ -165,16 +196,19 @@ int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bflo
     return -1;
   }
   const int pitch = S + 16;
-  const size_t smem = (size_t)3 * kRowsIn * pitch * 2 + (size_t)kWarps * 16 * 64 * 2;
-  dim3 grid((S / 2) / kRowsOut, B);
+  const size_t smem = (size_t)2 * 3 * kRowsIn * pitch * 2 + (size_t)kWarps * 16 * 64 * 2;
+  const int blocks = (S / 2) / kRowsOut;          // 8-row blocks per image
+  const int splits = blocks % 2 == 0 ? 2 : 1;     // CTAs per image
+  dim3 grid(splits, B);
   if (x_dtype == DT_F32) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_kernel<float><<<grid, kWarps * 32, smem, stream>>>(static_cast<const float*>(x), out, w, shift, S);
+    conv1_kernel<float>
+        <<<grid, kWarps * 32, smem, stream>>>(static_cast<const float*>(x), out, w, shift, S, blocks / splits);
   } else {
     HGR_CHECK_CUDA(
         cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_kernel<__nv_bfloat16>
-        <<<grid, kWarps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), out, w, shift, S);
+    conv1_kernel<__nv_bfloat16><<<grid, kWarps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), out, w,
+                                                                    shift, S, blocks / splits);
   }
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -99,7 +99,9 @@ struct TileMap {
 // One epilogue group (4 warps, 128 threads) drains accumulator stage `group` of every other tile:
 // tcgen05.ld -> scale/shift (+ residual) -> activation -> bf16 -> swizzled smem -> TMA store.
 // NBUF = staging buffers per group (each one 64-column chunk, 16 KiB).
-template <int BN, int ACT, bool RES, int NBUF>
+enum : int { ROW_NONE = 0, ROW_NORM_IN = 1, ROW_STATS_OUT = 2 };
+
+template <int BN, int ACT, bool RES, int NBUF, int ROW = ROW_NONE>
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtensorMap* tmO, const TileMap& tm,
                                                uint8_t* out_bufs, const float* s_scale, const float* s_shift,
                                                uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t tmem_base,
@@ -130,6 +132,17 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       // the residual of the first 64-column chunk is requested before the accumulator is even ready
 #pragma unroll
       for (int v = 0; v < 8; ++v) rnext[v] = res_row ? __ldg(res_row + v) : make_uint4(0, 0, 0, 0);
+    }
+
+    // folded LayerNorm: per-row scalars of the A operand (consumer) / running sums of the output row (producer)
+    float rstd = 1.0f, rmean = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    const long long stats_row = (long long)(n0 + ni) * p.st_sn + (w0 + wi) + p.out_w_off;
+    if constexpr (ROW == ROW_NORM_IN) {
+      if (valid) {
+        const float2 st = __ldg(p.stats_in + stats_row);
+        rstd = st.y;
+        rmean = st.x * st.y;
+      }
     }
 
     mbar_wait(&acc_full_bar[group], acc_phase);
@@ -163,10 +176,18 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 sc = sc4[e >> 2], sh = sh4[e >> 2];
-          float v0 = fmaf(__uint_as_float(acc[e]), sc.x, sh.x);
-          float v1 = fmaf(__uint_as_float(acc[e + 1]), sc.y, sh.y);
-          float v2 = fmaf(__uint_as_float(acc[e + 2]), sc.z, sh.z);
-          float v3 = fmaf(__uint_as_float(acc[e + 3]), sc.w, sh.w);
+          float v0, v1, v2, v3;
+          if constexpr (ROW == ROW_NORM_IN) {
+            v0 = fmaf(__uint_as_float(acc[e]), rstd, fmaf(-rmean, sc.x, sh.x));
+            v1 = fmaf(__uint_as_float(acc[e + 1]), rstd, fmaf(-rmean, sc.y, sh.y));
+            v2 = fmaf(__uint_as_float(acc[e + 2]), rstd, fmaf(-rmean, sc.z, sh.z));
+            v3 = fmaf(__uint_as_float(acc[e + 3]), rstd, fmaf(-rmean, sc.w, sh.w));
+          } else {
+            v0 = fmaf(__uint_as_float(acc[e]), sc.x, sh.x);
+            v1 = fmaf(__uint_as_float(acc[e + 1]), sc.y, sh.y);
+            v2 = fmaf(__uint_as_float(acc[e + 2]), sc.z, sh.z);
+            v3 = fmaf(__uint_as_float(acc[e + 3]), sc.w, sh.w);
+          }
           if constexpr (RES) {
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rcur) + half * 16 + (e >> 1);
             constexpr float rs = ACT == ACT_SILU ? 0.5f : 1.0f;
@@ -175,8 +196,16 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
             v2 = fmaf(bf16_lo(rw[1]), rs, v2);
             v3 = fmaf(bf16_hi(rw[1]), rs, v3);
           }
-          packed[e >> 1] = pack_bf16x2(apply_act<ACT>(v0), apply_act<ACT>(v1));
-          packed[(e >> 1) + 1] = pack_bf16x2(apply_act<ACT>(v2), apply_act<ACT>(v3));
+          v0 = apply_act<ACT>(v0);
+          v1 = apply_act<ACT>(v1);
+          v2 = apply_act<ACT>(v2);
+          v3 = apply_act<ACT>(v3);
+          if constexpr (ROW == ROW_STATS_OUT) {
+            s1 += (v0 + v1) + (v2 + v3);
+            s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
+          }
+          packed[e >> 1] = pack_bf16x2(v0, v1);
+          packed[(e >> 1) + 1] = pack_bf16x2(v2, v3);
         }
         // row-major 128-byte rows, 16-byte chunks XOR-swizzled by (row % 8):
         // the layout CU_TENSOR_MAP_SWIZZLE_128B expects on the store side.
@@ -199,6 +228,14 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
         tma_store_commit();
       }
     }
+    if constexpr (ROW == ROW_STATS_OUT) {
+      static_assert(ROW != ROW_STATS_OUT || BN == 256, "row statistics need the whole 256-wide row in one tile");
+      if (valid) {
+        const float mean = s1 * (1.0f / BN);
+        const float var = fmaxf(fmaf(s2, 1.0f / BN, -mean * mean), 0.0f);
+        p.stats_out[stats_row] = make_float2(mean, rsqrtf(var + 1e-5f));
+      }
+    }
   }
   if (gtid == 0) tma_store_wait_all();
 }
@@ -213,7 +250,7 @@ __device__ __forceinline__ void load_affine(const GemmParams& p, float* s_scale,
   }
 }
 
-template <int BN, int ACT, bool RES>
+template <int BN, int ACT, bool RES, int ROW = ROW_NONE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
@@ -273,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -314,15 +351,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + C::kOffA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smem + C::kOffB + stage * C::kBBytes);
+        // the issue block is guarded by elect.sync (not `lane == 0`) so that ptxas keeps the
+        // descriptors in uniform registers: ~4 instructions per MMA instead of a 15-instruction waterfall
+        const uint64_t a_base = umma_desc_sw128(smem_u32(smem + C::kOffA + stage * kABytes), 1024);
+        const uint64_t b_base = umma_desc_sw128(smem_u32(smem + C::kOffB + stage * C::kBBytes), 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32, 1024);
-            const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32, 1024);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (ks | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kTileK / 16; ++k)
+            umma_bf16_ss(tmem_d, a_base + 2 * k, b_base + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (ks == ksteps - 1) umma_commit(&acc_full_bar[acc]);
         }
@@ -336,8 +372,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ================= epilogue groups =================
     const int group = (warp - 4) >> 2;  // accumulator stage this group drains
-    epilogue_group<BN, ACT, RES, 2>(p, &tmO, tm, smem + C::kOffOut + group * 2 * kStageBufBytes, s_scale, s_shift,
-                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
+    epilogue_group<BN, ACT, RES, 2, ROW>(p, &tmO, tm, smem + C::kOffOut + group * 2 * kStageBufBytes, s_scale, s_shift,
+                                         acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
   }
 
   // ---- teardown ---------------------------------------------------------
@@ -431,7 +467,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN};
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // resident weights: tap t is rows [0, 64) x K columns [64 t, 64 t + 64)
       mbar_expect_tx(w_bar, C::kWBytes);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem + C::kOffW + t * 8192, &tmW, w_bar, t * 64, 0);
@@ -462,21 +498,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t tmem_d = tmem_base + acc * BN;
         const uint32_t patch = smem_u32(smem + C::kOffA + stage * C::kPatchStride);
         const uint32_t wres = smem_u32(smem + C::kOffW);
+        // descriptors differ only in the 14-bit start-address field: build the two constant parts once
+        const uint64_t a_base = umma_desc_sw128(patch, 10 * 128);
+        const uint64_t b_base = umma_desc_sw128(wres, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t a_addr = patch + ((tap / 3) * 10 + (tap % 3)) * 128;
-          const uint32_t b_addr = wres + tap * 8192;
+          for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_d, umma_desc_sw128(a_addr + k * 32, 10 * 128), umma_desc_sw128(b_addr + k * 32, 1024),
-                         idesc, (tap | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = a_base + static_cast<uint64_t>((((tap / 3) * 10 + (tap % 3)) * 128 + k * 32) >> 4);
+              const uint64_t bd = b_base + static_cast<uint64_t>((tap * 8192 + k * 32) >> 4);
+              umma_bf16_ss(tmem_d, ad, bd, idesc, (tap | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&acc_full_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&acc_full_bar[acc]);
       }
       __syncwarp();
       if (++stage == C::kStages) {
@@ -511,19 +552,19 @@ int launch_halo_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
   return 0;
 }
 
-template <int BN, int ACT, bool RES>
+template <int BN, int ACT, bool RES, int ROW = ROW_NONE>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                 int num_sms, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT, RES, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::kSmemBytes));
     configured = true;
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nout;
   const int grid = total < num_sms ? total : num_sms;
-  gemm_kernel<BN, ACT, RES><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
+  gemm_kernel<BN, ACT, RES, ROW><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -579,6 +620,26 @@ int launch_gemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
   if (p.tiles_nout * bn != p.cout) {
     set_error("launch_gemm: tiles_nout=%d * bn=%d != cout=%d", p.tiles_nout, bn, p.cout);
     return -1;
+  }
+  if (p.stats_in != nullptr || p.stats_out != nullptr) {
+    // LayerNorm-folded variants exist for the ViT's 256-wide token rows only
+    if (bn != 256 || p.cout % 256 != 0 || (p.stats_in && p.stats_out)) {
+      set_error("launch_gemm: row statistics need bn == 256 (cout %d) and only one of stats_in / stats_out", p.cout);
+      return -1;
+    }
+    if (p.stats_out != nullptr) {
+      if (p.cout != 256 || p.act != ACT_NONE || p.res == nullptr) {
+        set_error("launch_gemm: stats_out is built for the residual-stream producers (cout 256, no activation, residual)");
+        return -1;
+      }
+      return launch_impl<256, ACT_NONE, true, ROW_STATS_OUT>(tmA, tmW, tmO, p, num_sms, stream);
+    }
+    if (p.res != nullptr || (p.act != ACT_NONE && p.act != ACT_GELU)) {
+      set_error("launch_gemm: stats_in is built for to_qkv (no activation) and net.1 (GELU), without residual");
+      return -1;
+    }
+    return p.act == ACT_GELU ? launch_impl<256, ACT_GELU, false, ROW_NORM_IN>(tmA, tmW, tmO, p, num_sms, stream)
+                             : launch_impl<256, ACT_NONE, false, ROW_NORM_IN>(tmA, tmW, tmO, p, num_sms, stream);
   }
   switch (bn) {
     case 64: return launch_bn<64>(tmA, tmW, tmO, p, num_sms, stream);

@@ -50,6 +50,13 @@ struct GemmParams {
   const float* shift;  // nullable: 0
   const __nv_bfloat16* res;  // nullable; element strides below
   long long res_sn, res_sh, res_sw;
+  // LayerNorm folded into the GEMMs around it (BN == cout == 256 only, one thread owns a full row):
+  //  stats_out: the epilogue also writes (mean, rstd) of each output row (eps 1e-5, biased variance);
+  //  stats_in:  the A rows are the UN-normalised x; with gamma folded into W the epilogue computes
+  //             rstd * acc - rstd * mean * scale[n] + shift[n]   (scale = row sums of W', shift = W beta + b).
+  float2* stats_out;
+  const float2* stats_in;
+  long long st_sn;  // stats row = n * st_sn + w + out_w_off
 };
 
 // bn is the N tile (64, 128 or 256) and must divide cout.
@@ -73,7 +80,9 @@ int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bflo
 int launch_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamma, const float* beta, long long rows,
                      cudaStream_t stream);
 
-int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, int B, int T, cudaStream_t stream);
+// tokens[b, 0, :] = cls; row_stats[b * T] = cls_stats (mean, rstd) for the folded LayerNorm
+int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, const float* cls_stats, float* row_stats, int B, int T,
+                    cudaStream_t stream);
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
                      cudaStream_t stream);

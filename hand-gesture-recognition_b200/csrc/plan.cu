@@ -172,8 +172,9 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
 }
 
 // y = act(x W^T + b) (+ res) over a (rows, cin) matrix.
-int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const void* wgt, const float* bias, int act,
-                    const void* res, void* y, int cout) {
+int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const void* wgt, const float* scale,
+                    const float* bias, int act, const void* res, void* y, int cout, const float* stats_in = nullptr,
+                    float* stats_out = nullptr) {
   if (cin % 64 != 0 || cout % 64 != 0 || rows <= 0 || rows > 0x7fffffffLL) {
     set_error("linear: unsupported shape rows %lld cin %d cout %d", rows, cin, cout);
     return -1;
@@ -214,8 +215,11 @@ int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const vo
   p.NIMG = 1;
   p.cout = cout;
   p.act = act;
-  p.scale = nullptr;
+  p.scale = scale;
   p.shift = bias;
+  p.stats_in = reinterpret_cast<const float2*>(stats_in);
+  p.stats_out = reinterpret_cast<float2*>(stats_out);
+  p.st_sn = 0;
   if (res != nullptr) {
     p.res = static_cast<const __nv_bfloat16*>(res);
     p.res_sw = cout;
@@ -231,7 +235,7 @@ int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const vo
 // ViT.forward (transformer.py:132-139): rows are written at token index 1+p
 // and the sin-cos table is added as a batch-broadcast residual.
 int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const void* wgt, const void* pe, void* tokens,
-                  int T) {
+                  int T, float* stats_out) {
   if (P % 16 != 0) {
     set_error("proj: %d positions per image is not a multiple of 16", P);
     return -1;
@@ -277,6 +281,8 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
   p.res_sw = kDim;
   p.res_sh = 0;
   p.res_sn = 0;
+  p.stats_out = reinterpret_cast<float2*>(stats_out);
+  p.st_sn = T;
   op.flops = 2.0 * (double)B * P * cin * kDim;
   op.bytes = 2.0 * ((double)B * P * cin + (double)cin * kDim + (double)B * P * kDim + (double)P * kDim);
   return 0;
@@ -356,17 +362,19 @@ std::vector<ParamEntry> param_layout(int S, int J, int C) {
   add("proj.w", DT_BF16, kDim, 512);
   add("decoder.pos_embedding", DT_BF16, (int64_t)F * F, kDim);
   add("decoder.cls_token", DT_F32, kDim);
+  add("decoder.cls_token.stats", DT_F32, 2);  // (mean, rstd) of the bf16 class token, for the folded LayerNorm
   for (int l = 0; l < kDepth; ++l) {
     const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
     const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
-    add(a + "norm.weight", DT_F32, kDim);
-    add(a + "norm.bias", DT_F32, kDim);
+    // LayerNorm is folded into the GEMM that consumes it: W' = gamma (.) W in bf16,
+    // c[n] = sum_k W'[n, k], d[n] = sum_k beta[k] W[n, k] (+ bias)
     add(a + "to_qkv.w", DT_BF16, 3 * kDim, kDim);
+    add(a + "to_qkv.c", DT_F32, 3 * kDim);
+    add(a + "to_qkv.d", DT_F32, 3 * kDim);
     add(a + "to_out.w", DT_BF16, kDim, kDim);
-    add(f + "0.weight", DT_F32, kDim);
-    add(f + "0.bias", DT_F32, kDim);
     add(f + "1.w", DT_BF16, kDim, kDim);
-    add(f + "1.bias", DT_F32, kDim);
+    add(f + "1.c", DT_F32, kDim);
+    add(f + "1.d", DT_F32, kDim);
     add(f + "4.w", DT_BF16, kDim, kDim);
     add(f + "4.bias", DT_F32, kDim);
   }
@@ -422,7 +430,7 @@ std::vector<Buf> workspace_layout(int S, int B, size_t* total) {
   add("o3", H4, H4, 512);
   add("tokens", 1, T, kDim);
   add("tokens_b", 1, T, kDim);
-  add("ln", 1, T, kDim);
+  add("row_stats", 1, T, 4);  // (mean, rstd) fp32 per token row = 8 bytes
   add("qkv", 1, T, 3 * kDim);
   add("attn_out", 1, T, kDim);
   add("hidden", 1, T, kDim);
@@ -622,24 +630,32 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
   gelan("d1", H3, 256, "g2", "t2", "o2", 256, 128);
   conv("o2", H3, 256, 0, nullptr, 0, 0, "d2", 512, 0, ACT_SILU);         // down2
   gelan("d2", H4, 512, "g3", "t3", "o3", 512, 256);
+  float* stats = reinterpret_cast<float*>(pl->bp("row_stats"));
   if (!rc)
     rc = build_proj_op(pl->proj, pl->bp("o3"), B, H4 * H4, 512, pl->pp<void>("proj.w"),
-                       pl->pp<void>("decoder.pos_embedding"), pl->bp("tokens"), pl->T);
+                       pl->pp<void>("decoder.pos_embedding"), pl->bp("tokens"), pl->T, stats);
   const long long rows = (long long)B * pl->T;
   for (int l = 0; l < kDepth && !rc; ++l) {
     const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
     const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
-    rc = build_linear_op(pl->qkv[l], pl->bp("ln"), rows, kDim, pl->pp<void>(a + "to_qkv.w"), nullptr, ACT_NONE,
-                         nullptr, pl->bp("qkv"), 3 * kDim);
+    // Attention.forward (transformer.py:62-77): LN folded into to_qkv through the row statistics of x
+    rc = build_linear_op(pl->qkv[l], pl->bp("tokens"), rows, kDim, pl->pp<void>(a + "to_qkv.w"),
+                         pl->pp<float>(a + "to_qkv.c"), pl->pp<float>(a + "to_qkv.d"), ACT_NONE, nullptr,
+                         pl->bp("qkv"), 3 * kDim, stats, nullptr);
+    // x1 = to_out(attn) + x  (:93); its epilogue leaves the statistics of x1 for the FeedForward's LN
     if (!rc)
-      rc = build_linear_op(pl->out[l], pl->bp("attn_out"), rows, kDim, pl->pp<void>(a + "to_out.w"), nullptr,
-                           ACT_NONE, pl->bp("tokens"), pl->bp("tokens_b"), kDim);
+      rc = build_linear_op(pl->out[l], pl->bp("attn_out"), rows, kDim, pl->pp<void>(a + "to_out.w"), nullptr, nullptr,
+                           ACT_NONE, pl->bp("tokens"), pl->bp("tokens_b"), kDim, nullptr, stats);
+    // FeedForward (transformer.py:32-42): LN folded into net.1, GELU in its epilogue
     if (!rc)
-      rc = build_linear_op(pl->ff1[l], pl->bp("ln"), rows, kDim, pl->pp<void>(f + "1.w"), pl->pp<float>(f + "1.bias"),
-                           ACT_GELU, nullptr, pl->bp("hidden"), kDim);
+      rc = build_linear_op(pl->ff1[l], pl->bp("tokens_b"), rows, kDim, pl->pp<void>(f + "1.w"),
+                           pl->pp<float>(f + "1.c"), pl->pp<float>(f + "1.d"), ACT_GELU, nullptr, pl->bp("hidden"),
+                           kDim, stats, nullptr);
+    // x2 = net.4(h) + b + x1 (:94), statistics of x2 for the next layer's attention LN
     if (!rc)
-      rc = build_linear_op(pl->ff2[l], pl->bp("hidden"), rows, kDim, pl->pp<void>(f + "4.w"),
-                           pl->pp<float>(f + "4.bias"), ACT_NONE, pl->bp("tokens_b"), pl->bp("tokens"), kDim);
+      rc = build_linear_op(pl->ff2[l], pl->bp("hidden"), rows, kDim, pl->pp<void>(f + "4.w"), nullptr,
+                           pl->pp<float>(f + "4.bias"), ACT_NONE, pl->bp("tokens_b"), pl->bp("tokens"), kDim, nullptr,
+                           stats);
   }
   if (rc) {
     delete pl;
@@ -663,31 +679,22 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
       });
   for (int i = 0; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
   add("decoder.cls_token", 2, 0, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io&) {
-    return launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"), B, T, st);
+    return launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"),
+                           pl->pp<float>("decoder.cls_token.stats"), reinterpret_cast<float*>(pl->bp("row_stats")), B,
+                           T, st);
   });
   add_gemm("proj+pos_embedding", &pl->proj);
   for (int l = 0; l < kDepth; ++l) {
     const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
     const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
-    const double ln_bytes = 2.0 * (double)rows * kDim * 2;
-    // Attention (transformer.py:62-77) + residual (:93)
-    add(a + "norm", 2, 0, ln_bytes, [pl, a, rows](cudaStream_t st, const Io&) {
-      return launch_layernorm(pl->bp("tokens"), pl->bp("ln"), pl->pp<float>(a + "norm.weight"),
-                              pl->pp<float>(a + "norm.bias"), rows, st);
-    });
-    add_gemm(a + "to_qkv", &pl->qkv[l]);
+    add_gemm(a + "norm+to_qkv", &pl->qkv[l]);
     const bool last = l == kDepth - 1;
     add(a + "attention", 1, 4.0 * dB * kHeads * T * T * 32, (double)rows * kDim * 2 * 4,
         [pl, B, T, last](cudaStream_t st, const Io& io) {
           return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st);
         });
     add_gemm(a + "to_out+residual", &pl->out[l]);
-    // FeedForward (transformer.py:32-42) + residual (:94)
-    add(f + "0", 2, 0, ln_bytes, [pl, f, rows](cudaStream_t st, const Io&) {
-      return launch_layernorm(pl->bp("tokens_b"), pl->bp("ln"), pl->pp<float>(f + "0.weight"),
-                              pl->pp<float>(f + "0.bias"), rows, st);
-    });
-    add_gemm(f + "1+gelu", &pl->ff1[l]);
+    add_gemm(f + "0+1+gelu", &pl->ff1[l]);
     add_gemm(f + "4+residual", &pl->ff2[l]);
   }
   add("decoder.mlp_head", 2, 2.0 * dB * kDim * C, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io& io) {
@@ -846,10 +853,13 @@ int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, int in_c
   return run_op(op, static_cast<cudaStream_t>(stream));
 }
 
-int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_bias, int act,
-               const void* d_res, void* d_y, int cout, void* stream) {
+int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale, const float* d_bias,
+               int act, const void* d_res, void* d_y, int cout, const float* d_row_stats_in, float* d_row_stats_out,
+               void* stream) {
   GemmOp op;
-  if (int rc = build_linear_op(op, d_x, rows, cin, d_w, d_bias, act, d_res, d_y, cout)) return rc;
+  if (int rc = build_linear_op(op, d_x, rows, cin, d_w, d_scale, d_bias, act, d_res, d_y, cout, d_row_stats_in,
+                               d_row_stats_out))
+    return rc;
   return run_op(op, static_cast<cudaStream_t>(stream));
 }
 

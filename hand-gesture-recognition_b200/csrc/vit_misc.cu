@@ -71,11 +71,13 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
   reinterpret_cast<uint4*>(y + row * kDim)[lane] = o;
 }
 
-__global__ void fill_cls_kernel(__nv_bfloat16* __restrict__ tokens, const float* __restrict__ cls, int B, int T) {
+__global__ void fill_cls_kernel(__nv_bfloat16* __restrict__ tokens, const float* __restrict__ cls,
+                                const float* __restrict__ cls_stats, float* __restrict__ row_stats, int B, int T) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kDim) return;
   const int b = i / kDim, c = i % kDim;
   tokens[(size_t)b * T * kDim + c] = __float2bfloat16_rn(cls[c]);
+  if (c < 2 && row_stats != nullptr) row_stats[(size_t)b * T * 2 + c] = cls_stats[c];
 }
 
 template <typename TOut>
@@ -116,9 +118,10 @@ int launch_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamm
   return 0;
 }
 
-int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, int B, int T, cudaStream_t stream) {
+int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, const float* cls_stats, float* row_stats, int B, int T,
+                    cudaStream_t stream) {
   const int n = B * kDim;
-  fill_cls_kernel<<<(n + 255) / 256, 256, 0, stream>>>(tokens, cls, B, T);
+  fill_cls_kernel<<<(n + 255) / 256, 256, 0, stream>>>(tokens, cls, cls_stats, row_stats, B, T);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 BN_EPS = 1e-5
+LN_EPS = 1e-5
 
 
 def sincos_table(h: int, w: int, dim: int = 256, temperature: float = 10000.0) -> torch.Tensor:
@@ -61,16 +62,34 @@ def packed_tensors(sd, image_size: int, device) -> dict:
     f = image_size // 16
     out["decoder.pos_embedding"] = sincos_table(f, f).to(device).to(torch.bfloat16)
     out["decoder.cls_token"] = sd["decoder.cls_token"].float().reshape(256)
-    for k, v in sd.items():
-        if not k.startswith("decoder."):
-            continue
-        if k.endswith("to_qkv.weight") or k.endswith("to_out.weight") or k.endswith("net.1.weight") \
-                or k.endswith("net.4.weight"):
-            out[k[: -len("weight")] + "w"] = v.float().to(torch.bfloat16)
-        elif k == "decoder.simple_decoder.1.weight":
-            out["decoder.simple_decoder.1.w"] = v.float().reshape(v.shape[0], 256).to(torch.bfloat16)
-        elif k != "decoder.cls_token":
-            out[k] = v.float()
+    cls_bf = out["decoder.cls_token"].to(torch.bfloat16).float()
+    out["decoder.cls_token.stats"] = torch.stack(
+        [cls_bf.mean(), torch.rsqrt(cls_bf.var(unbiased=False) + LN_EPS)]).float()
+
+    def fold_ln(w, gamma, beta, bias=None):
+        """LayerNorm folded into the Linear that consumes it: (W' = gamma (.) W in bf16, c = W' 1, d = W beta + b)."""
+        w, gamma, beta = w.float(), gamma.float(), beta.float()
+        wp = (w * gamma[None, :]).to(torch.bfloat16)
+        d = w @ beta
+        if bias is not None:
+            d = d + bias.float()
+        return wp, wp.float().sum(dim=1), d
+
+    for l in range(4):
+        a = f"decoder.transformer.layers.{l}.0."
+        f = f"decoder.transformer.layers.{l}.1.net."
+        out[a + "to_qkv.w"], out[a + "to_qkv.c"], out[a + "to_qkv.d"] = fold_ln(
+            sd[a + "to_qkv.weight"], sd[a + "norm.weight"], sd[a + "norm.bias"])
+        out[a + "to_out.w"] = sd[a + "to_out.weight"].float().to(torch.bfloat16)
+        out[f + "1.w"], out[f + "1.c"], out[f + "1.d"] = fold_ln(
+            sd[f + "1.weight"], sd[f + "0.weight"], sd[f + "0.bias"], sd[f + "1.bias"])
+        out[f + "4.w"] = sd[f + "4.weight"].float().to(torch.bfloat16)
+        out[f + "4.bias"] = sd[f + "4.bias"].float()
+    for k in ("decoder.mlp_head.0.weight", "decoder.mlp_head.0.bias", "decoder.mlp_head.1.weight",
+              "decoder.mlp_head.1.bias", "decoder.simple_decoder.1.bias"):
+        out[k] = sd[k].float()
+    v = sd["decoder.simple_decoder.1.weight"]
+    out["decoder.simple_decoder.1.w"] = v.float().reshape(v.shape[0], 256).to(torch.bfloat16)
     return out
 
 

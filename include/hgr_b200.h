@@ -120,11 +120,20 @@ HGR_API int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, 
                     const float* d_scale, const float* d_shift, int k, int s, int act, const void* d_res,
                     int res_ctot, int res_coff, void* d_out, int out_ctot, int out_coff, int cout, void* stream);
 
-/* y = act(x W^T + bias) (+ residual): nn.Linear of the ViT
+/* y = act(scale (.) (x W^T) + bias) (+ residual): nn.Linear of the ViT
  * (reference model/transformer.py:34,37,65,75).  x (rows, cin) bf16,
- * W (cout, cin) bf16, y (rows, cout) bf16. */
-HGR_API int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_bias, int act,
-               const void* d_res, void* d_y, int cout, void* stream);
+ * W (cout, cin) bf16, y (rows, cout) bf16; d_scale / d_bias / d_res nullable.
+ * LayerNorm folding (cout % 256 == 0, model/transformer.py:33,63 fused into the
+ * GEMMs around it):
+ *   d_row_stats_out  (rows, 2) fp32: the epilogue also writes (mean, rstd) of every
+ *                    output row (cout == 256, residual given, no activation);
+ *   d_row_stats_in   (rows, 2) fp32 statistics of the rows of x: with gamma folded
+ *                    into W (W' = gamma (.) W), d_scale[n] = sum_k W'[n,k] and
+ *                    d_bias[n] = sum_k beta[k] W[n,k] + b[n], the result is
+ *                    act(LayerNorm(x) W^T + b). */
+HGR_API int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale,
+                       const float* d_bias, int act, const void* d_res, void* d_y, int cout,
+                       const float* d_row_stats_in, float* d_row_stats_out, void* stream);
 
 /* encoder.conv1: NCHW (fp32|bf16) -> NHWC bf16 (B, S/2, S/2, 64).
  * d_w bf16 [64][32] (k = (kh*3+kw)*3+c, BN scale folded, zero padded). */

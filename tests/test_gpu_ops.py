@@ -137,8 +137,8 @@ def test_linear(lib, case):
     bd = None if bias is None else bias.to(dev)
     rd = None if res is None else res.to(dev, torch.bfloat16)
     y = torch.full((rows, cout), 7.0, dtype=torch.bfloat16, device=dev)
-    _chk(lib.hgr_linear(xd.data_ptr(), rows, cin, wd.data_ptr(), _ptr(bd), act, _ptr(rd), y.data_ptr(), cout,
-                        _stream()), "hgr_linear")
+    _chk(lib.hgr_linear(xd.data_ptr(), rows, cin, wd.data_ptr(), None, _ptr(bd), act, _ptr(rd), y.data_ptr(), cout,
+                        None, None, _stream()), "hgr_linear")
     torch.cuda.synchronize()
     ref = F.linear(x, w, bias)
     if res is not None:
@@ -146,6 +146,47 @@ def test_linear(lib, case):
     ref = _act(ref, act)
     r, m = report("linear " + name, y, ref)
     assert r <= REL_TOL and m <= MAX_TOL
+
+
+@pytest.mark.parametrize("rows,cout,act", [(300, 768, 0), (1160, 256, 2), (77, 256, 0)])
+def test_linear_with_folded_layernorm(lib, rows, cout, act):
+    """LayerNorm -> Linear (reference model/transformer.py:33-34, 63-65) as ONE GEMM on the un-normalised rows:
+    the producer GEMM's epilogue leaves (mean, rstd) per row, the consumer folds gamma into W and applies
+    rstd * acc - rstd * mean * c + d.  Checked as a producer/consumer pair against the oracle's operators."""
+    from hgr_b200 import packing
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows + cout)
+    # producer: x1 = a Wo^T + x0 (to_out + residual), emits row statistics of x1
+    a = bf16_round(torch.randn(rows, 256, generator=g))
+    x0 = bf16_round(torch.randn(rows, 256, generator=g) * 3 + 0.5)
+    wo = bf16_round(torch.randn(256, 256, generator=g) / 16)
+    ad, x0d, wod = (t.to(dev, torch.bfloat16) for t in (a, x0, wo))
+    x1 = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
+    stats = torch.full((rows, 2), 7.0, dtype=torch.float32, device=dev)
+    _chk(lib.hgr_linear(ad.data_ptr(), rows, 256, wod.data_ptr(), None, None, 0, x0d.data_ptr(), x1.data_ptr(), 256,
+                        None, stats.data_ptr(), _stream()), "hgr_linear stats_out")
+    torch.cuda.synchronize()
+    x1_ref = F.linear(a, wo) + x0
+    r, m = report("folded-LN producer x1", x1, x1_ref)
+    assert r <= REL_TOL and m <= MAX_TOL
+    mean_ref, var_ref = x1_ref.mean(1), x1_ref.var(1, unbiased=False)
+    torch.testing.assert_close(stats[:, 0].cpu(), mean_ref, rtol=0, atol=2e-3)
+    torch.testing.assert_close(stats[:, 1].cpu(), torch.rsqrt(var_ref + 1e-5), rtol=2e-3, atol=0)
+    # consumer: y = act(LN(x1) W^T + b) from the bf16 x1 and the statistics above
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    w = torch.randn(cout, 256, generator=g) / 16
+    bias = torch.randn(cout, generator=g) * 0.2
+    wp = (w * gamma[None, :]).to(torch.bfloat16)
+    c, d = wp.float().sum(1), w @ beta + bias
+    wpd, cd, dd = wp.to(dev), c.to(dev), d.to(dev)
+    y = torch.full((rows, cout), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_linear(x1.data_ptr(), rows, 256, wpd.data_ptr(), cd.data_ptr(), dd.data_ptr(), act, None,
+                        y.data_ptr(), cout, stats.data_ptr(), None, _stream()), "hgr_linear stats_in")
+    torch.cuda.synchronize()
+    ref = _act(F.linear(F.layer_norm(x1.float().cpu(), (256,), gamma, beta, 1e-5), w, bias), act)
+    r, m = report(f"folded-LN consumer rows={rows} cout={cout} act={act}", y, ref)
+    assert r <= 6e-3 and m <= 2 * MAX_TOL  # W' = bf16(gamma*W) and the cancellation add about one more bf16 ulp
+    del packing
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
