@@ -164,12 +164,21 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       // the TMA store that last read this buffer must be done
       if (gtid == 0) tma_store_wait_read<NBUF - 1>();
       bar_sync(bar_id, 128);
+      // Pull the whole 64-column chunk out of TMEM first; on the last chunk the accumulator stage goes back to
+      // the MMA warp BEFORE the arithmetic, so the tensor core restarts on this stage while the values are
+      // still being activated and stored (for BN = 64 that is right after one TMEM round trip).
+      uint32_t acc_all[64];
+      tmem_ld_32x32b_x32(t_row + j * 64, acc_all);
+      tmem_ld_32x32b_x32(t_row + j * 64 + 32, acc_all + 32);
+      tmem_ld_wait();
+      if (j == BN / 64 - 1) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty_bar[group]);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int c0 = j * 64 + half * 32;  // column inside the tile
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_row + c0, acc);
-        tmem_ld_wait();
+        const uint32_t* acc = acc_all + half * 32;
         const float4* sc4 = reinterpret_cast<const float4*>(s_scale + noff + c0);
         const float4* sh4 = reinterpret_cast<const float4*>(s_shift + noff + c0);
         uint32_t packed[16];
@@ -215,11 +224,6 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
           *reinterpret_cast<uint4*>(buf + row * 128 + chunk * 16) =
               make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
         }
-      }
-      if (j == BN / 64 - 1) {
-        // every TMEM read of this accumulator stage is complete: hand it back
-        tc_fence_before();
-        mbar_arrive(&acc_empty_bar[group]);
       }
       fence_proxy_async_smem();
       bar_sync(bar_id, 128);

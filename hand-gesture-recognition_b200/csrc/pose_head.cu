@@ -5,13 +5,21 @@
 //
 // The reference materialises the up-sampled (256, 4F, 4F) tensor in HBM
 // (590 K elements per image at 192x192) and reads it back for the conv.  Here
-// a CTA owns 8 output rows of one image: it interpolates vertically once into
-// shared memory (fp32), and each warp then builds its MMA A-fragments on the
-// fly by interpolating horizontally, applying ReLU and rounding to bf16 - the
-// up-sampled tensor never exists.  The contraction (M = pixels, N = J padded
-// to 24, K = 256) runs on mma.sync m16n8k16; at 0.6 % of the network's FLOPs
-// and N = 21 it cannot fill a tcgen05 tile.  Heatmaps are written NCHW, the
-// layout get_max_preds and the reference's callers expect.
+// a CTA owns 4 output rows of one image: it pulls the (at most 3) token rows
+// they depend on into shared memory with one burst of cp.async.  Phase A interpolates VERTICALLY in
+// fp32 and leaves, per (row, token column, channel pair), the value a = v(x)
+// and the horizontal slope d = v(x+1) - v(x) as bf16x2 in shared memory.
+// Phase B builds the MMA A-fragments on the fly: one 128-bit shared load and
+// two fma.rn.relu.bf16x2 (a + w*d, ReLU fused) give a pixel's four channels of
+// a k-step, already in fragment layout - the up-sampled tensor never exists.
+// The contraction (M = pixels, N = J padded to 24, K = 256) runs on mma.sync
+// m16n8k16; at 0.6 % of the network's FLOPs and N = 21 it cannot fill a
+// tcgen05 tile.  The MMA's k index is only a summation index, so inside each
+// 16-channel block fragment slot k = 2t + e + 8*hf is bound to channel
+// 4t + 2*hf + e (for A and W alike): a thread's four channels are then
+// contiguous and every fragment is one conflict-free vector load.
+// Heatmaps are written NCHW, the layout get_max_preds and the reference's
+// callers expect.
 #include "hgr_internal.h"
 #include "ptx.cuh"
 
@@ -20,10 +28,11 @@ namespace hgr {
 namespace {
 
 constexpr int kDim = 256;
-constexpr int kRows = 8;        // output rows per CTA
-constexpr int kWarps = 8;
-constexpr int kVPitch = kDim + 8;   // fp32 words per (row, x) line of the vertical-interp buffer
-constexpr int kWPitch = kDim + 8;   // bf16 elements per weight row
+constexpr int kRows = 4;   // output rows per CTA
+constexpr int kWarps = 6;
+constexpr int kTokRows = 3;  // token rows a 4-row output band can touch: floor(s*oy0) .. floor(s*(oy0+3)) + 1
+constexpr int kVPitch = kDim * 4 + 32;  // bytes per (row, token column): 128 channel pairs x (a, d) bf16x2 + pad
+constexpr int kWPitch = kDim + 16;      // bf16 elements per weight row (544 B: two conflict-free wavefronts per LDS.64)
 constexpr int kJPad = 24;
 
 template <typename TOut>
@@ -37,13 +46,21 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
   *p = __float2bfloat16_rn(v);
 }
 
-template <typename TOut>
+// relu(a + w * d) on two bf16 lanes
+__device__ __forceinline__ uint32_t fma_relu_bf16x2(uint32_t w, uint32_t d, uint32_t a) {
+  uint32_t r;
+  asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(d), "r"(a));
+  return r;
+}
+
+template <typename TOut, int F>
 __global__ void __launch_bounds__(kWarps * 32)
 pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* __restrict__ w,
-                 const float* __restrict__ bias, TOut* __restrict__ heat, int F, int J) {
+                 const float* __restrict__ bias, TOut* __restrict__ heat, int J) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* vbuf = reinterpret_cast<float*>(smem_raw);                                   // [kRows][F][kVPitch]
-  __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(vbuf + kRows * F * kVPitch);   // [kJPad][kWPitch]
+  uint8_t* vbuf = smem_raw;                                                          // [kRows][F][kVPitch]
+  __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(vbuf + kRows * F * kVPitch);  // [kJPad][kWPitch], K permuted
+  __nv_bfloat16* stok = sw + kJPad * kWPitch;                                        // [kTokRows][F][kDim]
 
   const int So = 4 * F;
   const int b = blockIdx.y;
@@ -52,74 +69,72 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
   const int g = lane >> 2, t = lane & 3;
   const float scale = (float)(F - 1) / (float)(So - 1);
 
-  // ---- weights -> smem (rows >= J are zero) ------------------------------
+  // ---- the token rows this band interpolates between: one burst of cp.async, a single exposed latency ----
+  const int ty0 = (int)(scale * (float)oy0);
+  const __nv_bfloat16* tok = tokens + ((size_t)b * (F * F + 1) + 1) * kDim;  // skip the class token
+  for (int i = tid; i < kTokRows * F * (kDim / 8); i += kWarps * 32) {
+    const int row = i / (F * (kDim / 8));
+    const int ty = ty0 + row < F ? ty0 + row : F - 1;
+    const int rem = i % (F * (kDim / 8));
+    cp_async_16(stok + (size_t)i * 8, tok + (size_t)ty * F * kDim + rem * 8, 16u);
+  }
+  cp_async_commit();
+
+  // ---- weights -> smem in natural order (rows >= J are zero-filled) ----
   for (int i = tid; i < kJPad * (kDim / 8); i += kWarps * 32) {
     const int j = i / (kDim / 8), c8 = i % (kDim / 8);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (j < J) v = __ldg(reinterpret_cast<const uint4*>(w + (size_t)j * kDim) + c8);
-    *reinterpret_cast<uint4*>(sw + j * kWPitch + c8 * 8) = v;
+    cp_async_16(sw + j * kWPitch + c8 * 8, j < J ? w + (size_t)j * kDim + c8 * 8 : w, j < J ? 16u : 0u);
   }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
 
-  // ---- vertical interpolation of the 8 output rows -----------------------
-  const __nv_bfloat16* tok = tokens + ((size_t)b * (F * F + 1) + 1) * kDim;  // skip the class token
-  const int nitems = kRows * F * (kDim / 8);
-  for (int i0 = tid; i0 < nitems; i0 += 4 * kWarps * 32) {
-    // eight 16-byte requests in flight per thread before the first one is consumed
-    uint4 ua[4], ub[4];
-    float l1v[4];
+  // ---- phase A: vertical interpolation, value + horizontal slope per token column ----
+  for (int i = tid; i < kRows * F * (kDim / 8); i += kWarps * 32) {
+    const int c8 = i % (kDim / 8);
+    const int x = (i / (kDim / 8)) % F;
+    const int r = i / ((kDim / 8) * F);
+    const int x1 = x + (x < F - 1 ? 1 : 0);
+    const float sy = scale * (float)(oy0 + r);
+    const int y0 = (int)sy;
+    const int y1 = y0 + (y0 < F - 1 ? 1 : 0);
+    const float l1 = sy - (float)y0, l0 = 1.0f - l1;
+    const uint4 q00 = *reinterpret_cast<const uint4*>(stok + ((y0 - ty0) * F + x) * kDim + c8 * 8);
+    const uint4 q10 = *reinterpret_cast<const uint4*>(stok + ((y1 - ty0) * F + x) * kDim + c8 * 8);
+    const uint4 q01 = *reinterpret_cast<const uint4*>(stok + ((y0 - ty0) * F + x1) * kDim + c8 * 8);
+    const uint4 q11 = *reinterpret_cast<const uint4*>(stok + ((y1 - ty0) * F + x1) * kDim + c8 * 8);
+    const uint32_t* t00 = reinterpret_cast<const uint32_t*>(&q00);
+    const uint32_t* t10 = reinterpret_cast<const uint32_t*>(&q10);
+    const uint32_t* t01 = reinterpret_cast<const uint32_t*>(&q01);
+    const uint32_t* t11 = reinterpret_cast<const uint32_t*>(&q11);
+    uint32_t ad[8];  // (a, d) for the four channel pairs 4*c8 .. 4*c8+3
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kWarps * 32;
-      const int c8 = i % (kDim / 8);
-      const int x = (i / (kDim / 8)) % F;
-      const int r = i / ((kDim / 8) * F);
-      const float sy = scale * (float)(oy0 + r);
-      const int y0 = (int)sy;
-      const int y1 = y0 + (y0 < F - 1 ? 1 : 0);
-      l1v[u] = sy - (float)y0;
-      ua[u] = ub[u] = make_uint4(0, 0, 0, 0);
-      if (i < nitems) {
-        ua[u] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y0 * F + x) * kDim) + c8);
-        ub[u] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)(y1 * F + x) * kDim) + c8);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float a0 = l0 * bf16_lo(t00[k]) + l1 * bf16_lo(t10[k]);
+      const float a1 = l0 * bf16_hi(t00[k]) + l1 * bf16_hi(t10[k]);
+      const float n0 = l0 * bf16_lo(t01[k]) + l1 * bf16_lo(t11[k]);
+      const float n1 = l0 * bf16_hi(t01[k]) + l1 * bf16_hi(t11[k]);
+      ad[2 * k] = pack_bf16x2(a0, a1);
+      ad[2 * k + 1] = pack_bf16x2(n0 - a0, n1 - a1);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kWarps * 32;
-      if (i >= nitems) break;
-      const int c8 = i % (kDim / 8);
-      const int rx = i / (kDim / 8);  // r * F + x
-      const float l1 = l1v[u], l0 = 1.0f - l1;
-      const uint32_t a[4] = {ua[u].x, ua[u].y, ua[u].z, ua[u].w};
-      const uint32_t bb[4] = {ub[u].x, ub[u].y, ub[u].z, ub[u].w};
-      float o[8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        o[2 * k] = l0 * bf16_lo(a[k]) + l1 * bf16_lo(bb[k]);
-        o[2 * k + 1] = l0 * bf16_hi(a[k]) + l1 * bf16_hi(bb[k]);
-      }
-      float4* dst = reinterpret_cast<float4*>(vbuf + rx * kVPitch + c8 * 8);
-      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-    }
+    uint4* dst = reinterpret_cast<uint4*>(vbuf + (r * F + x) * kVPitch + c8 * 32);
+    dst[0] = make_uint4(ad[0], ad[1], ad[2], ad[3]);
+    dst[1] = make_uint4(ad[4], ad[5], ad[6], ad[7]);
   }
   __syncthreads();
 
+  // ---- phase B: horizontal interpolation + ReLU straight into A fragments, MMA against the weights ----
   const int mt_per_row = So >> 4;
   const int mtiles = kRows * mt_per_row;
   for (int mt = warp; mt < mtiles; mt += kWarps) {
     const int r = mt / mt_per_row;
     const int ox0 = (mt % mt_per_row) << 4;
-    // horizontal source positions of this thread's two pixels
-    const float sx0 = scale * (float)(ox0 + g), sx1 = scale * (float)(ox0 + g + 8);
-    const int xa0 = (int)sx0, xb0 = (int)sx1;
-    const int xa1 = xa0 + (xa0 < F - 1 ? 1 : 0), xb1 = xb0 + (xb0 < F - 1 ? 1 : 0);
-    const float wa1 = sx0 - (float)xa0, wa0 = 1.0f - wa1;
-    const float wb1 = sx1 - (float)xb0, wb0 = 1.0f - wb1;
-    const float* va0 = vbuf + (r * F + xa0) * kVPitch + 2 * t;
-    const float* va1 = vbuf + (r * F + xa1) * kVPitch + 2 * t;
-    const float* vb0 = vbuf + (r * F + xb0) * kVPitch + 2 * t;
-    const float* vb1 = vbuf + (r * F + xb1) * kVPitch + 2 * t;
+    const float sxa = scale * (float)(ox0 + g), sxb = scale * (float)(ox0 + g + 8);
+    const int xa = (int)sxa, xb = (int)sxb;
+    const float wa = sxa - (float)xa, wb = sxb - (float)xb;
+    const uint32_t wa2 = pack_bf16x2(wa, wa), wb2 = pack_bf16x2(wb, wb);
+    const uint8_t* pa = vbuf + (r * F + xa) * kVPitch + t * 16;
+    const uint8_t* pb = vbuf + (r * F + xb) * kVPitch + t * 16;
 
     float acc[3][4];
 #pragma unroll
@@ -127,23 +142,18 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
 
 #pragma unroll 4
     for (int ks = 0; ks < kDim / 16; ++ks) {
+      // (a, d) of channel pairs (2t, 2t+1) and (2t+8, 2t+9) for both pixels
+      const uint4 va = *reinterpret_cast<const uint4*>(pa + ks * 64);
+      const uint4 vb = *reinterpret_cast<const uint4*>(pb + ks * 64);
       uint32_t a[4];
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {  // channel pairs (2t,2t+1) and (2t+8,2t+9) of this k-step
-        const int c = ks * 16 + hf * 8;
-        const float2 p00 = *reinterpret_cast<const float2*>(va0 + c);
-        const float2 p01 = *reinterpret_cast<const float2*>(va1 + c);
-        const float2 p10 = *reinterpret_cast<const float2*>(vb0 + c);
-        const float2 p11 = *reinterpret_cast<const float2*>(vb1 + c);
-        a[2 * hf] = pack_bf16x2(fmaxf(wa0 * p00.x + wa1 * p01.x, 0.f), fmaxf(wa0 * p00.y + wa1 * p01.y, 0.f));
-        a[2 * hf + 1] = pack_bf16x2(fmaxf(wb0 * p10.x + wb1 * p11.x, 0.f), fmaxf(wb0 * p10.y + wb1 * p11.y, 0.f));
-      }
+      a[0] = fma_relu_bf16x2(wa2, va.y, va.x);  // row g,   slots 2t, 2t+1   = channels 4t, 4t+1
+      a[1] = fma_relu_bf16x2(wb2, vb.y, vb.x);  // row g+8
+      a[2] = fma_relu_bf16x2(wa2, va.w, va.z);  // row g,   slots 2t+8, 2t+9 = channels 4t+2, 4t+3
+      a[3] = fma_relu_bf16x2(wb2, vb.w, vb.z);  // row g+8
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
-        const __nv_bfloat16* wr = sw + (nt * 8 + g) * kWPitch + ks * 16 + 2 * t;
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-        mma_bf16_16816(acc[nt], a, b0, b1);
+        const uint2 bw = *reinterpret_cast<const uint2*>(sw + (nt * 8 + g) * kWPitch + ks * 16 + 4 * t);
+        mma_bf16_16816(acc[nt], a, bw.x, bw.y);
       }
     }
     // ---- NCHW store: for one joint, lanes g = 0..7 cover 8 consecutive pixels ----
@@ -164,33 +174,45 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
   }
 }
 
+template <typename TOut, int F>
+int launch_pose_impl(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const float* bias, TOut* heat, int B, int J,
+                     cudaStream_t stream) {
+  constexpr size_t smem = (size_t)kRows * F * kVPitch + (size_t)kJPad * kWPitch * 2 + (size_t)kTokRows * F * kDim * 2;
+  static_assert(smem <= 227 * 1024, "feature side does not fit shared memory");
+  HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_kernel<TOut, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(4 * F / kRows, B);
+  pose_head_kernel<TOut, F><<<grid, kWarps * 32, smem, stream>>>(tokens, w, bias, heat, J);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename TOut>
+int launch_pose_f(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const float* bias, TOut* heat, int B, int F,
+                  int J, cudaStream_t stream) {
+  // the feature side is a compile-time constant (no integer divisions in the staging loops): 64..512-pixel inputs
+  switch (F) {
+    case 4: return launch_pose_impl<TOut, 4>(tokens, w, bias, heat, B, J, stream);
+    case 8: return launch_pose_impl<TOut, 8>(tokens, w, bias, heat, B, J, stream);
+    case 12: return launch_pose_impl<TOut, 12>(tokens, w, bias, heat, B, J, stream);
+    case 16: return launch_pose_impl<TOut, 16>(tokens, w, bias, heat, B, J, stream);
+    case 20: return launch_pose_impl<TOut, 20>(tokens, w, bias, heat, B, J, stream);
+    case 24: return launch_pose_impl<TOut, 24>(tokens, w, bias, heat, B, J, stream);
+    case 28: return launch_pose_impl<TOut, 28>(tokens, w, bias, heat, B, J, stream);
+    case 32: return launch_pose_impl<TOut, 32>(tokens, w, bias, heat, B, J, stream);
+    default: set_error("pose_head: feature side %d not instantiated (multiples of 4 up to 32)", F); return -1;
+  }
+}
+
 }  // namespace
 
 int launch_pose_head(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const float* bias, void* heatmaps,
                      int out_dtype, int B, int F, int J, cudaStream_t stream) {
-  if (J > kJPad || (4 * F) % 16 != 0 || (4 * F) % kRows != 0) {
-    set_error("pose_head: unsupported J=%d F=%d", J, F);
+  if (J > kJPad || J < 1) {
+    set_error("pose_head: unsupported J=%d", J);
     return -1;
   }
-  const size_t smem = (size_t)kRows * F * kVPitch * 4 + (size_t)kJPad * kWPitch * 2;
-  if (smem > 227 * 1024) {
-    set_error("pose_head: feature side %d does not fit shared memory", F);
-    return -1;
-  }
-  dim3 grid(4 * F / kRows, B);
-  if (out_dtype == DT_F32) {
-    HGR_CHECK_CUDA(
-        cudaFuncSetAttribute(pose_head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pose_head_kernel<float>
-        <<<grid, kWarps * 32, smem, stream>>>(tokens, w, bias, static_cast<float*>(heatmaps), F, J);
-  } else {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    pose_head_kernel<__nv_bfloat16>
-        <<<grid, kWarps * 32, smem, stream>>>(tokens, w, bias, static_cast<__nv_bfloat16*>(heatmaps), F, J);
-  }
-  HGR_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  if (out_dtype == DT_F32) return launch_pose_f<float>(tokens, w, bias, static_cast<float*>(heatmaps), B, F, J, stream);
+  return launch_pose_f<__nv_bfloat16>(tokens, w, bias, static_cast<__nv_bfloat16*>(heatmaps), B, F, J, stream);
 }
 
 }  // namespace hgr

@@ -218,7 +218,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane
 // (base_lane + i), columns [col, col+32).
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
