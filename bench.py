@@ -69,6 +69,23 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic_per_launch():
+    """DRAM bytes per launch of the tcgen05 GEMM kernel from the committed `ncu --set full` capture of one step
+    (profiles/*_step_ncu_full.csv: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    import csv
+    files = sorted((ROOT / "profiles").glob("*_step_ncu_full.csv"))
+    if not files:
+        return None, None
+    rows = [r for r in csv.DictReader(files[-1].open()) if "gemm_kernel" in r["Kernel Name"] or "halo" in r["Kernel Name"]]
+    if not rows:
+        return None, None
+    rd = [k for k in rows[0] if k.startswith("dram__bytes_read.sum")][0]
+    wr = [k for k in rows[0] if k.startswith("dram__bytes_write.sum")][0]
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[rd.split("[")[1].rstrip("]")]
+    total = sum(float(r[rd]) + float(r[wr]) for r in rows) * unit
+    return total / len(rows), files[-1].name
+
+
 def synthetic_weights(model, seed=0):
     """He-scaled conv/linear weights and non-trivial BN statistics, so activations stay O(1) through the net."""
     import torch
@@ -294,8 +311,13 @@ def main():
         gem = [(fl, t) for (name, kind, fl, by), t in zip(info, ms) if kind == 0]
         g_fl, g_ms = sum(f for f, _ in gem), sum(t for _, t in gem)
         ach = g_fl / (g_ms * 1e-3) / 1e12
+        traffic, traffic_src = ncu_traffic_per_launch() if (B, S) == (1024, 192) else (None, None)
+        g_by = sum(by for (name, kind, fl, by) in info if kind == 0)
         roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_sustained"], "traffic": None,
+                    "frac": ach / pk["bf16_sustained"], "traffic": traffic,
+                    "traffic_source": (f"profiles/{traffic_src}: dram__bytes_read.sum + dram__bytes_write.sum, bytes per "
+                                       "launch averaged over the GEMM launches of one step") if traffic else None,
+                    "algorithmic_bytes_per_launch_avg": g_by / len(gem),
                     "kernel": f"hgr::gemm_kernel<BN> (tcgen05 implicit GEMM), {len(gem)} launches per step",
                     "share_of_step": g_ms / step_ms, "launch_ms_avg": g_ms / len(gem),
                     "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",

@@ -82,6 +82,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // ---- stage Q, K, V (zero rows beyond T) --------------------------------
   const __nv_bfloat16* base = qkv + (size_t)b * T * (3 * kHeads * kHd) + h * kHd;
@@ -196,14 +198,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 template <typename TP, int NKB>
 __global__ void __launch_bounds__(kWarps * 32, 3)
 attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, TP* __restrict__ probs,
-                       int T, float scale_log2e) {
+                       int T, float scale_log2e, int reverse) {
   constexpr int Tp = NKB * kKeyBlock;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sk = sq + Tp * kPitch;
   __nv_bfloat16* sv = sk + Tp * kPitch;
 
-  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int bid = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int b = bid / kHeads, h = bid % kHeads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
@@ -325,7 +330,7 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int reverse) {
   const int Tp = (T + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
   const size_t smem = (size_t)3 * Tp * kPitch * 2;
   if (smem > 227 * 1024) {
@@ -338,26 +343,24 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   if (T <= 5 * kKeyBlock && T > 4 * kKeyBlock) {
     const size_t smem1 = (size_t)3 * 5 * kKeyBlock * kPitch * 2;
     if (attn_probs != nullptr && probs_dtype == DT_BF16)
-      attention_kernel_1pass<__nv_bfloat16, 5><<<grid, kWarps * 32, smem1, stream>>>(
-          qkv, out, static_cast<__nv_bfloat16*>(attn_probs), T, scale_log2e);
+      HGR_CHECK_CUDA(launch_pdl(attention_kernel_1pass<__nv_bfloat16, 5>, dim3(grid), dim3(kWarps * 32), smem1, stream, qkv,
+                                out, static_cast<__nv_bfloat16*>(attn_probs), T, scale_log2e, reverse));
     else
-      attention_kernel_1pass<float, 5>
-          <<<grid, kWarps * 32, smem1, stream>>>(qkv, out, static_cast<float*>(attn_probs), T, scale_log2e);
-    HGR_CHECK_CUDA(cudaGetLastError());
+      HGR_CHECK_CUDA(launch_pdl(attention_kernel_1pass<float, 5>, dim3(grid), dim3(kWarps * 32), smem1, stream, qkv, out,
+                                static_cast<float*>(attn_probs), T, scale_log2e, reverse));
     return 0;
   }
   if (attn_probs != nullptr && probs_dtype == DT_BF16) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-    attention_kernel<__nv_bfloat16><<<grid, kWarps * 32, smem, stream>>>(
-        qkv, out, static_cast<__nv_bfloat16*>(attn_probs), T, Tp, scale_log2e);
+    HGR_CHECK_CUDA(launch_pdl(attention_kernel<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out,
+                              static_cast<__nv_bfloat16*>(attn_probs), T, Tp, scale_log2e));
   } else {
     HGR_CHECK_CUDA(
         cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_kernel<float>
-        <<<grid, kWarps * 32, smem, stream>>>(qkv, out, static_cast<float*>(attn_probs), T, Tp, scale_log2e);
+    HGR_CHECK_CUDA(launch_pdl(attention_kernel<float>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out,
+                              static_cast<float*>(attn_probs), T, Tp, scale_log2e));
   }
-  HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

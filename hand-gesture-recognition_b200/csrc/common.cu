@@ -1,6 +1,7 @@
 // Error reporting and TMA tensor-map construction for libhgr_b200.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include <cudaTypedefs.h>
@@ -21,6 +22,22 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (v == nullptr || *v == 0) return dflt;
+  return *v != '0';
+}
+
+bool pdl_enabled() {
+  static const bool on = env_flag("HGR_PDL", true);
+  return on;
+}
+
+bool zigzag_enabled() {
+  static const bool on = env_flag("HGR_ZIGZAG", true);
+  return on;
+}
 
 namespace {
 

@@ -86,6 +86,8 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const TIn* xb = x + (size_t)b * 3 * S * S;
+  pdl_launch_dependents();
+  pdl_wait();
 
   stage_patch<TIn>(patch0, xb, rb0, S, pitch, tid);
   cp_async_commit();
@@ -202,15 +204,14 @@ int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bflo
   dim3 grid(splits, B);
   if (x_dtype == DT_F32) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_kernel<float>
-        <<<grid, kWarps * 32, smem, stream>>>(static_cast<const float*>(x), out, w, shift, S, blocks / splits);
+    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<float>, grid, dim3(kWarps * 32), smem, stream, static_cast<const float*>(x), out, w,
+                              shift, S, blocks / splits));
   } else {
     HGR_CHECK_CUDA(
         cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_kernel<__nv_bfloat16><<<grid, kWarps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(x), out, w,
-                                                                    shift, S, blocks / splits);
+    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<__nv_bfloat16>, grid, dim3(kWarps * 32), smem, stream,
+                              static_cast<const __nv_bfloat16*>(x), out, w, shift, S, blocks / splits));
   }
-  HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -82,7 +82,9 @@ __device__ __forceinline__ float apply_act(float v) {
 // tile index -> pixel-box origin and output-channel offset
 struct TileMap {
   int tiles_w, tiles_h, tiles_nout, bw, bh, bimg, bn;
+  int last;  // >= 0: walk the grid back to front (tile -> last - tile)
   __device__ __forceinline__ void coords(int tile, int& w0, int& h0, int& n0, int& noff) const {
+    if (last >= 0) tile = last - tile;
     const int nt = tile % tiles_nout;
     int mt = tile / tiles_nout;
     const int tw = mt % tiles_w;
@@ -303,6 +305,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above touched only parameters; from here on the previous kernel's output is read
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = tiles_m * p.tiles_nout;
@@ -310,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
   const int bimg = kTileM >> (p.bw_log2 + p.bh_log2);
 
-  const TileMap tm{p.tiles_w, p.tiles_h, p.tiles_nout, bw, bh, bimg, BN};
+  const TileMap tm{p.tiles_w, p.tiles_h, p.tiles_nout, bw, bh, bimg, BN, p.reverse ? total_tiles - 1 : -1};
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -466,9 +471,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above touched only parameters; from here on the previous kernel's output is read
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN};
+  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN, p.reverse ? total_tiles - 1 : -1};
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -551,8 +559,8 @@ int launch_halo_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n;
   const int grid = total < num_sms ? total : num_sms;
-  conv3x3_halo_kernel<ACT, RES><<<grid, kThreads, HaloCfg::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
-  HGR_CHECK_CUDA(cudaGetLastError());
+  HGR_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<ACT, RES>, dim3(grid), dim3(kThreads), HaloCfg::kSmemBytes, stream, tmA, tmW,
+                            tmO, p));
   return 0;
 }
 
@@ -568,8 +576,8 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMa
   }
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nout;
   const int grid = total < num_sms ? total : num_sms;
-  gemm_kernel<BN, ACT, RES, ROW><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmW, tmO, p);
-  HGR_CHECK_CUDA(cudaGetLastError());
+  HGR_CHECK_CUDA(launch_pdl(gemm_kernel<BN, ACT, RES, ROW>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, tmA, tmW, tmO,
+                            p));
   return 0;
 }
 

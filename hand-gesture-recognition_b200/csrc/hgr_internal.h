@@ -22,6 +22,32 @@ const char* last_error();
     }                                                                                         \
   } while (0)
 
+// ---------------------------------------------------------- launch ----
+// Programmatic dependent launch: the kernel may be scheduled while the previous kernel of the
+// stream drains, so its prologue (barrier init, TMEM allocation, tensor-map prefetch, affine
+// tables) and the launch latency overlap the predecessor's tail.  Every kernel launched this way
+// executes griddepcontrol.wait (ptx.cuh: pdl_wait) before it touches memory another kernel wrote.
+// HGR_PDL=0 in the environment falls back to plain stream-ordered launches.
+bool pdl_enabled();
+// HGR_ZIGZAG=0 disables the alternating tile order of plan.cu.
+bool zigzag_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------- implicit-GEMM conv / linear ----
 //
 // One launch computes   OUT[pix, n] = act( scale[n] * sum_k A[pix, k] W[n, k] + shift[n] (+ RES[pix, n]) )
@@ -46,6 +72,7 @@ struct GemmParams {
   int out_w_off;         // extra w offset of the OUT box (token assembly writes at +1)
   int cout;              // channels produced by this layer (length of scale/shift)
   int act;
+  int reverse;           // walk the tile grid back to front (see plan.cu: zig-zag order for L2 reuse)
   const float* scale;  // nullable: 1
   const float* shift;  // nullable: 0
   const __nv_bfloat16* res;  // nullable; element strides below
@@ -84,8 +111,9 @@ int launch_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamm
 int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, const float* cls_stats, float* row_stats, int B, int T,
                     cudaStream_t stream);
 
+// reverse: walk the (image, head) grid back to front (zig-zag order, see plan.cu)
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int reverse = 0);
 
 int launch_cls_head(const __nv_bfloat16* tokens, const float* gamma, const float* beta, const float* w /*[C][256]*/,
                     const float* bias, void* logits, int out_dtype, int B, int T, int num_classes,

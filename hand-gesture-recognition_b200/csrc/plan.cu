@@ -667,7 +667,15 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
                  std::function<int(cudaStream_t, const Io&)> fn) {
     pl->steps.push_back({name, kind, flops, bytes, std::move(fn)});
   };
-  auto add_gemm = [&](const std::string& name, const GemmOp* op) {
+  // Zig-zag tile order: every activation buffer of a batch-1024 step is larger than the L2, so a consumer
+  // that walks its tile grid in the producer's order starts on the lines that were evicted first.  Alternating
+  // the direction from launch to launch makes each kernel begin with what the previous one wrote last, which
+  // is still L2-resident.  (HGR_ZIGZAG=0 keeps every launch front to back.)
+  const bool zig = zigzag_enabled();
+  int dir = 0;  // direction of the previous launch; conv1 runs front to back
+  auto add_gemm = [&](const std::string& name, GemmOp* op) {
+    dir = zig ? !dir : 0;
+    op->p.reverse = dir;
     add(name, 0, op->flops, op->bytes, [op](cudaStream_t st, const Io&) { return run_op(*op, st); });
   };
   const int T = pl->T;
@@ -689,9 +697,12 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
     const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
     add_gemm(a + "norm+to_qkv", &pl->qkv[l]);
     const bool last = l == kDepth - 1;
+    dir = zig ? !dir : 0;
+    const int attn_dir = dir;
     add(a + "attention", 1, 4.0 * dB * kHeads * T * T * 32, (double)rows * kDim * 2 * 4,
-        [pl, B, T, last](cudaStream_t st, const Io& io) {
-          return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st);
+        [pl, B, T, last, attn_dir](cudaStream_t st, const Io& io) {
+          return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st,
+                                  attn_dir);
         });
     add_gemm(a + "to_out+residual", &pl->out[l]);
     add_gemm(f + "0+1+gelu", &pl->ff1[l]);

@@ -68,6 +68,8 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const float scale = (float)(F - 1) / (float)(So - 1);
+  pdl_launch_dependents();
+  pdl_wait();
 
   // ---- the token rows this band interpolates between: one burst of cp.async, a single exposed latency ----
   const int ty0 = (int)(scale * (float)oy0);
@@ -181,8 +183,7 @@ int launch_pose_impl(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const 
   static_assert(smem <= 227 * 1024, "feature side does not fit shared memory");
   HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_kernel<TOut, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(4 * F / kRows, B);
-  pose_head_kernel<TOut, F><<<grid, kWarps * 32, smem, stream>>>(tokens, w, bias, heat, J);
-  HGR_CHECK_CUDA(cudaGetLastError());
+  HGR_CHECK_CUDA(launch_pdl(pose_head_kernel<TOut, F>, grid, dim3(kWarps * 32), smem, stream, tokens, w, bias, heat, J));
   return 0;
 }
 

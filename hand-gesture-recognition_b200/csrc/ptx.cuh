@@ -38,6 +38,15 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ------------------------------------- programmatic dependent launch ----
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl in
+// hgr_internal.h) may start while the previous kernel of the stream is still draining:
+// pdl_launch_dependents() lets the next grid be scheduled as soon as every CTA of this one has
+// passed it, pdl_wait() blocks until the previous grid has completed and its writes are visible.
+// Both are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------ mbarrier ----
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

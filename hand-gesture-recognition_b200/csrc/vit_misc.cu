@@ -73,6 +73,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict_
 
 __global__ void fill_cls_kernel(__nv_bfloat16* __restrict__ tokens, const float* __restrict__ cls,
                                 const float* __restrict__ cls_stats, float* __restrict__ row_stats, int B, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kDim) return;
   const int b = i / kDim, c = i % kDim;
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(256)
 cls_head_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ w, const float* __restrict__ bias,
                 TOut* __restrict__ logits, int B, int T, int num_classes) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -121,8 +125,8 @@ int launch_layernorm(const __nv_bfloat16* x, __nv_bfloat16* y, const float* gamm
 int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, const float* cls_stats, float* row_stats, int B, int T,
                     cudaStream_t stream) {
   const int n = B * kDim;
-  fill_cls_kernel<<<(n + 255) / 256, 256, 0, stream>>>(tokens, cls, cls_stats, row_stats, B, T);
-  HGR_CHECK_CUDA(cudaGetLastError());
+  HGR_CHECK_CUDA(launch_pdl(fill_cls_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, tokens, cls, cls_stats, row_stats,
+                            B, T));
   return 0;
 }
 
@@ -131,12 +135,11 @@ int launch_cls_head(const __nv_bfloat16* tokens, const float* gamma, const float
                     cudaStream_t stream) {
   const int blocks = (B + 7) / 8;
   if (out_dtype == DT_F32)
-    cls_head_kernel<float><<<blocks, 256, 0, stream>>>(tokens, gamma, beta, w, bias, static_cast<float*>(logits), B, T,
-                                                        num_classes);
+    HGR_CHECK_CUDA(launch_pdl(cls_head_kernel<float>, dim3(blocks), dim3(256), 0, stream, tokens, gamma, beta, w, bias,
+                              static_cast<float*>(logits), B, T, num_classes));
   else
-    cls_head_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(tokens, gamma, beta, w, bias,
-                                                                static_cast<__nv_bfloat16*>(logits), B, T, num_classes);
-  HGR_CHECK_CUDA(cudaGetLastError());
+    HGR_CHECK_CUDA(launch_pdl(cls_head_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, stream, tokens, gamma, beta, w, bias,
+                              static_cast<__nv_bfloat16*>(logits), B, T, num_classes));
   return 0;
 }
 
