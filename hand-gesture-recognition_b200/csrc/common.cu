@@ -30,7 +30,7 @@ static bool env_flag(const char* name, bool dflt) {
 }
 
 bool pdl_enabled() {
-  static const bool on = env_flag("HGR_PDL", true);
+  static const bool on = env_flag("HGR_PDL", false);
   return on;
 }
 

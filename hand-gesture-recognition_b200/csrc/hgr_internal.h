@@ -27,7 +27,9 @@ const char* last_error();
 // stream drains, so its prologue (barrier init, TMEM allocation, tensor-map prefetch, affine
 // tables) and the launch latency overlap the predecessor's tail.  Every kernel launched this way
 // executes griddepcontrol.wait (ptx.cuh: pdl_wait) before it touches memory another kernel wrote.
-// HGR_PDL=0 in the environment falls back to plain stream-ordered launches.
+// Measured on B200 (gpurun r1n, batch 1024): 7.06 ms/step with it against 6.88 ms without - the early-scheduled
+// CTAs of the next grid take the SM slots the persistent kernels' stragglers are about to free and gain nothing
+// back - so it is OFF by default; HGR_PDL=1 in the environment turns it on.
 bool pdl_enabled();
 // HGR_ZIGZAG=0 disables the alternating tile order of plan.cu.
 bool zigzag_enabled();

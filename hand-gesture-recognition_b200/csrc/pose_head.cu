@@ -31,7 +31,8 @@ constexpr int kDim = 256;
 constexpr int kRows = 4;   // output rows per CTA
 constexpr int kWarps = 6;
 constexpr int kTokRows = 3;  // token rows a 4-row output band can touch: floor(s*oy0) .. floor(s*(oy0+3)) + 1
-constexpr int kVPitch = kDim * 4 + 32;  // bytes per (row, token column): 128 channel pairs x (a, d) bf16x2 + pad
+constexpr int kVPitch = kDim * 4 + 64;  // bytes per (row, token column): 128 channel pairs x (a, d) bf16x2; pitch = 64 (mod 128) so that
+                                        // the two token columns a quarter-warp touches in phase B land in disjoint banks
 constexpr int kWPitch = kDim + 16;      // bf16 elements per weight row (544 B: two conflict-free wavefronts per LDS.64)
 constexpr int kJPad = 24;
 
@@ -119,57 +120,85 @@ pose_head_kernel(const __nv_bfloat16* __restrict__ tokens, const __nv_bfloat16* 
       ad[2 * k] = pack_bf16x2(a0, a1);
       ad[2 * k + 1] = pack_bf16x2(n0 - a0, n1 - a1);
     }
+    // a lane owns 32 contiguous bytes; which 16-byte half goes first alternates so that the eight lanes of a
+    // store phase cover all 32 banks exactly once
     uint4* dst = reinterpret_cast<uint4*>(vbuf + (r * F + x) * kVPitch + c8 * 32);
-    dst[0] = make_uint4(ad[0], ad[1], ad[2], ad[3]);
-    dst[1] = make_uint4(ad[4], ad[5], ad[6], ad[7]);
+    const int hsel = (lane ^ (lane >> 2)) & 1;
+    const uint4 lo = make_uint4(ad[0], ad[1], ad[2], ad[3]), hi = make_uint4(ad[4], ad[5], ad[6], ad[7]);
+    dst[hsel] = hsel ? hi : lo;
+    dst[hsel ^ 1] = hsel ? lo : hi;
   }
   __syncthreads();
 
   // ---- phase B: horizontal interpolation + ReLU straight into A fragments, MMA against the weights ----
+  // Two 16-pixel m-tiles per warp and pass (tile u of the pass sits kWarps tiles further): they share every
+  // weight-fragment load, which is 40 % of the shared-memory wavefronts of a single-tile loop.
   const int mt_per_row = So >> 4;
   const int mtiles = kRows * mt_per_row;
-  for (int mt = warp; mt < mtiles; mt += kWarps) {
-    const int r = mt / mt_per_row;
-    const int ox0 = (mt % mt_per_row) << 4;
-    const float sxa = scale * (float)(ox0 + g), sxb = scale * (float)(ox0 + g + 8);
-    const int xa = (int)sxa, xb = (int)sxb;
-    const float wa = sxa - (float)xa, wb = sxb - (float)xb;
-    const uint32_t wa2 = pack_bf16x2(wa, wa), wb2 = pack_bf16x2(wb, wb);
-    const uint8_t* pa = vbuf + (r * F + xa) * kVPitch + t * 16;
-    const uint8_t* pb = vbuf + (r * F + xb) * kVPitch + t * 16;
-
-    float acc[3][4];
+  for (int mt0 = warp; mt0 < mtiles; mt0 += 2 * kWarps) {
+    const uint8_t* pa[2];
+    const uint8_t* pb[2];
+    uint32_t wa2[2], wb2[2];
+    int rr[2], oxs[2];
+    bool on[2];
 #pragma unroll
-    for (int nt = 0; nt < 3; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const int mt = mt0 + u * kWarps;
+      on[u] = mt < mtiles;
+      const int mtc = on[u] ? mt : mt0;
+      rr[u] = mtc / mt_per_row;
+      oxs[u] = (mtc % mt_per_row) << 4;
+      const float sxa = scale * (float)(oxs[u] + g), sxb = scale * (float)(oxs[u] + g + 8);
+      const int xa = (int)sxa, xb = (int)sxb;
+      const float wa = sxa - (float)xa, wb = sxb - (float)xb;
+      wa2[u] = pack_bf16x2(wa, wa);
+      wb2[u] = pack_bf16x2(wb, wb);
+      pa[u] = vbuf + (rr[u] * F + xa) * kVPitch + t * 16;
+      pb[u] = vbuf + (rr[u] * F + xb) * kVPitch + t * 16;
+    }
+
+    float acc[2][3][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) acc[u][nt][0] = acc[u][nt][1] = acc[u][nt][2] = acc[u][nt][3] = 0.f;
 
 #pragma unroll 4
     for (int ks = 0; ks < kDim / 16; ++ks) {
-      // (a, d) of channel pairs (2t, 2t+1) and (2t+8, 2t+9) for both pixels
-      const uint4 va = *reinterpret_cast<const uint4*>(pa + ks * 64);
-      const uint4 vb = *reinterpret_cast<const uint4*>(pb + ks * 64);
-      uint32_t a[4];
-      a[0] = fma_relu_bf16x2(wa2, va.y, va.x);  // row g,   slots 2t, 2t+1   = channels 4t, 4t+1
-      a[1] = fma_relu_bf16x2(wb2, vb.y, vb.x);  // row g+8
-      a[2] = fma_relu_bf16x2(wa2, va.w, va.z);  // row g,   slots 2t+8, 2t+9 = channels 4t+2, 4t+3
-      a[3] = fma_relu_bf16x2(wb2, vb.w, vb.z);  // row g+8
+      uint32_t a[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        // (a, d) of channel pairs (2t, 2t+1) and (2t+8, 2t+9) for both pixels
+        const uint4 va = *reinterpret_cast<const uint4*>(pa[u] + ks * 64);
+        const uint4 vb = *reinterpret_cast<const uint4*>(pb[u] + ks * 64);
+        a[u][0] = fma_relu_bf16x2(wa2[u], va.y, va.x);  // row g,   slots 2t, 2t+1   = channels 4t, 4t+1
+        a[u][1] = fma_relu_bf16x2(wb2[u], vb.y, vb.x);  // row g+8
+        a[u][2] = fma_relu_bf16x2(wa2[u], va.w, va.z);  // row g,   slots 2t+8, 2t+9 = channels 4t+2, 4t+3
+        a[u][3] = fma_relu_bf16x2(wb2[u], vb.w, vb.z);  // row g+8
+      }
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
         const uint2 bw = *reinterpret_cast<const uint2*>(sw + (nt * 8 + g) * kWPitch + ks * 16 + 4 * t);
-        mma_bf16_16816(acc[nt], a, bw.x, bw.y);
+        mma_bf16_16816(acc[0][nt], a[0], bw.x, bw.y);
+        mma_bf16_16816(acc[1][nt], a[1], bw.x, bw.y);
       }
     }
     // ---- NCHW store: for one joint, lanes g = 0..7 cover 8 consecutive pixels ----
-    const int oy = oy0 + r;
 #pragma unroll
-    for (int nt = 0; nt < 3; ++nt) {
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) continue;
+      const int oy = oy0 + rr[u];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = nt * 8 + 2 * t + e;
-        if (j < J) {
-          const float bj = bias[j];
-          TOut* dst = heat + (((size_t)b * J + j) * So + oy) * So + ox0 + g;
-          store_out<TOut>(dst, acc[nt][e] + bj);
-          store_out<TOut>(dst + 8, acc[nt][2 + e] + bj);
+      for (int nt = 0; nt < 3; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          if (j < J) {
+            const float bj = bias[j];
+            TOut* dst = heat + (((size_t)b * J + j) * So + oy) * So + oxs[u] + g;
+            store_out<TOut>(dst, acc[u][nt][e] + bj);
+            store_out<TOut>(dst + 8, acc[u][nt][2 + e] + bj);
+          }
         }
       }
     }
