@@ -70,7 +70,9 @@ __device__ __forceinline__ void stage_patch(__nv_bfloat16* patch, const TIn* xb,
 // w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale already folded in, k>=27 zero.
 // grid = (splits, B): a CTA walks `nrb` consecutive 8-row blocks of one image with two patch buffers, so the
 // copy of block i+1 overlaps the MMAs and the stores of block i.
-template <typename TIn>
+// RAW = true (training): the un-normalised convolution output is written (batch-statistics BatchNorm follows
+// as separate kernels), `shift` is ignored.
+template <typename TIn, bool RAW = false>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
              const float* __restrict__ shift, int S, int nrb) {
@@ -106,8 +108,8 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
   float sh[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    sh[nt][0] = 0.5f * __ldg(shift + nt * 8 + 2 * t);
-    sh[nt][1] = 0.5f * __ldg(shift + nt * 8 + 2 * t + 1);
+    sh[nt][0] = RAW ? 0.f : 0.5f * __ldg(shift + nt * 8 + 2 * t);
+    sh[nt][1] = RAW ? 0.f : 0.5f * __ldg(shift + nt * 8 + 2 * t + 1);
   }
   // per-thread gather offsets of its 8 k values: k = 16*s + 2*t + {0,1,8,9}
   int koff[8];
@@ -164,12 +166,17 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
         mma_bf16_16816(d, a[0], bfrag[nt][0][0], bfrag[nt][0][1]);
         mma_bf16_16816(d, a[1], bfrag[nt][1][0], bfrag[nt][1][1]);
         float h[4];
-        h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
-        h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
-        h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
-        h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
+        if constexpr (RAW) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
+          for (int i = 0; i < 4; ++i) h[i] = d[i];
+        } else {
+          h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
+          h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
+          h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
+          h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
+        }
         // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
         *reinterpret_cast<uint32_t*>(st + g * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[0], h[1]);
         *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[2], h[3]);
@@ -191,8 +198,9 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
 
 }  // namespace
 
-int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
-                 int S, cudaStream_t stream) {
+template <bool RAW>
+static int launch_conv1_impl(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift,
+                             int B, int S, cudaStream_t stream) {
   if (S % 32 != 0 || S < 32 || S > 1024) {
     set_error("conv1: image side %d must be a multiple of 32 in [32, 1024]", S);
     return -1;
@@ -203,16 +211,26 @@ int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bflo
   const int splits = blocks % 2 == 0 ? 2 : 1;     // CTAs per image
   dim3 grid(splits, B);
   if (x_dtype == DT_F32) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<float>, grid, dim3(kWarps * 32), smem, stream, static_cast<const float*>(x), out, w,
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_kernel<float, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<float, RAW>, grid, dim3(kWarps * 32), smem, stream, static_cast<const float*>(x), out, w,
                               shift, S, blocks / splits));
   } else {
     HGR_CHECK_CUDA(
-        cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<__nv_bfloat16>, grid, dim3(kWarps * 32), smem, stream,
+        cudaFuncSetAttribute(conv1_kernel<__nv_bfloat16, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HGR_CHECK_CUDA(launch_pdl(conv1_kernel<__nv_bfloat16, RAW>, grid, dim3(kWarps * 32), smem, stream,
                               static_cast<const __nv_bfloat16*>(x), out, w, shift, S, blocks / splits));
   }
   return 0;
+}
+
+int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
+                 int S, cudaStream_t stream) {
+  return launch_conv1_impl<false>(x, x_dtype, out, w, shift, B, S, stream);
+}
+
+int launch_conv1_raw(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, int B, int S,
+                     cudaStream_t stream) {
+  return launch_conv1_impl<true>(x, x_dtype, out, w, nullptr, B, S, stream);
 }
 
 }  // namespace hgr

@@ -1,0 +1,43 @@
+// Implicit-GEMM launch descriptors shared by the inference plan (plan.cu) and the training plan
+// (train_plan.cu): tensor maps + GemmParams + N tile for one conv / linear launch.
+#pragma once
+
+#include "hgr_internal.h"
+
+namespace hgr {
+
+struct GemmOp {
+  CUtensorMap a, w, o;
+  GemmParams p;
+  int bn;
+  bool halo;     // 64->64 3x3 s1 layer on the halo-staging kernel
+  double flops;  // algorithmic: 2 * M * N * K, unpadded
+  double bytes;  // algorithmic: A + W + OUT (+ RES) in bf16
+};
+
+size_t align_up(size_t v, size_t a);
+int device_sm_count();
+
+// Conv / 1x1 / stride-2 layer over NHWC bf16 buffers (weights [Cout][kh][kw][Cin] bf16).
+int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, int in_coff, int cin, const void* wgt,
+                  const float* scale, const float* shift, int k, int s, int act, const void* res, int res_ctot,
+                  int res_coff, void* out, int out_ctot, int out_coff, int cout);
+
+// y = act(x W^T + b) (+ res) over a (rows, cin) matrix.
+int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const void* wgt, const float* scale,
+                    const float* bias, int act, const void* res, void* y, int cout, const float* stats_in = nullptr,
+                    float* stats_out = nullptr);
+
+// proj (1x1 conv 512->256) fused with the token assembly: rows land at token index 1 + p, + position table.
+int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const void* wgt, const void* pe, void* tokens,
+                  int T, float* stats_out);
+
+// One parity class (ph, pw) of the input-gradient of a 3x3 stride-2 convolution (training): reads the
+// output-gradient map dz (B, H/2, W/2, cout_fwd) and writes dx[:, ph::2, pw::2, :cin_fwd] of a (B, H, W, cin_fwd)
+// buffer.  wgt is the per-parity weight block [cin_fwd][ntaps][cout_fwd] bf16 (see train_plan.cu).
+int build_dgrad_s2_op(GemmOp& op, const void* dz, int B, int H, int W, int cout_fwd, const void* wgt, int ph, int pw,
+                      void* dx, int cin_fwd);
+
+int run_op(const GemmOp& op, cudaStream_t stream);
+
+}  // namespace hgr

@@ -8,15 +8,16 @@
 #include <vector>
 
 #include "../../include/hgr_b200.h"
+#include "gemm_ops.h"
 #include "hgr_internal.h"
 
 namespace hgr {
 
 namespace {
-
 constexpr int kDim = 256;
 constexpr int kHeads = 8;
 constexpr int kDepth = 4;
+}  // namespace
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -30,18 +31,7 @@ int device_sm_count() {
   return n;
 }
 
-// ------------------------------------------------------------------------
-// One implicit-GEMM launch: maps + params + N tile.
-// ------------------------------------------------------------------------
-struct GemmOp {
-  CUtensorMap a, w, o;
-  GemmParams p;
-  int bn;
-  bool halo;     // 64->64 3x3 s1 layer on the halo-staging kernel
-  double flops;  // algorithmic: 2 * M * N * K, unpadded
-  double bytes;  // algorithmic: A + W + OUT (+ RES) in bf16
-};
-
+namespace {
 int pick_bn(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
 
 int ilog2(int v) {
@@ -59,6 +49,8 @@ void pick_box(int W, int H, int& bw, int& bh, int& bi) {
   while (bh > 1 && H % bh != 0) bh >>= 1;
   bi = 128 / (bw * bh);
 }
+
+}  // namespace
 
 // Conv / 1x1 / stride-2 layer over NHWC bf16 buffers.
 int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, int in_coff, int cin, const void* wgt,
@@ -173,8 +165,8 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
 
 // y = act(x W^T + b) (+ res) over a (rows, cin) matrix.
 int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const void* wgt, const float* scale,
-                    const float* bias, int act, const void* res, void* y, int cout, const float* stats_in = nullptr,
-                    float* stats_out = nullptr) {
+                    const float* bias, int act, const void* res, void* y, int cout, const float* stats_in,
+                    float* stats_out) {
   if (cin % 64 != 0 || cout % 64 != 0 || rows <= 0 || rows > 0x7fffffffLL) {
     set_error("linear: unsupported shape rows %lld cin %d cout %d", rows, cin, cout);
     return -1;
@@ -288,10 +280,80 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
   return 0;
 }
 
+// Input gradient of a 3x3 stride-2 convolution, one parity class per launch (training, see train_plan.cu).
+// Forward: z[oh, ow] = sum_{kh,kw} W[kh][kw] x[2 oh + kh - 1, 2 ow + kw - 1].  For dx[2i + ph, 2j + pw] only the
+// taps with (ph - kh + 1) even contribute: ph = 0 -> kh = 1 (oh = i); ph = 1 -> kh = 0 (oh = i + 1) and kh = 2
+// (oh = i); the same along w.  That is a 1-, 2-, 2- or 4-tap stride-1 "convolution" of dz whose output lands on
+// the (ph, pw) sub-grid of dx, which a strided TMA store map addresses directly.  Tap order (and therefore
+// the K order of the packed weights): kh-candidates outer, kw-candidates inner, each in the order listed above.
+int build_dgrad_s2_op(GemmOp& op, const void* dz, int B, int H, int W, int cout_fwd, const void* wgt, int ph, int pw,
+                      void* dx, int cin_fwd) {
+  if (cout_fwd % 64 != 0 || cin_fwd % 64 != 0 || (H & 1) || (W & 1) || ph < 0 || ph > 1 || pw < 0 || pw > 1) {
+    set_error("dgrad_s2: unsupported shape (cout %d cin %d %dx%d parity %d,%d)", cout_fwd, cin_fwd, H, W, ph, pw);
+    return -1;
+  }
+  const int Ho = H / 2, Wo = W / 2;
+  int bw, bh, bi;
+  pick_box(Wo, Ho, bw, bh, bi);
+  memset(&op, 0, sizeof(op));
+  op.bn = pick_bn(cin_fwd);
+  GemmParams& p = op.p;
+  const int nh = ph ? 2 : 1, nw = pw ? 2 : 1;
+  p.num_taps = nh * nw;
+  p.chunks_per_tap = cout_fwd / 64;
+  {
+    const uint64_t dims[5] = {(uint64_t)cout_fwd, (uint64_t)Wo, 1, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t row = (uint64_t)cout_fwd * 2;
+    const uint64_t strides[4] = {row, row * Wo, row * Wo, row * Wo * Ho};
+    const uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bi};
+    if (int r = make_tensor_map_bf16(&op.a, dz, 5, dims, strides, box)) return r;
+  }
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) {
+      const int t = a * nw + b;
+      p.tap_dc[t] = 0;
+      p.tap_p[t] = 0;
+      p.tap_dh[t] = (ph && a == 0) ? 1 : 0;
+      p.tap_dw[t] = (pw && b == 0) ? 1 : 0;
+    }
+  {
+    const uint64_t K = (uint64_t)p.num_taps * cout_fwd;
+    const uint64_t dims[2] = {K, (uint64_t)cin_fwd};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cin_fwd, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    const uint64_t pix = (uint64_t)cin_fwd * 2;
+    const uint64_t strides[3] = {2 * pix, 2 * pix * W, pix * W * H};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bi};
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(dx) + ((size_t)ph * W + pw) * cin_fwd;
+    if (int r = make_tensor_map_bf16(&op.o, base, 4, dims, strides, box)) return r;
+  }
+  p.tiles_w = (Wo + bw - 1) / bw;
+  p.tiles_h = (Ho + bh - 1) / bh;
+  p.tiles_n = (B + bi - 1) / bi;
+  p.tiles_nout = cin_fwd / op.bn;
+  p.bw_log2 = ilog2(bw);
+  p.bh_log2 = ilog2(bh);
+  p.W = Wo;
+  p.H = Ho;
+  p.NIMG = B;
+  p.cout = cin_fwd;
+  p.act = ACT_NONE;
+  const double M = (double)B * Ho * Wo;
+  op.flops = 2.0 * M * cin_fwd * p.num_taps * cout_fwd;
+  op.bytes = 2.0 * (M * cout_fwd + (double)cin_fwd * p.num_taps * cout_fwd + M * cin_fwd);
+  return 0;
+}
+
 int run_op(const GemmOp& op, cudaStream_t stream) {
   if (op.halo) return launch_conv3x3_halo(op.a, op.w, op.o, op.p, device_sm_count(), stream);
   return launch_gemm(op.bn, op.a, op.w, op.o, op.p, device_sm_count(), stream);
 }
+
+namespace {
 
 // ------------------------------------------------------------------------
 // Parameter block layout

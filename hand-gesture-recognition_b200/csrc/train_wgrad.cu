@@ -1,0 +1,312 @@
+// Weight gradients of the training step: for every Conv2d / Linear of the path
+//     dW[co][tap][ci] = sum over output pixels p of  G[p][co] * X[shift_tap(p)][ci]
+// i.e. a GEMM whose reduction runs over PIXELS while both operands are stored channel-contiguous (NHWC), so
+// both are "MN-major" from the tensor core's point of view.  This first version runs on mma.sync m16n8k16
+// (ldmatrix.trans turns the pixel-major shared-memory tiles into K-major fragments) with split-K over pixel
+// chunks: grid = (co-tile x ci-tile, tap, chunk), fp32 partial tiles, and a fixed-order reduction kernel that
+// also writes PyTorch's (Cout, Cin, kh, kw) layout.  At the 32-crop training batch the whole backward wgrad is
+// 140 GFLOP; a tcgen05 MN-major version is the follow-up once the step is no longer launch-bound.
+#include "hgr_internal.h"
+#include "ptx.cuh"
+#include "train.h"
+
+namespace hgr {
+
+namespace {
+
+constexpr int kWThreads = 128;     // 4 warps: warp w owns co rows [16 w, 16 w + 16) of the 64 x 64 tile
+constexpr int kPix = 64;           // pixels (K) per pipeline stage
+constexpr int kPitchB = 144;       // bytes per smem row: 64 bf16 + 16 B pad -> conflict-free ldmatrix
+constexpr int kStages = 3;
+constexpr int kTileBytes = kPix * kPitchB;  // 9216
+
+struct WgradParams {
+  const __nv_bfloat16* g;  // [P][g_ctot], channel offset applied
+  const __nv_bfloat16* x;  // [B][H][W][x_ctot], channel offset applied
+  float* partial;          // [chunks][taps][Cout][Cin]
+  int g_ctot, x_ctot;
+  int Cout, Cin;
+  int B, H, W, Ho, Wo;  // input map H x W, output map Ho x Wo
+  int k, s;             // kernel size (1 or 3), stride
+  long long P;          // B * Ho * Wo
+  long long per_chunk;  // pixels per chunk (multiple of kPix)
+};
+
+__global__ void __launch_bounds__(kWThreads)
+wgrad_kernel(const WgradParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sg = smem;                         // [kStages][kPix][kPitchB]
+  uint8_t* sx = smem + kStages * kTileBytes;  // [kStages][kPix][kPitchB]
+
+  const int ci_tiles = p.Cin >> 6;
+  const int co0 = (blockIdx.x / ci_tiles) << 6;
+  const int ci0 = (blockIdx.x % ci_tiles) << 6;
+  const int tap = blockIdx.y;
+  const int kh = tap / p.k, kw = tap % p.k;
+  const int pad = p.k >> 1;
+  const long long p_begin = (long long)blockIdx.z * p.per_chunk;
+  long long p_end = p_begin + p.per_chunk;
+  if (p_end > p.P) p_end = p.P;
+  const int nsteps = p_end > p_begin ? (int)((p_end - p_begin + kPix - 1) / kPix) : 0;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // loader: thread owns 16-byte chunk `lc` of pixels lp, lp + 16, lp + 32, lp + 48
+  const int lc = tid & 7, lp = tid >> 3;
+
+  auto load_stage = [&](int stage, int step) {
+    const long long base = p_begin + (long long)step * kPix;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pr = lp + i * 16;
+      const long long pix = base + pr;
+      const bool in_range = pix < p_end;
+      const long long pc = in_range ? pix : p_begin;
+      const __nv_bfloat16* gsrc = p.g + pc * p.g_ctot + co0 + lc * 8;
+      cp_async_16(sg + stage * kTileBytes + pr * kPitchB + lc * 16, gsrc, in_range ? 16u : 0u);
+      const int ow = (int)(pc % p.Wo);
+      const long long t = pc / p.Wo;
+      const int oh = (int)(t % p.Ho);
+      const long long n = t / p.Ho;
+      const int ih = oh * p.s + kh - pad, iw = ow * p.s + kw - pad;
+      const bool ok = in_range && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+      const __nv_bfloat16* xsrc = ok ? p.x + ((n * p.H + ih) * p.W + iw) * p.x_ctot + ci0 + lc * 8 : p.x;
+      cp_async_16(sx + stage * kTileBytes + pr * kPitchB + lc * 16, xsrc, ok ? 16u : 0u);
+    }
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (s < nsteps) load_stage(s, s);
+    cp_async_commit();
+  }
+  // ldmatrix.trans lane addresses.  Stored tiles are [pixel (k)][channel]; after .trans a thread holds
+  // (channel = g, pixels 2t, 2t+1), which is the A fragment (m = co, k = pixel) and the B fragment (k = pixel, n = ci).
+  //  A x4: matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15)
+  const int a_row = (lane & 7) + ((lane >> 4) << 3);
+  const int a_col = warp * 16 + (((lane >> 3) & 1) << 3);
+  //  B x4: matrices (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15)
+  const int b_row = (lane & 7) + (((lane >> 3) & 1) << 3);
+  const int b_col = (lane >> 4) << 3;
+
+  for (int step = 0; step < nsteps; ++step) {
+    cp_async_wait<kStages - 2>();
+    __syncthreads();
+    {
+      const int nxt = step + kStages - 1;
+      if (nxt < nsteps) load_stage(nxt % kStages, nxt);
+      cp_async_commit();
+    }
+    const uint32_t g_base = smem_u32(sg + (step % kStages) * kTileBytes);
+    const uint32_t x_base = smem_u32(sx + (step % kStages) * kTileBytes);
+#pragma unroll
+    for (int kk = 0; kk < kPix / 16; ++kk) {
+      uint32_t a[4];
+      ldmatrix_x4_trans(a, g_base + (kk * 16 + a_row) * kPitchB + a_col * 2);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, x_base + (kk * 16 + b_row) * kPitchB + (np * 16 + b_col) * 2);
+        mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
+        mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // partial[chunk][tap][co][ci]
+  const int g = lane >> 2, t = lane & 3;
+  float* out = p.partial + (((size_t)blockIdx.z * gridDim.y + tap) * p.Cout + co0 + warp * 16) * p.Cin + ci0;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<float2*>(out + (size_t)g * p.Cin + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+    *reinterpret_cast<float2*>(out + (size_t)(g + 8) * p.Cin + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+}
+
+// dW[(co * Cin + ci) * taps + tap] = sum_chunk partial[chunk][tap][co][ci]   (PyTorch's (Cout, Cin, kh, kw))
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int taps, int Cout, int Cin, float* __restrict__ dw) {
+  const long long total = (long long)Cout * Cin * taps;
+  const long long slab = (long long)taps * Cout * Cin;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    // i walks the partial layout [tap][co][ci] so that the loads are coalesced
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((long long)Cin * Cout));
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[c * slab + i];
+    dw[((size_t)co * Cin + ci) * taps + tap] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1 (3 -> 64, 3x3 s2) weight gradient.  The input is the NCHW crop (fp32 or bf16) and K = 27 per output
+// pixel, so this one runs on the CUDA cores: a CTA owns `rows_per_cta` output rows of one image, stages the
+// dz row (96 x 64 bf16) and the three input rows it touches in shared memory, and thread (co, q) accumulates
+// the 7 (or 6) weights k = q, q + 4, ... of output channel co.  Per-CTA partials, fixed-order reduce.
+// ---------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const TIn* __restrict__ x, int S, int rows_per_cta,
+                   float* __restrict__ partial) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int So = S >> 1;
+  float* sxin = reinterpret_cast<float*>(smem);                             // [3 ci][3 rows][S + 2]
+  __nv_bfloat16* sdz = reinterpret_cast<__nv_bfloat16*>(sxin + 9 * (S + 2));  // [So][64]
+  const int b = blockIdx.y;
+  const int oh0 = blockIdx.x * rows_per_cta;
+  const int co = threadIdx.x & 63, q = threadIdx.x >> 6;
+  float acc[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = 0.f;
+  // the (up to) 7 taps of this thread: k = q + 4 i -> (kh, kw, ci), offset into sxin for ow = 0
+  int koff[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int k = q + 4 * i;
+    if (k < 27) {
+      const int ci = k % 3, kw = (k / 3) % 3, kh = k / 9;
+      koff[i] = (ci * 3 + kh) * (S + 2) + kw;  // column index iw + 1 = 2 ow + kw
+    } else {
+      koff[i] = -1;
+    }
+  }
+  for (int r = 0; r < rows_per_cta; ++r) {
+    const int oh = oh0 + r;
+    if (oh >= So) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * (S + 2); i += 256) {
+      const int col = i % (S + 2), rr = i / (S + 2);
+      const int ci = rr / 3, kh = rr % 3;
+      const int ih = 2 * oh + kh - 1, iw = col - 1;
+      float v = 0.f;
+      if (ih >= 0 && ih < S && iw >= 0 && iw < S) {
+        if constexpr (sizeof(TIn) == 4) v = x[(((size_t)b * 3 + ci) * S + ih) * S + iw];
+        else v = __bfloat162float(x[(((size_t)b * 3 + ci) * S + ih) * S + iw]);
+      }
+      // the forward kernel multiplies bf16-rounded inputs: mirror it
+      sxin[i] = __bfloat162float(__float2bfloat16_rn(v));
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(dz + (((size_t)b * So + oh) * So) * 64);
+    for (int i = threadIdx.x; i < So * 8; i += 256) reinterpret_cast<uint4*>(sdz)[i] = __ldg(src + i);
+    __syncthreads();
+    for (int ow = 0; ow < So; ++ow) {
+      const float gz = __bfloat162float(sdz[ow * 64 + co]);
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        if (koff[i] >= 0) acc[i] = fmaf(gz, sxin[koff[i] + 2 * ow], acc[i]);
+    }
+  }
+  // partial[cta][co][27]  (27 = ci-major PyTorch order: (ci, kh, kw))
+  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * 27 + co * 27;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int k = q + 4 * i;
+    if (k < 27) {
+      const int ci = k % 3, kw = (k / 3) % 3, kh = k / 9;
+      out[ci * 9 + kh * 3 + kw] = acc[i];
+    }
+  }
+}
+
+__global__ void partial_sum_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < nparts; ++c) s += (double)partial[(size_t)c * n + i];
+  dst[i] = (float)s;
+}
+
+}  // namespace
+
+size_t wgrad_partial_floats(int Cout, int Cin, int k, long long P, int* chunks_out) {
+  const int taps = k * k;
+  const long long tiles = (long long)(Cout / 64) * (Cin / 64) * taps;
+  long long chunks = (148 * 4 + tiles - 1) / tiles;
+  const long long max_chunks = (P + 4 * kPix - 1) / (4 * kPix);  // at least 256 pixels per chunk
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks_out) *chunks_out = (int)chunks;
+  return (size_t)chunks * taps * Cout * Cin;
+}
+
+int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int x_ctot, int B, int H, int W, int Cin,
+                 int Cout, int k, int s, float* partial, float* dw, cudaStream_t st) {
+  if (Cin % 64 != 0 || Cout % 64 != 0 || !(k == 1 || k == 3) || !(s == 1 || s == 2) || g_ctot % 8 || x_ctot % 8) {
+    set_error("wgrad: unsupported shape cin %d cout %d k %d s %d", Cin, Cout, k, s);
+    return -1;
+  }
+  WgradParams p;
+  p.g = g;
+  p.x = x;
+  p.partial = partial;
+  p.g_ctot = g_ctot;
+  p.x_ctot = x_ctot;
+  p.Cout = Cout;
+  p.Cin = Cin;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.Ho = H / s;
+  p.Wo = W / s;
+  p.k = k;
+  p.s = s;
+  p.P = (long long)B * p.Ho * p.Wo;
+  int chunks = 1;
+  wgrad_partial_floats(Cout, Cin, k, p.P, &chunks);
+  long long per = (p.P + chunks - 1) / chunks;
+  per = (per + kPix - 1) / kPix * kPix;
+  p.per_chunk = per;
+  static bool configured = false;
+  const int smem = 2 * kStages * kTileBytes;
+  if (!configured) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((Cout / 64) * (Cin / 64), k * k, chunks);
+  wgrad_kernel<<<grid, kWThreads, smem, st>>>(p);
+  const long long total = (long long)Cout * Cin * k * k;
+  int rb = (int)((total + 255) / 256);
+  if (rb > 148 * 8) rb = 148 * 8;
+  wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, chunks, k * k, Cout, Cin, dw);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t conv1_wgrad_partial_floats(int B, int S) {
+  const int So = S / 2;
+  const int rows_per_cta = 8;
+  return (size_t)B * ((So + rows_per_cta - 1) / rows_per_cta) * 64 * 27;
+}
+
+int launch_conv1_wgrad(const __nv_bfloat16* dz, const void* x, int x_dtype, int B, int S, float* partial, float* dw,
+                       cudaStream_t st) {
+  const int So = S / 2;
+  const int rows_per_cta = 8;
+  dim3 grid((So + rows_per_cta - 1) / rows_per_cta, B);
+  const size_t smem = (size_t)9 * (S + 2) * sizeof(float) + (size_t)So * 64 * 2;
+  if (x_dtype == DT_F32) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv1_wgrad_kernel<float><<<grid, 256, smem, st>>>(dz, static_cast<const float*>(x), S, rows_per_cta, partial);
+  } else {
+    HGR_CHECK_CUDA(
+        cudaFuncSetAttribute(conv1_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv1_wgrad_kernel<__nv_bfloat16>
+        <<<grid, 256, smem, st>>>(dz, static_cast<const __nv_bfloat16*>(x), S, rows_per_cta, partial);
+  }
+  const int nparts = grid.x * grid.y;
+  partial_sum_kernel<<<(64 * 27 + 127) / 128, 128, 0, st>>>(partial, nparts, 64 * 27, dw);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_partial_sum(const float* partial, int nparts, int n, float* dst, cudaStream_t st) {
+  partial_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, nparts, n, dst);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hgr

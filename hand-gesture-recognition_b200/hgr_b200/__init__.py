@@ -2,5 +2,6 @@
 from .model import MultiTaskNet  # noqa: F401
 from .ops import crop_normalize, get_max_preds  # noqa: F401
 from .pipeline import HandPipeline  # noqa: F401
+from .training import DataParallelTrainer, loss_and_grads  # noqa: F401
 
-__all__ = ["MultiTaskNet", "HandPipeline", "get_max_preds", "crop_normalize"]
+__all__ = ["MultiTaskNet", "HandPipeline", "DataParallelTrainer", "loss_and_grads", "get_max_preds", "crop_normalize"]

@@ -46,6 +46,26 @@ SIGNATURES = {
     "hgr_pose_head": (_i, [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_get_max_preds": (_i, [_vp, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "hgr_crop_normalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    # ---- training step ----
+    "hgr_train_param_count": (_i, [_i, _i]),
+    "hgr_train_param_info": (_i, [_i, _i, _i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz)]),
+    "hgr_train_param_floats": (_sz, [_i, _i]),
+    "hgr_train_bnstat_count": (_i, []),
+    "hgr_train_bnstat_info": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(_sz), C.POINTER(_sz)]),
+    "hgr_train_bnstat_floats": (_sz, []),
+    "hgr_train_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "hgr_train_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "hgr_train_plan_destroy": (None, [_vp]),
+    "hgr_train_buffer": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(C.c_int64)]),
+    "hgr_train_forward": (_i, [_vp, _vp, _i, _vp, _vp, C.c_float, _vp]),
+    "hgr_train_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "hgr_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp]),
+    "hgr_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i,
+                            C.c_float, _vp]),
+    "hgr_wgrad": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hgr_wgrad_partial_floats": (_sz, [_i, _i, _i, _ll]),
+    "hgr_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "hgr_dgrad_s2": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
 }
 
 
@@ -97,4 +117,29 @@ def param_layout(image_size: int, num_joints: int, num_classes: int):
         check(lib.hgr_param_info(image_size, num_joints, num_classes, i, C.byref(name), C.byref(off), C.byref(nb),
                                  C.byref(dt), dims), "hgr_param_info")
         out.append((name.value.decode(), off.value, nb.value, dt.value, tuple(dims)))
+    return out
+
+
+def train_param_layout(num_joints: int, num_classes: int):
+    """[(state_dict key, offset in floats, numel)] of the flat training parameter / gradient block."""
+    lib = load()
+    out = []
+    for i in range(lib.hgr_train_param_count(num_joints, num_classes)):
+        name = C.c_char_p()
+        off, n = _sz(), _sz()
+        check(lib.hgr_train_param_info(num_joints, num_classes, i, C.byref(name), C.byref(off), C.byref(n)),
+              "hgr_train_param_info")
+        out.append((name.value.decode(), off.value, n.value))
+    return out
+
+
+def train_bnstat_layout():
+    """[(state_dict key, offset in floats, numel)] of the flat BatchNorm running-statistics block."""
+    lib = load()
+    out = []
+    for i in range(lib.hgr_train_bnstat_count()):
+        name = C.c_char_p()
+        off, n = _sz(), _sz()
+        check(lib.hgr_train_bnstat_info(i, C.byref(name), C.byref(off), C.byref(n)), "hgr_train_bnstat_info")
+        out.append((name.value.decode(), off.value, n.value))
     return out

@@ -3,7 +3,8 @@
 Same constructor `MultiTaskNet(num_joints, num_classes, image_size)`, same
 module tree and therefore the same 180 `state_dict` keys (reference
 model/multitasknet.py:8-29, model/gelan.py:18-176, model/transformer.py:45-127),
-same `forward(x) -> (cls_out, hmap_out, attnmap)` contract.  The sub-modules
+same `forward(x) -> (cls_out, hmap_out, attnmap)` contract, in `.eval()` (BatchNorm folded into the
+convolutions) and in `.train()` (batch statistics, running-stat updates, autograd).  The sub-modules
 are parameter containers only: all arithmetic happens in the hand-written
 sm_100a kernels of libhgr_b200.so, reached through the C ABI in
 include/hgr_b200.h.  There is no CPU path and no PyTorch-operator path:
@@ -225,9 +226,6 @@ class MultiTaskNet(nn.Module):
             raise TypeError("expected a (B, 3, S, S) tensor")
         if not x.is_cuda:
             raise RuntimeError("the B200 MultiTaskNet has no CPU path: move the input (and the module) to a CUDA device")
-        if self.training:
-            raise NotImplementedError(
-                "train-mode forward (batch-statistics BatchNorm + autograd) is not built yet; call .eval()")
         s = self.image_size[0]
         if tuple(x.shape[1:]) != (3, s, s):
             raise ValueError(f"input {tuple(x.shape)} does not match image_size {self.image_size} "
@@ -240,6 +238,10 @@ class MultiTaskNet(nn.Module):
         f = s // 16
         t = f * f + 1
         x = x.contiguous()
+        if self.training:
+            # batch-statistics BatchNorm + autograd (training.py): the parameters become views of one flat block
+            from . import training
+            return training.forward_autograd(self, x)
         dt = _lib.F32 if x.dtype == torch.float32 else _lib.BF16
         with torch.cuda.device(x.device):
             plan = self.plan_for(b, x.device)

@@ -1,0 +1,267 @@
+"""Training step of the B200 MultiTaskNet: flat parameter storage, train-mode forward / backward through
+the C ABI, and the data-parallel trainer of BASELINE.json configs[4].
+
+Reference behaviour reproduced (train.py:24-108, libs/loss.py):
+  * `model.train()` forward uses batch statistics in every BatchNorm2d and updates `running_mean` /
+    `running_var` (momentum 0.1, unbiased variance) and `num_batches_tracked`;
+  * loss = 0.001 * CrossEntropy(logits, label) + JointsMSELoss(heatmap, target, target_weight);
+  * optimiser = torch.optim.AdamW(model.parameters(), lr) (weight decay 0.01).
+
+Storage: the module's parameters become views of ONE flat fp32 device block whose layout the library owns
+(state_dict order), the gradients live in a second block of the same layout, the BatchNorm running statistics
+in a third.  `torch.optim.AdamW` keeps working on the views (the drop-in path: `MultiTaskNet.forward` in train
+mode is a `torch.autograd.Function`), and `DataParallelTrainer` runs the fused path: forward -> loss kernel ->
+backward -> ONE all-reduce over the flat gradient block (NCCL over NVLink; the reference itself is
+single-GPU, train.py:228-229) -> fused AdamW.  There is no CPU or PyTorch-operator fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, packing
+
+BN_MOMENTUM = 0.1  # nn.BatchNorm2d default, reference model/gelan.py:46
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class TrainPlan:
+    """A bound hgr_train_plan (one per batch size) plus the workspace tensor that owns its memory."""
+
+    def __init__(self, state: "TrainState", batch: int):
+        lib = _lib.load()
+        m = state.model
+        s, j, c = m.image_size[0], m.num_joints, m.num_classes
+        nbytes = lib.hgr_train_workspace_bytes(s, j, c, batch)
+        if nbytes == 0:
+            _lib.check(-1, "hgr_train_workspace_bytes")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=state.device)
+        self.state = state
+        self.batch = batch
+        handle = C.c_void_p()
+        _lib.check(lib.hgr_train_plan_create(C.byref(handle), s, j, c, batch, state.params.data_ptr(),
+                                             state.grads.data_ptr(), state.bnstats.data_ptr(),
+                                             state.pos_embedding.data_ptr(), self.workspace.data_ptr(), nbytes),
+                   "hgr_train_plan_create")
+        self.handle = handle
+
+    def buffer(self, name: str) -> torch.Tensor:
+        """bf16 view of a named workspace buffer (activations, gradients, probabilities) for tests / attnmap."""
+        ptr, nb = C.c_void_p(), C.c_size_t()
+        dims = (C.c_int64 * 4)()
+        _lib.check(_lib.load().hgr_train_buffer(self.handle, name.encode(), C.byref(ptr), C.byref(nb), dims),
+                   "hgr_train_buffer")
+        off = ptr.value - self.workspace.data_ptr()
+        t = self.workspace[off: off + nb.value].view(torch.bfloat16)
+        return t.view(*dims) if dims[0] > 0 else t
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().hgr_train_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class TrainState:
+    """Flat fp32 parameter / gradient / running-statistics blocks of one MultiTaskNet on one device."""
+
+    def __init__(self, model, device):
+        self.model = model
+        self.device = device
+        j, c = model.num_joints, model.num_classes
+        lib = _lib.load()
+        self.layout = _lib.train_param_layout(j, c)
+        self.bn_layout = _lib.train_bnstat_layout()
+        self.numel = lib.hgr_train_param_floats(j, c)
+        self.params = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.bnstats = torch.zeros(lib.hgr_train_bnstat_floats(), dtype=torch.float32, device=device)
+        named_p = dict(model.named_parameters())
+        named_b = dict(model.named_buffers())
+        if len(named_p) != len(self.layout):
+            raise RuntimeError(f"parameter layout mismatch: module has {len(named_p)}, library {len(self.layout)}")
+        self._views = []
+        with torch.no_grad():
+            for name, off, n in self.layout:
+                p = named_p[name]
+                if p.numel() != n:
+                    raise RuntimeError(f"parameter '{name}': {p.numel()} elements, library expects {n}")
+                view = self.params[off: off + n].view(p.shape)
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = view
+                self._views.append((p, off, n))
+            for name, off, n in self.bn_layout:
+                b = named_b[name]
+                view = self.bnstats[off: off + n].view(b.shape)
+                view.copy_(b.detach().to(device=device, dtype=torch.float32))
+                b.data = view
+            nbt = [(k, b) for k, b in named_b.items() if k.endswith("num_batches_tracked")]
+            self.num_batches_tracked = torch.zeros(len(nbt), dtype=torch.int64, device=device)
+            for i, (_, b) in enumerate(nbt):
+                self.num_batches_tracked[i] = b.to(device)
+                b.data = self.num_batches_tracked[i]
+        f = model.image_size[0] // 16
+        self.pos_embedding = packing.sincos_table(f, f).to(device).to(torch.bfloat16).contiguous()
+        self._plans = {}
+
+    def attached(self) -> bool:
+        """True while every parameter still is a view of the flat block (`.to()` / `load_state_dict` keep it)."""
+        base = self.params.data_ptr()
+        return all(p.data_ptr() == base + 4 * off and p.device == self.params.device for p, off, _ in self._views)
+
+    def plan_for(self, batch: int) -> TrainPlan:
+        if batch not in self._plans:
+            self._plans[batch] = TrainPlan(self, batch)
+        return self._plans[batch]
+
+    def grad_views(self):
+        return [self.grads[off: off + n].view(p.shape) for p, off, n in self._views]
+
+
+def train_state(model, device) -> TrainState:
+    st = getattr(model, "_train_state_obj", None)
+    if st is None or st.device != device or not st.attached():
+        st = TrainState(model, device)
+        model._train_state_obj = st
+        model._packed = None  # the inference pack is keyed on data pointers; force a re-pack after re-homing
+    return st
+
+
+def _dt(t):
+    return _lib.F32 if t.dtype == torch.float32 else _lib.BF16
+
+
+def forward_train(state: TrainState, x: torch.Tensor, update_running: bool = True):
+    """Raw train-mode forward: (logits fp32 (B, C), heatmaps fp32 (B, J, S/4, S/4), plan)."""
+    m = state.model
+    b, s = x.shape[0], m.image_size[0]
+    plan = state.plan_for(b)
+    logits = torch.empty(b, m.num_classes, dtype=torch.float32, device=x.device)
+    heat = torch.empty(b, m.num_joints, s // 4, s // 4, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hgr_train_forward(plan.handle, x.data_ptr(), _dt(x), logits.data_ptr(), heat.data_ptr(),
+                                                 BN_MOMENTUM if update_running else -1.0, _stream(x.device)),
+                   "hgr_train_forward")
+        if update_running:
+            state.num_batches_tracked += 1
+    return logits, heat, plan
+
+
+def backward_train(state: TrainState, plan: TrainPlan, x, dlogits, dheat):
+    """Fills state.grads from the loss gradients (fp32, contiguous)."""
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hgr_train_backward(plan.handle, x.data_ptr(), _dt(x), dlogits.data_ptr(),
+                                                  dheat.data_ptr(), _stream(x.device)), "hgr_train_backward")
+
+
+class _TrainFunction(torch.autograd.Function):
+    """MultiTaskNet.forward under .train(): the drop-in path for the reference's train.py (Lightning backward +
+    torch.optim.AdamW).  Parameters are passed so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        state = train_state(model, x.device)
+        logits, heat, plan = forward_train(state, x)
+        ctx.state, ctx.plan, ctx.x = state, plan, x
+        attn = None
+        if model.return_attention:
+            attn = plan.buffer(f"l{3}.probs").to(x.dtype)
+            ctx.mark_non_differentiable(attn)
+        if x.dtype != torch.float32:
+            logits, heat = logits.to(x.dtype), heat.to(x.dtype)
+        return logits, heat, attn
+
+    @staticmethod
+    def backward(ctx, dlogits, dheat, _dattn):
+        state, plan, x = ctx.state, ctx.plan, ctx.x
+        m = state.model
+        if dlogits is None:
+            dlogits = torch.zeros(x.shape[0], m.num_classes, device=x.device)
+        if dheat is None:
+            dheat = torch.zeros(x.shape[0], m.num_joints, m.image_size[0] // 4, m.image_size[0] // 4, device=x.device)
+        backward_train(state, plan, x, dlogits.float().contiguous(), dheat.float().contiguous())
+        # clones: autograd may keep or accumulate into what it is given, the flat block is rewritten every step
+        grads = [g.clone() for g in state.grad_views()]
+        return (None, None, *grads)
+
+
+def forward_autograd(model, x):
+    state = train_state(model, x.device)
+    params = [p for p, _, _ in state._views]
+    return _TrainFunction.apply(model, x, *params)
+
+
+def loss_and_grads(logits, heat, labels, target, target_weight, cls_weight=0.001, want_grads=True):
+    """train.py:63-64 on the device: returns (loss3 = [total, class, joints], dlogits, dheat)."""
+    b, c = logits.shape
+    _, j, h, w = heat.shape
+    dev = logits.device
+    loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+    scratch = torch.empty(512, dtype=torch.float32, device=dev)
+    dlogits = torch.empty_like(logits) if want_grads else None
+    dheat = torch.empty_like(heat) if want_grads else None
+    tw = target_weight.reshape(b, j).float().contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().hgr_loss(logits.data_ptr(), heat.data_ptr(), labels.contiguous().data_ptr(),
+                                        target.float().contiguous().data_ptr(), tw.data_ptr(), b, j, c, h * w,
+                                        cls_weight, dlogits.data_ptr() if want_grads else None,
+                                        dheat.data_ptr() if want_grads else None, scratch.data_ptr(),
+                                        loss3.data_ptr(), _stream(dev)), "hgr_loss")
+    return loss3, dlogits, dheat
+
+
+def allreduce_sum_(flat: torch.Tensor, group=None) -> int:
+    """SUM all-reduce of the flat gradient block over the data-parallel group; returns the world size.
+    (One call, one bucket: 7.4 M fp32 values = 29.6 MB cross NVSwitch in tens of microseconds, so the cost is
+    launch latency, not bandwidth - SURVEY.md 8e.)"""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return world
+
+
+class DataParallelTrainer:
+    """One rank of the data-parallel training step (BASELINE.json configs[4]).
+
+    step(x, labels, target, target_weight): local forward with LOCAL BatchNorm batch statistics (the reference
+    has plain nn.BatchNorm2d, no SyncBN) -> loss kernel -> backward -> all-reduce(SUM) of the flat gradient
+    block -> fused AdamW with grad_scale = 1 / world (identical update on every rank).  Running statistics stay
+    rank-local, like DDP with broadcast_buffers=False.
+    """
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, cls_weight=0.001, group=None):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("DataParallelTrainer needs the module on a CUDA device (no CPU path)")
+        self.model = model
+        self.state = train_state(model, dev)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.cls_weight = cls_weight
+        self.group = group
+        self.exp_avg = torch.zeros_like(self.state.params)
+        self.exp_avg_sq = torch.zeros_like(self.state.params)
+        self.steps = 0
+
+    def step(self, x, labels, target, target_weight):
+        st = self.state
+        logits, heat, plan = forward_train(st, x)
+        loss3, dlogits, dheat = loss_and_grads(logits, heat, labels, target, target_weight, self.cls_weight)
+        backward_train(st, plan, x, dlogits, dheat)
+        world = allreduce_sum_(st.grads, self.group)
+        self.steps += 1
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().hgr_adamw_step(st.params.data_ptr(), st.grads.data_ptr(), self.exp_avg.data_ptr(),
+                                                  self.exp_avg_sq.data_ptr(), st.numel, self.lr, self.betas[0],
+                                                  self.betas[1], self.eps, self.weight_decay, self.steps, 1.0 / world,
+                                                  _stream(x.device)), "hgr_adamw_step")
+        self.model._packed = None  # the eval-mode weight pack is stale now (the kernel does not bump tensor versions)
+        return loss3

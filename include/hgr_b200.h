@@ -165,6 +165,71 @@ HGR_API int hgr_get_max_preds(const void* d_heatmaps, int dtype, int B, int J, i
  * ((v / 255) - mean[c]) / std[c], ImageNet constants by channel index. */
 HGR_API int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, int H, int W, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Training step (BASELINE.json configs[4]; reference train.py:58-108 with
+ * libs/loss.py and torch.optim.AdamW).  Parameters, gradients and BatchNorm
+ * running statistics are three flat fp32 device blocks whose layout follows
+ * the reference's state_dict order; the host mirror (hgr_b200/training.py)
+ * makes the module's nn.Parameters views of the parameter block.
+ * ---------------------------------------------------------------------- */
+typedef struct hgr_train_plan hgr_train_plan_t;
+
+/* Flat parameter / gradient block: entry i = state_dict key, offset and size in
+ * floats (every entry starts on a 256-byte boundary). */
+HGR_API int hgr_train_param_count(int num_joints, int num_classes);
+HGR_API int hgr_train_param_info(int num_joints, int num_classes, int index, const char** name, size_t* offset_floats,
+                                 size_t* numel);
+HGR_API size_t hgr_train_param_floats(int num_joints, int num_classes);
+/* Flat BatchNorm running-statistics block (running_mean / running_var of the 22 Conv blocks). */
+HGR_API int hgr_train_bnstat_count(void);
+HGR_API int hgr_train_bnstat_info(int index, const char** name, size_t* offset_floats, size_t* numel);
+HGR_API size_t hgr_train_bnstat_floats(void);
+
+HGR_API size_t hgr_train_workspace_bytes(int image_size, int num_joints, int num_classes, int batch);
+/* d_pos_embedding_bf16: the (F*F, 256) sin-cos table of transformer.py:9-26 in bf16. */
+HGR_API int hgr_train_plan_create(hgr_train_plan_t** out, int image_size, int num_joints, int num_classes, int batch,
+                                  float* d_params, float* d_grads, float* d_bnstats, const void* d_pos_embedding_bf16,
+                                  void* d_workspace, size_t workspace_bytes);
+HGR_API void hgr_train_plan_destroy(hgr_train_plan_t* plan);
+/* Named workspace buffer (activations "a1".."o3", "z.<conv>", "x0".."x4", "l<k>.probs", gradients "d_<act>" ...). */
+HGR_API int hgr_train_buffer(hgr_train_plan_t* plan, const char* name, void** d_ptr, size_t* nbytes, int64_t dims[4]);
+
+/* MultiTaskNet.forward under .train(): batch-statistics BatchNorm (running statistics updated with `momentum`,
+ * unbiased variance; momentum < 0 leaves them untouched), fp32 logits (B, C) and heatmaps (B, J, S/4, S/4). */
+HGR_API int hgr_train_forward(hgr_train_plan_t* plan, const void* d_x, int x_dtype, float* d_logits, float* d_heatmaps,
+                              float momentum, void* stream);
+/* Backward of the last hgr_train_forward of this plan (same d_x): overwrites the whole gradient block. */
+HGR_API int hgr_train_backward(hgr_train_plan_t* plan, const void* d_x, int x_dtype, const float* d_dlogits,
+                               const float* d_dheatmaps, void* stream);
+
+/* train.py:63-64 / libs/loss.py: total = cls_weight * CrossEntropy(logits, labels) + JointsMSELoss(heatmaps, target,
+ * target_weight).  d_loss3 = {total, weighted class loss, joints loss}; d_dlogits / d_dheatmaps (nullable) receive
+ * d total / d logits and d total / d heatmaps.  d_scratch: >= 296 floats.  labels are int64. */
+HGR_API int hgr_loss(const float* d_logits, const float* d_heatmaps, const long long* d_labels, const float* d_target,
+                     const float* d_target_weight, int B, int J, int C, int hw, float cls_weight, float* d_dlogits,
+                     float* d_dheatmaps, float* d_scratch, float* d_loss3, void* stream);
+
+/* torch.optim.AdamW (train.py:50-51) over a flat block; grad_scale multiplies the gradient first
+ * (1 / world_size after an all-reduce SUM).  step counts from 1. */
+HGR_API int hgr_adamw_step(float* d_params, const float* d_grads, float* d_exp_avg, float* d_exp_avg_sq, long long n,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                           void* stream);
+
+/* Single kernels of the training step (parity tests).
+ * hgr_wgrad: dW (cout, cin, k, k) fp32 = sum over output pixels of g[p, :cout]^T x[shift(p), :cin]; g is the
+ *   (B*Ho*Wo, g_ctot) bf16 output gradient, x the (B, H, W, x_ctot) bf16 NHWC input, stride s, padding k/2;
+ *   d_partial: hgr_wgrad_partial_floats(...) floats of scratch. */
+HGR_API int hgr_wgrad(const void* d_g, int g_ctot, const void* d_x, int x_ctot, int B, int H, int W, int cin, int cout,
+                      int k, int s, float* d_partial, float* d_dw, void* stream);
+HGR_API size_t hgr_wgrad_partial_floats(int cout, int cin, int k, long long pixels);
+/* qkv (B, T, 768), probs (B, 8, T, T), o / do (B, T, 256) -> dqkv (B, T, 768), all bf16 */
+HGR_API int hgr_attention_bwd(const void* d_qkv, const void* d_probs, const void* d_o, const void* d_do, void* d_dqkv,
+                              int B, int T, void* stream);
+/* One parity class (ph, pw) of the input gradient of a 3x3 stride-2 convolution: dz (B, H/2, W/2, cout_fwd) bf16,
+ * d_w_parity [cin_fwd][ntaps][cout_fwd] bf16, writes dx[:, ph::2, pw::2, :] of a (B, H, W, cin_fwd) bf16 buffer. */
+HGR_API int hgr_dgrad_s2(const void* d_dz, int B, int H, int W, int cout_fwd, const void* d_w_parity, int ph, int pw,
+                         void* d_dx, int cin_fwd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

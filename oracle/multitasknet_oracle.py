@@ -252,3 +252,100 @@ def synthetic_images(batch, size, seed=1):
     contrast = 0.5 + torch.rand(batch, 1, 1, 1, generator=g)
     offset = 0.5 * torch.randn(batch, 1, 1, 1, generator=g)
     return (x * contrast + offset).contiguous()
+
+
+# --------------------------------------------------------------------------
+# training step (reference train.py:58-108, libs/loss.py, nn.BatchNorm2d in train mode)
+# --------------------------------------------------------------------------
+BN_MOMENTUM = 0.1  # nn.BatchNorm2d default, model/gelan.py:46
+
+
+def _conv_bn_act_train(p, stats, prefix, x, k, s, act=True):
+    """Conv.forward under .train(): batch statistics, running-stat update (momentum 0.1, unbiased variance)."""
+    y = F.conv2d(x, p[prefix + ".conv.weight"], None, stride=s, padding=k // 2)
+    y = F.batch_norm(y, stats[prefix + ".bn.running_mean"], stats[prefix + ".bn.running_var"], p[prefix + ".bn.weight"],
+                     p[prefix + ".bn.bias"], training=True, momentum=BN_MOMENTUM, eps=BN_EPS)
+    return F.silu(y) if act else y
+
+
+def _res_basic_block_train(p, stats, prefix, x):
+    y = _conv_bn_act_train(p, stats, prefix + ".cv1", x, 3, 1, act=True)
+    y = _conv_bn_act_train(p, stats, prefix + ".cv2", y, 3, 1, act=False)
+    return F.silu(x + y)
+
+
+def _gelan_block_train(p, stats, prefix, x):
+    y = list(_conv_bn_act_train(p, stats, prefix + ".cv1", x, 1, 1).chunk(2, 1))
+    y.append(_res_basic_block_train(p, stats, prefix + ".cv2.0", y[-1]))
+    y.append(_res_basic_block_train(p, stats, prefix + ".cv3.0", y[-1]))
+    return _conv_bn_act_train(p, stats, prefix + ".cv4", torch.cat(y, 1), 1, 1)
+
+
+def multitasknet_forward_train(p, stats, x):
+    """MultiTaskNet.forward under .train() (model/multitasknet.py:24-29): differentiable in the entries of `p`;
+    `stats` (running_mean / running_var tensors) is updated in place like the module's buffers."""
+    x = _conv_bn_act_train(p, stats, "encoder.conv1", x, 3, 2)
+    x = _conv_bn_act_train(p, stats, "encoder.conv2", x, 3, 2)
+    x = _gelan_block_train(p, stats, "encoder.cspelan1", x)
+    x = _conv_bn_act_train(p, stats, "encoder.down1", x, 3, 2)
+    x = _gelan_block_train(p, stats, "encoder.cspelan2", x)
+    x = _conv_bn_act_train(p, stats, "encoder.down2", x, 3, 2)
+    x = _gelan_block_train(p, stats, "encoder.cspelan3", x)
+    feat = F.conv2d(x, p["proj.weight"])
+    return vit(p, feat)
+
+
+def joints_mse_loss(output, target, target_weight):
+    """libs/loss.py:10-30 (use_target_weight=True): (1/J) sum_j 0.5 * mean((pred_j * w_j - gt_j * w_j)^2)."""
+    b, j = output.shape[0], output.shape[1]
+    pred = output.reshape(b, j, -1)
+    gt = target.reshape(b, j, -1)
+    loss = 0
+    for i in range(j):
+        w = target_weight[:, i]
+        loss = loss + 0.5 * F.mse_loss(pred[:, i] * w, gt[:, i] * w, reduction="mean")
+    return loss / j
+
+
+def total_loss(cls_out, hmap_out, labels, target, target_weight, cls_weight=0.001):
+    """train.py:63-64,75: (total, class_loss, joints_loss)."""
+    cl = F.cross_entropy(cls_out, labels, reduction="mean") * cls_weight
+    jl = joints_mse_loss(hmap_out, target, target_weight)
+    return cl + jl, cl, jl
+
+
+def train_step_grads(sd, x, labels, target, target_weight, cls_weight=0.001):
+    """One reference training forward/backward in fp32: returns (loss3, grads {key: tensor}, new running stats,
+    (cls_out, hmap_out))."""
+    p = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()
+         if v.is_floating_point() and "running_" not in k}
+    stats = {k: v.detach().clone().float() for k, v in sd.items() if "running_" in k}
+    cls_out, hmap_out, _ = multitasknet_forward_train(p, stats, x.float())
+    tot, cl, jl = total_loss(cls_out, hmap_out, labels, target, target_weight, cls_weight)
+    tot.backward()
+    grads = {k: v.grad.detach() for k, v in p.items()}
+    return torch.stack([tot.detach(), cl.detach(), jl.detach()]), grads, stats, (cls_out.detach(), hmap_out.detach())
+
+
+def synthetic_targets(batch, size, num_joints=21, num_classes=19, seed=2):
+    """Seeded labels, Gaussian-blob target heatmaps and visibility weights (libs/load.py:148-206 in spirit)."""
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.randint(0, num_classes, (batch,), generator=g)
+    hs = size // 4
+    cy = torch.rand(batch, num_joints, 1, 1, generator=g) * hs
+    cx = torch.rand(batch, num_joints, 1, 1, generator=g) * hs
+    yy = torch.arange(hs).view(1, 1, hs, 1).float()
+    xx = torch.arange(hs).view(1, 1, 1, hs).float()
+    target = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 2.0 ** 2))
+    weight = (torch.rand(batch, num_joints, 1, generator=g) > 0.2).float()
+    return labels, target.contiguous(), weight
+
+
+def adamw_step(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.01):
+    """torch.optim.AdamW's single-tensor update (train.py:50-51), restated; returns (p, m, v)."""
+    p = p * (1 - lr * wd)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    denom = v.sqrt() / (bc2 ** 0.5) + eps
+    return p - (lr / bc1) * m / denom, m, v
