@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-launch table (json) here")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+                    help="forward = the headline metric (BASELINE.json configs[1]); train = the data-parallel "
+                         "training step of configs[4] (batch 32 per GPU unless --batch is given)")
     return ap.parse_args()
 
 
@@ -205,6 +208,73 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0}), flush=True)
 
 
+def run_train(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: fwd + bwd (CE + heatmap MSE) + gradient all-reduce + AdamW, batch 32 per GPU."""
+    import torch
+    import torch.distributed as dist
+    from hgr_b200 import DataParallelTrainer, MultiTaskNet
+    from hgr_b200.sharding import max_over_ranks
+    from oracle import multitasknet_oracle as O  # synthetic targets only (seeded blobs); no oracle arithmetic is timed
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    B = args.batch if args.batch != 1024 else 32
+    S, K, W = args.size, args.steps, max(args.warmup, 3)
+    torch.manual_seed(0)
+    model = MultiTaskNet(21, 19, [S, S])
+    synthetic_weights(model)
+    model = model.to(dev).train()
+    tr = DataParallelTrainer(model, lr=1e-4)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(B, 3, S, S, generator=g, device=dev)
+    labels, target, weight = (t.to(dev) for t in O.synthetic_targets(B, S, seed=3 + rank))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(W):
+        loss = tr.step(x, labels, target, weight)
+    barrier()
+    if rank == 0:
+        sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = tr.step(x, labels, target, weight)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    clocks = sampler.stop() if rank == 0 else None
+    lv = [float(v) for v in loss.cpu()]
+    assert all(v == v for v in lv), "non-finite loss"
+    if rank == 0:
+        gf = GFLOP_PER_IMG.get(S)
+        pk = peaks()
+        value = world * B * K / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "training images/s, MultiTaskNet fwd+bwd+allreduce+AdamW", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"MultiTaskNet training step bf16 (fp32 master weights), batch {B} per GPU, 3x{S}x{S}, "
+                                   "loss 0.001*CE + JointsMSE, AdamW, NCCL all-reduce of the flat 7.4M-element gradient "
+                                   "block (BASELINE.json configs[4])",
+                       "batch_per_gpu": B, "image_size": S,
+                       "train_gflop_per_image_convention_3x_forward": 3 * gf if gf else None,
+                       "tensor_frac_of_sustained": value / world * 3 * gf * 1e9 / (pk["bf16_sustained"] * 1e12) if gf else None},
+            "clocks": clocks, "final_loss": lv}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +282,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.workload == "train":
+        run_train(args, rank, world, local_rank)
         return
 
     import torch

@@ -154,8 +154,8 @@ conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const TIn* __restrict__
                    float* __restrict__ partial) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int So = S >> 1;
-  float* sxin = reinterpret_cast<float*>(smem);                             // [3 ci][3 rows][S + 2]
-  __nv_bfloat16* sdz = reinterpret_cast<__nv_bfloat16*>(sxin + 9 * (S + 2));  // [So][64]
+  float* sxin = reinterpret_cast<float*>(smem);  // [3 ci][3 rows][S + 2], padded to a 16-byte multiple
+  __nv_bfloat16* sdz = reinterpret_cast<__nv_bfloat16*>(sxin + ((9 * (S + 2) + 3) & ~3));  // [So][64]
   const int b = blockIdx.y;
   const int oh0 = blockIdx.x * rows_per_cta;
   const int co = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -287,7 +287,7 @@ int launch_conv1_wgrad(const __nv_bfloat16* dz, const void* x, int x_dtype, int 
   const int So = S / 2;
   const int rows_per_cta = 8;
   dim3 grid((So + rows_per_cta - 1) / rows_per_cta, B);
-  const size_t smem = (size_t)9 * (S + 2) * sizeof(float) + (size_t)So * 64 * 2;
+  const size_t smem = (size_t)((9 * (S + 2) + 3) & ~3) * sizeof(float) + (size_t)So * 64 * 2;
   if (x_dtype == DT_F32) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv1_wgrad_kernel<float><<<grid, 256, smem, st>>>(dz, static_cast<const float*>(x), S, rows_per_cta, partial);

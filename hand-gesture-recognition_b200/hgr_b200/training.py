@@ -207,10 +207,14 @@ def loss_and_grads(logits, heat, labels, target, target_weight, cls_weight=0.001
     scratch = torch.empty(512, dtype=torch.float32, device=dev)
     dlogits = torch.empty_like(logits) if want_grads else None
     dheat = torch.empty_like(heat) if want_grads else None
+    # keep every converted operand alive until the launch is enqueued (a temporary's block could be re-used)
     tw = target_weight.reshape(b, j).float().contiguous()
+    lab = labels.to(torch.int64).contiguous()
+    tgt = target.float().contiguous()
+    logits, heat = logits.contiguous(), heat.contiguous()
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().hgr_loss(logits.data_ptr(), heat.data_ptr(), labels.contiguous().data_ptr(),
-                                        target.float().contiguous().data_ptr(), tw.data_ptr(), b, j, c, h * w,
+        _lib.check(_lib.load().hgr_loss(logits.data_ptr(), heat.data_ptr(), lab.data_ptr(),
+                                        tgt.data_ptr(), tw.data_ptr(), b, j, c, h * w,
                                         cls_weight, dlogits.data_ptr() if want_grads else None,
                                         dheat.data_ptr() if want_grads else None, scratch.data_ptr(),
                                         loss3.data_ptr(), _stream(dev)), "hgr_loss")

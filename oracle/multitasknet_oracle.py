@@ -314,16 +314,22 @@ def total_loss(cls_out, hmap_out, labels, target, target_weight, cls_weight=0.00
     return cl + jl, cl, jl
 
 
-def train_step_grads(sd, x, labels, target, target_weight, cls_weight=0.001):
-    """One reference training forward/backward in fp32: returns (loss3, grads {key: tensor}, new running stats,
-    (cls_out, hmap_out))."""
+def train_step_grads(sd, x, labels, target, target_weight, cls_weight=0.001, autocast_bf16=False):
+    """One reference training forward/backward: returns (loss3, grads {key: tensor}, new running stats,
+    (cls_out, hmap_out)).  fp32 like the reference (train.py:230 precision=32); autocast_bf16=True runs the same
+    graph under torch.autocast(bfloat16) and is the NOISE FLOOR the bf16 CUDA path is judged against."""
     p = {k: v.detach().clone().float().requires_grad_(True) for k, v in sd.items()
          if v.is_floating_point() and "running_" not in k}
     stats = {k: v.detach().clone().float() for k, v in sd.items() if "running_" in k}
-    cls_out, hmap_out, _ = multitasknet_forward_train(p, stats, x.float())
+    if autocast_bf16:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            cls_out, hmap_out, _ = multitasknet_forward_train(p, stats, x.float())
+        cls_out, hmap_out = cls_out.float(), hmap_out.float()
+    else:
+        cls_out, hmap_out, _ = multitasknet_forward_train(p, stats, x.float())
     tot, cl, jl = total_loss(cls_out, hmap_out, labels, target, target_weight, cls_weight)
     tot.backward()
-    grads = {k: v.grad.detach() for k, v in p.items()}
+    grads = {k: v.grad.detach().float() for k, v in p.items()}
     return torch.stack([tot.detach(), cl.detach(), jl.detach()]), grads, stats, (cls_out.detach(), hmap_out.detach())
 
 
