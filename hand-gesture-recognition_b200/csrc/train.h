@@ -7,7 +7,7 @@
 
 namespace hgr {
 
-// number of per-CTA partial rows the column reductions use for `rows` rows (<= 296)
+// number of per-CTA partial rows the column reductions use for `rows` rows (<= 592)
 int train_partial_blocks(long long rows);
 
 // ---- train-mode BatchNorm over a dense [rows][C] bf16 matrix (NHWC conv output) ----

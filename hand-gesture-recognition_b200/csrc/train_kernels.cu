@@ -58,8 +58,10 @@ __device__ __forceinline__ void column_partials(long long rows, int C, float* __
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-  if (prow < nrow)
+  if (prow < nrow) {
+#pragma unroll 4
     for (long long r = r0 + prow; r < r1; r += nrow) body(r, cg * 8, acc);
+  }
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -73,9 +75,27 @@ __device__ __forceinline__ void column_partials(long long rows, int C, float* __
   }
 }
 
+// Fixed-order sum of column c over the per-CTA partials: lane l adds partials l, l + 32, ... (ascending), then the
+// 32 lane sums are folded by a butterfly.  The order depends only on nblk, so the result is reproducible.
+template <int K>
+__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partial, int nblk, int C, int c,
+                                                  double (&out)[K]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] += (double)partial[((size_t)b * K + k) * C + c];
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) out[k] += __shfl_xor_sync(0xffffffffu, out[k], o);
+}
+
 int reduce_blocks(long long rows) {
-  long long b = (rows + 255) / 256;  // at least 256 rows per CTA
-  if (b > 296) b = 296;
+  long long b = (rows + 127) / 128;  // at least 128 rows per CTA
+  if (b > 592) b = 592;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -97,21 +117,19 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int
 
 // mean / biased variance of the batch -> scale = gamma * rstd, shift = beta - mean * scale, x-hat parameters
 // (mean, rstd) for the backward pass, and the running statistics (unbiased variance, momentum).
-__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                      float* __restrict__ rstd_out, float* __restrict__ running_mean,
-                                      float* __restrict__ running_var, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
+                      float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                      float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per channel
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
-    s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
-  }
+  double s[2];
+  warp_sum_partials<2>(partial, nblk, C, c, s);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = (double)rows;
-  const double mean = s1 / n;
-  double var = s2 / n - mean * mean;
+  const double mean = s[0] / n;
+  double var = s[1] / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + 1e-5));
   const float sc = gamma[c] * rstd;
@@ -180,20 +198,18 @@ bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const _
 }
 
 // d beta = S1, d gamma = S2; c1 = S1 / n, c2 = S2 / n for the apply pass
-__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ c1,
-                                    float* __restrict__ c2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
-    s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
-  }
-  dbeta[c] = (float)s1;
-  dgamma[c] = (float)s2;
-  c1[c] = (float)(s1 / (double)rows);
-  c2[c] = (float)(s2 / (double)rows);
+  double s[2];
+  warp_sum_partials<2>(partial, nblk, C, c, s);
+  if ((threadIdx.x & 31) != 0) return;
+  dbeta[c] = (float)s[0];
+  dgamma[c] = (float)s[1];
+  c1[c] = (float)(s[0] / (double)rows);
+  c2[c] = (float)(s[1] / (double)rows);
 }
 
 // dz = scale * (du - c1 - x-hat * c2)   [scale = gamma * rstd];   residual branch: dres += du
@@ -275,15 +291,22 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C
 }
 
 // out_k[c] = sum_b partial[b][k][c]  (k < K <= 2; dst1 may be null)
-__global__ void sums_final_kernel(const float* __restrict__ partial, int nblk, int K, int C, float* __restrict__ dst0,
-                                  float* __restrict__ dst1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+sums_final_kernel(const float* __restrict__ partial, int nblk, int K, int C, float* __restrict__ dst0,
+                  float* __restrict__ dst1) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
-  for (int k = 0; k < K; ++k) {
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partial[((size_t)b * K + k) * C + c];
-    float* dst = k == 0 ? dst0 : dst1;
-    if (dst != nullptr) dst[c] = (float)s;
+  if (K == 1) {
+    double s[1];
+    warp_sum_partials<1>(partial, nblk, C, c, s);
+    if ((threadIdx.x & 31) == 0 && dst0 != nullptr) dst0[c] = (float)s[0];
+  } else {
+    double s[2];
+    warp_sum_partials<2>(partial, nblk, C, c, s);
+    if ((threadIdx.x & 31) == 0) {
+      if (dst0 != nullptr) dst0[c] = (float)s[0];
+      if (dst1 != nullptr) dst1[c] = (float)s[1];
+    }
   }
 }
 
@@ -554,7 +577,7 @@ int launch_bn_stats(const __nv_bfloat16* z, long long rows, int C, const float* 
   }
   const int nblk = reduce_blocks(rows);
   bn_stats_partial_kernel<<<nblk, kThreads, kThreads * 16 * sizeof(float), st>>>(z, rows, C, partial);
-  bn_stats_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, rows, gamma, beta, scale, shift, mean, rstd,
+  bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, rows, gamma, beta, scale, shift, mean, rstd,
                                                          running_mean, running_var, momentum);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -592,7 +615,7 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
   do {                                                                                                             \
     bn_bwd_partial_kernel<S, R><<<nblk, kThreads, sm, st>>>(dy, dy_ctot, z, rows, C, scale, shift, mean, rstd, res, \
                                                             res_ctot, partial);                                    \
-    bn_bwd_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, rows, dgamma, dbeta, c1, c2);            \
+    bn_bwd_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, rows, dgamma, dbeta, c1, c2);            \
     bn_bwd_apply_kernel<S, R><<<blocks, kThreads, 0, st>>>(dy, dy_ctot, z, rows, C, scale, shift, mean, rstd, c1,   \
                                                            c2, res, res_ctot, dres, dres_ctot, dz);                \
   } while (0)
@@ -624,7 +647,7 @@ int launch_colsum(const __nv_bfloat16* g, long long rows, int C, float* dst, flo
   }
   const int nblk = reduce_blocks(rows);
   colsum_partial_kernel<<<nblk, kThreads, kThreads * 8 * sizeof(float), st>>>(g, rows, C, partial);
-  sums_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, 1, C, dst, nullptr);
+  sums_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, 1, C, dst, nullptr);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -633,7 +656,7 @@ int launch_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* 
                   __nv_bfloat16* g_out, long long rows, float* dgamma, float* dbeta, float* partial, cudaStream_t st) {
   const int nblk = reduce_blocks(rows);
   ln_bwd_kernel<<<nblk, kThreads, 0, st>>>(dy, x, gamma, g_in, g_out, rows, partial);
-  sums_final_kernel<<<2, 128, 0, st>>>(partial, nblk, 2, 256, dgamma, dbeta);
+  sums_final_kernel<<<32, 256, 0, st>>>(partial, nblk, 2, 256, dgamma, dbeta);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -654,11 +677,11 @@ int launch_pack_jobs(const PackJob* d_jobs, int njobs, const float* params, cuda
 
 int launch_loss(const float* logits, const float* heat, const long long* labels, const float* target,
                 const float* weight, int B, int J, int C, int hw, float cls_weight, float* dlogits, float* dheat,
-                float* partial /* >= 296 floats */, float* out3, cudaStream_t st) {
+                float* partial /* >= 592 floats */, float* out3, cudaStream_t st) {
   const long long n = (long long)B * J * hw;
   const float inv_norm = 1.0f / ((float)B * (float)hw * (float)J);
   int nblk = ew_blocks(n);
-  if (nblk > 296) nblk = 296;
+  if (nblk > 592) nblk = 592;
   loss_heat_kernel<<<nblk, kThreads, 0, st>>>(heat, target, weight, n, hw, inv_norm, dheat, partial);
   loss_final_kernel<<<1, kThreads, 0, st>>>(logits, labels, B, C, cls_weight, dlogits, partial, nblk, inv_norm, out3);
   HGR_CHECK_CUDA(cudaGetLastError());

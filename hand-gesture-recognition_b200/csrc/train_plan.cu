@@ -271,7 +271,7 @@ std::vector<WsBuf> train_workspace(int S, int J, int C, int B, size_t* total) {
   add("wproj_t", (size_t)kDim * 512 * 2);
   add("wpose", (size_t)24 * kDim * 2);
   // reduction scratch
-  add("partial", (size_t)296 * 2 * 1024 * 4);
+  add("partial", (size_t)592 * 2 * 1024 * 4);
   add("c1c2", (size_t)2 * 1024 * 4);
   size_t wp = conv1_wgrad_partial_floats(B, S);
   for (int i = 1; i < kNumDefs; ++i) {

@@ -187,28 +187,29 @@ cls_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __res
 // once per pixel (by the CTA with y0 == ty) into a per-CTA partial.  Thread c = channel c.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxJ = 24;
+constexpr int kPhases = 4;  // pixel phases per CTA: thread (c, q) handles output columns ox = q (mod 4)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256 * kPhases, 1)
 pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __restrict__ w /*[J][256] fp32*/,
                      const float* __restrict__ dheat, int F, int J, __nv_bfloat16* __restrict__ dtokens,
                      float* __restrict__ dw_partial) {
   extern __shared__ float smp[];
   const int So = 4 * F;
-  float* sdx = smp;              // [F][256]
-  float* sdh = sdx + F * kDim;   // [J][So]
+  float* sdx = smp;                        // [kPhases][F][256]  per-phase accumulators of this token row
+  float* sdh = sdx + kPhases * F * kDim;   // [J][So]            dheat of the current output row
+  float* sw = sdh + kMaxJ * So;            // [J][256]           bf16-rounded weights (as the forward used them)
   const int b = blockIdx.y, ty = blockIdx.x;
-  const int c = threadIdx.x;
+  const int c = threadIdx.x & 255, q = threadIdx.x >> 8;
   const int T = F * F + 1;
   const float scale = (float)(F - 1) / (float)(So - 1);
   const __nv_bfloat16* tok = tokens + ((size_t)b * T + 1) * kDim;
 
-  float wr[kMaxJ], dwacc[kMaxJ];
+  float dwacc[kMaxJ];
 #pragma unroll
-  for (int j = 0; j < kMaxJ; ++j) {
-    wr[j] = j < J ? __bfloat162float(__float2bfloat16_rn(w[(size_t)j * kDim + c])) : 0.f;  // the forward used bf16 weights
-    dwacc[j] = 0.f;
-  }
-  for (int x = 0; x < F; ++x) sdx[x * kDim + c] = 0.f;
+  for (int j = 0; j < kMaxJ; ++j) dwacc[j] = 0.f;
+  for (int i = threadIdx.x; i < J * kDim; i += 256 * kPhases) sw[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
+  float* mydx = sdx + q * F * kDim;
+  for (int x = 0; x < F; ++x) mydx[x * kDim + c] = 0.f;
 
   for (int oy = 0; oy < So; ++oy) {
     const float sy = scale * (float)oy;
@@ -219,12 +220,12 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
     const float wy = (y0 == ty ? l0 : 0.f) + (y1 == ty ? l1 : 0.f);
     const bool owner = y0 == ty;
     __syncthreads();
-    for (int i = c; i < J * So; i += 256) {
+    for (int i = threadIdx.x; i < J * So; i += 256 * kPhases) {
       const int j = i / So, ox = i % So;
       sdh[i] = dheat[(((size_t)b * J + j) * So + oy) * So + ox];
     }
     __syncthreads();
-    for (int ox = 0; ox < So; ++ox) {
+    for (int ox = q; ox < So; ox += kPhases) {
       const float sx = scale * (float)ox;
       const int x0 = (int)sx;
       const int x1 = x0 + (x0 < F - 1 ? 1 : 0);
@@ -240,21 +241,36 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
         for (int j = 0; j < kMaxJ; ++j)
           if (j < J) {
             const float dh = sdh[j * So + ox];
-            dup = fmaf(dh, wr[j], dup);
+            dup = fmaf(dh, sw[j * kDim + c], dup);
             if (owner) dwacc[j] = fmaf(dh, up, dwacc[j]);
           }
         const float v = wy * dup;
-        sdx[x0 * kDim + c] = fmaf(m0, v, sdx[x0 * kDim + c]);
-        sdx[x1 * kDim + c] = fmaf(m1, v, sdx[x1 * kDim + c]);
+        mydx[x0 * kDim + c] = fmaf(m0, v, mydx[x0 * kDim + c]);
+        mydx[x1 * kDim + c] = fmaf(m1, v, mydx[x1 * kDim + c]);
       }
     }
   }
-  for (int x = 0; x < F; ++x)
-    dtokens[((size_t)b * T + 1 + (size_t)ty * F + x) * kDim + c] = __float2bfloat16_rn(sdx[x * kDim + c]);
-  float* out = dw_partial + ((size_t)b * gridDim.x + ty) * J * kDim;
+  __syncthreads();
+  // fold the phases in a fixed order: token-row gradient, then the weight-gradient partial (through sdh / sw space)
+  if (q == 0)
+    for (int x = 0; x < F; ++x) {
+      float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxJ; ++j)
-    if (j < J) out[(size_t)j * kDim + c] = dwacc[j];
+      for (int p = 0; p < kPhases; ++p) s += sdx[(p * F + x) * kDim + c];
+      dtokens[((size_t)b * T + 1 + (size_t)ty * F + x) * kDim + c] = __float2bfloat16_rn(s);
+    }
+  __syncthreads();
+  float* sacc = sdx;  // [J][256], re-used after the token rows have been written
+  for (int p = 0; p < kPhases; ++p) {
+    if (q == p) {
+#pragma unroll
+      for (int j = 0; j < kMaxJ; ++j)
+        if (j < J) sacc[j * kDim + c] = (p == 0 ? 0.f : sacc[j * kDim + c]) + dwacc[j];
+    }
+    __syncthreads();
+  }
+  float* out = dw_partial + ((size_t)b * gridDim.x + ty) * J * kDim;
+  for (int i = threadIdx.x; i < J * kDim; i += 256 * kPhases) out[i] = sacc[i];
 }
 
 // dbias[j] = sum_{b, pix} dheat[b][j][pix]: one CTA per joint, fixed order
@@ -313,9 +329,15 @@ int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const floa
     return -1;
   }
   const int So = 4 * F;
-  const size_t smem = ((size_t)F * kDim + (size_t)J * So) * sizeof(float);
+  size_t accf = (size_t)kPhases * F * kDim;
+  if (accf < (size_t)kMaxJ * kDim) accf = (size_t)kMaxJ * kDim;  // the phase fold re-uses this space as [J][256]
+  const size_t smem = (accf + (size_t)kMaxJ * So + (size_t)kMaxJ * kDim) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("pose_head_bwd: feature side %d does not fit shared memory", F);
+    return -1;
+  }
   HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pose_head_bwd_kernel<<<dim3(F, B), 256, smem, st>>>(tokens, w, dheat, F, J, dtokens, dw_partial);
+  pose_head_bwd_kernel<<<dim3(F, B), 256 * kPhases, smem, st>>>(tokens, w, dheat, F, J, dtokens, dw_partial);
   if (int rc = launch_partial_sum(dw_partial, B * F, J * kDim, dw, st)) return rc;
   heat_bias_grad_kernel<<<J, 256, 0, st>>>(dheat, B, J, So * So, dbias);
   HGR_CHECK_CUDA(cudaGetLastError());

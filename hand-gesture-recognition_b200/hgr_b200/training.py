@@ -126,6 +126,9 @@ class TrainState:
 
 
 def train_state(model, device) -> TrainState:
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     st = getattr(model, "_train_state_obj", None)
     if st is None or st.device != device or not st.attached():
         st = TrainState(model, device)
@@ -204,7 +207,7 @@ def loss_and_grads(logits, heat, labels, target, target_weight, cls_weight=0.001
     _, j, h, w = heat.shape
     dev = logits.device
     loss3 = torch.empty(3, dtype=torch.float32, device=dev)
-    scratch = torch.empty(512, dtype=torch.float32, device=dev)
+    scratch = torch.empty(1024, dtype=torch.float32, device=dev)
     dlogits = torch.empty_like(logits) if want_grads else None
     dheat = torch.empty_like(heat) if want_grads else None
     # keep every converted operand alive until the launch is enqueued (a temporary's block could be re-used)

@@ -204,7 +204,7 @@ HGR_API int hgr_train_backward(hgr_train_plan_t* plan, const void* d_x, int x_dt
 
 /* train.py:63-64 / libs/loss.py: total = cls_weight * CrossEntropy(logits, labels) + JointsMSELoss(heatmaps, target,
  * target_weight).  d_loss3 = {total, weighted class loss, joints loss}; d_dlogits / d_dheatmaps (nullable) receive
- * d total / d logits and d total / d heatmaps.  d_scratch: >= 296 floats.  labels are int64. */
+ * d total / d logits and d total / d heatmaps.  d_scratch: >= 592 floats.  labels are int64. */
 HGR_API int hgr_loss(const float* d_logits, const float* d_heatmaps, const long long* d_labels, const float* d_target,
                      const float* d_target_weight, int B, int J, int C, int hw, float cls_weight, float* d_dlogits,
                      float* d_dheatmaps, float* d_scratch, float* d_loss3, void* stream);

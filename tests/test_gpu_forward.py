@@ -147,5 +147,6 @@ def test_errors_are_loud():
     with pytest.raises(TypeError):
         m(torch.zeros(1, 3, 192, 192, device="cuda", dtype=torch.float16))
     m.train()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 192, 192, device="cuda"))
+    from hgr_b200._lib import HgrError
+    with pytest.raises(HgrError, match="batch"):
+        m(torch.zeros(1, 3, 192, 192, device="cuda"))  # batch statistics need at least two crops

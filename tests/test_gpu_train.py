@@ -5,7 +5,7 @@ step (itself pinned against the REAL reference by tests/test_train_cpu.py).
 Stated tolerances.  The reference trains in fp32 (train.py:230); this path computes in bf16 with fp32
 accumulation and carries activations and inter-kernel gradients in bf16, so:
   * single backward kernels on bf16-rounded operands: rel-L2 <= 6e-3 (fp32 outputs) / 1e-2 (bf16 outputs);
-  * train-mode forward vs fp32 oracle: logits / heatmaps rel-L2 <= 3e-2, loss relative error <= 1e-2,
+  * train-mode forward vs fp32 oracle: logits / heatmaps rel-L2 <= 3e-2, loss relative error <= 2e-2,
     running statistics rel-L2 <= 1e-2;
   * parameter gradients vs fp32 oracle: judged against the reference's OWN bf16 noise floor, i.e. the same
     graph under torch.autocast(bfloat16) on the same inputs (oracle.train_step_grads(autocast_bf16=True)),
@@ -192,7 +192,7 @@ def test_train_forward_backward_vs_oracle(size, seed, batch):
     torch.cuda.synchronize()
     assert report("train logits", logits, cls_ref)[0] <= 3e-2
     assert report("train heatmaps", heat, hm_ref)[0] <= 3e-2
-    np.testing.assert_allclose(loss3.cpu().numpy(), loss_ref.numpy(), rtol=1e-2)
+    np.testing.assert_allclose(loss3.cpu().numpy(), loss_ref.numpy(), rtol=2e-2)
     named_b = dict(m.named_buffers())
     for k, v in stats_ref.items():
         assert report("stat " + k, named_b[k], v)[0] <= 1e-2, k
