@@ -73,7 +73,7 @@ __device__ __forceinline__ void score_block(const uint32_t (&qa)[2][4], uint32_t
 template <typename TP>
 __global__ void __launch_bounds__(kWarps * 32)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, TP* __restrict__ probs, int T,
-                 int Tp, float scale_log2e) {
+                 int Tp, float scale_log2e, int pp) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sk = sq + Tp * kPitch;
@@ -153,14 +153,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         s[nt][2] = key < T ? ex2((s[nt][2] - m1) * scale_log2e) * inv1 : 0.f;
         s[nt][3] = key + 1 < T ? ex2((s[nt][3] - m1) * scale_log2e) * inv1 : 0.f;
         if (probs != nullptr) {
-          TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
+          TP* pr = probs + ((size_t)(b * kHeads + h) * T) * pp;
           if (row0 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[nt][0]);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[nt][1]);
+            if (key < T) store_prob<TP>(pr + (size_t)row0 * pp + key, s[nt][0]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * pp + key + 1, s[nt][1]);
           }
           if (row1 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[nt][2]);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[nt][3]);
+            if (key < T) store_prob<TP>(pr + (size_t)row1 * pp + key, s[nt][2]);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * pp + key + 1, s[nt][3]);
           }
         }
       }
@@ -198,7 +198,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 template <typename TP, int NKB>
 __global__ void __launch_bounds__(kWarps * 32, 3)
 attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, TP* __restrict__ probs,
-                       int T, float scale_log2e, int reverse) {
+                       int T, float scale_log2e, int reverse, int pp) {
   constexpr int Tp = NKB * kKeyBlock;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -286,17 +286,17 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 #pragma unroll
     for (int kb = 0; kb < NKB; ++kb) {
       if (probs != nullptr) {
-        TP* pr = probs + ((size_t)(b * kHeads + h) * T) * T;
+        TP* pr = probs + ((size_t)(b * kHeads + h) * T) * pp;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int key = kb * kKeyBlock + nt * 8 + 2 * t;
           if (row0 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row0 * T + key, s[kb][nt][0] * inv0);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * T + key + 1, s[kb][nt][1] * inv0);
+            if (key < T) store_prob<TP>(pr + (size_t)row0 * pp + key, s[kb][nt][0] * inv0);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row0 * pp + key + 1, s[kb][nt][1] * inv0);
           }
           if (row1 < T) {
-            if (key < T) store_prob<TP>(pr + (size_t)row1 * T + key, s[kb][nt][2] * inv1);
-            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * T + key + 1, s[kb][nt][3] * inv1);
+            if (key < T) store_prob<TP>(pr + (size_t)row1 * pp + key, s[kb][nt][2] * inv1);
+            if (key + 1 < T) store_prob<TP>(pr + (size_t)row1 * pp + key + 1, s[kb][nt][3] * inv1);
           }
         }
       }
@@ -330,7 +330,8 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
-                     cudaStream_t stream, int reverse) {
+                     cudaStream_t stream, int reverse, int probs_pitch) {
+  const int pp = probs_pitch > 0 ? probs_pitch : T;
   const int Tp = (T + kKeyBlock - 1) / kKeyBlock * kKeyBlock;
   const size_t smem = (size_t)3 * Tp * kPitch * 2;
   if (smem > 227 * 1024) {
@@ -344,22 +345,22 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
     const size_t smem1 = (size_t)3 * 5 * kKeyBlock * kPitch * 2;
     if (attn_probs != nullptr && probs_dtype == DT_BF16)
       HGR_CHECK_CUDA(launch_pdl(attention_kernel_1pass<__nv_bfloat16, 5>, dim3(grid), dim3(kWarps * 32), smem1, stream, qkv,
-                                out, static_cast<__nv_bfloat16*>(attn_probs), T, scale_log2e, reverse));
+                                out, static_cast<__nv_bfloat16*>(attn_probs), T, scale_log2e, reverse, pp));
     else
       HGR_CHECK_CUDA(launch_pdl(attention_kernel_1pass<float, 5>, dim3(grid), dim3(kWarps * 32), smem1, stream, qkv, out,
-                                static_cast<float*>(attn_probs), T, scale_log2e, reverse));
+                                static_cast<float*>(attn_probs), T, scale_log2e, reverse, pp));
     return 0;
   }
   if (attn_probs != nullptr && probs_dtype == DT_BF16) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     HGR_CHECK_CUDA(launch_pdl(attention_kernel<__nv_bfloat16>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out,
-                              static_cast<__nv_bfloat16*>(attn_probs), T, Tp, scale_log2e));
+                              static_cast<__nv_bfloat16*>(attn_probs), T, Tp, scale_log2e, pp));
   } else {
     HGR_CHECK_CUDA(
         cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HGR_CHECK_CUDA(launch_pdl(attention_kernel<float>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out,
-                              static_cast<float*>(attn_probs), T, Tp, scale_log2e));
+                              static_cast<float*>(attn_probs), T, Tp, scale_log2e, pp));
   }
   return 0;
 }

@@ -114,8 +114,10 @@ int launch_fill_cls(__nv_bfloat16* tokens, const float* cls, const float* cls_st
                     cudaStream_t stream);
 
 // reverse: walk the (image, head) grid back to front (zig-zag order, see plan.cu)
+// probs_pitch: elements per row of the probability map (0 = T, dense (B, 8, T, T)); the training step stores
+// it with a 16-byte-aligned pitch so that the backward kernel can stage it with 128-bit copies
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
-                     cudaStream_t stream, int reverse = 0);
+                     cudaStream_t stream, int reverse = 0, int probs_pitch = 0);
 
 int launch_cls_head(const __nv_bfloat16* tokens, const float* gamma, const float* beta, const float* w /*[C][256]*/,
                     const float* bias, void* logits, int out_dtype, int B, int T, int num_classes,

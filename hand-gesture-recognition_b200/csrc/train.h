@@ -59,8 +59,11 @@ int launch_conv1_wgrad(const __nv_bfloat16* dz, const void* x, int x_dtype, int 
 int launch_partial_sum(const float* partial, int nparts, int n, float* dst, cudaStream_t st);
 
 // ---- ViT backward ----
-int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, const __nv_bfloat16* o,
-                         const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int T, cudaStream_t st);
+// probs: (B, 8, T, probs_pitch) bf16 (pitch 0 = T); a pitch that is a multiple of 8 and >= round_up(T, 32) is
+// staged with 128-bit copies and requires zero pad columns
+int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, int probs_pitch,
+                         const __nv_bfloat16* o, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int T,
+                         cudaStream_t st);
 int launch_cls_head_bwd(const __nv_bfloat16* tokens, const float* gamma, const float* beta, const float* w,
                         const float* dlogits, int B, int T, int NC, __nv_bfloat16* dtokens, float* dgamma,
                         float* dbeta, float* dw, float* dbias, cudaStream_t st);

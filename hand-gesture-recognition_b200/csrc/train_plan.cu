@@ -207,6 +207,9 @@ int check_train_config(int S, int J, int C, int B) {
   return 0;
 }
 
+// row pitch of the stored attention probabilities: 16-byte aligned rows, covers the 32-padded token count
+int probs_pitch(int T) { return (T + 31) / 32 * 32 + 8; }
+
 // workspace plan: every named buffer of the training step
 std::vector<WsBuf> train_workspace(int S, int J, int C, int B, size_t* total) {
   std::vector<WsBuf> v;
@@ -251,7 +254,7 @@ std::vector<WsBuf> train_workspace(int S, int J, int C, int B, size_t* total) {
     const std::string p = "l" + std::to_string(l) + ".";
     add(p + "ln1", R * kDim * 2, B, 1, T, kDim);
     add(p + "qkv", R * 3 * kDim * 2, B, 1, T, 3 * kDim);
-    add(p + "probs", (size_t)B * kHeads * T * T * 2, B, kHeads, T, T);
+    add(p + "probs", (size_t)B * kHeads * T * probs_pitch(T) * 2, B, kHeads, T, probs_pitch(T));
     add(p + "attn_out", R * kDim * 2, B, 1, T, kDim);
     add(p + "xmid", R * kDim * 2, B, 1, T, kDim);
     add(p + "ln2", R * kDim * 2, B, 1, T, kDim);
@@ -472,6 +475,8 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
     L.ln1 = pl->bp(p + "ln1");
     L.qkv = pl->bp(p + "qkv");
     L.probs = pl->bp(p + "probs");
+    // pad columns of the probability maps are never written by the forward kernel and must read as zero
+    if (cudaMemset(L.probs, 0, (size_t)B * kHeads * T * probs_pitch(T) * 2) != cudaSuccess) rc = -2;
     L.attn_out = pl->bp(p + "attn_out");
     L.xmid = pl->bp(p + "xmid");
     L.ln2 = pl->bp(p + "ln2");
@@ -586,7 +591,7 @@ int hgr_train_forward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, float*
     const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
     if (int rc = launch_layernorm(pl->x[l], L.ln1, pl->P(a + "norm.weight"), pl->P(a + "norm.bias"), R, st)) return rc;
     if (int rc = run(L.f_qkv, st)) return rc;
-    if (int rc = launch_attention(L.qkv, L.attn_out, L.probs, DT_BF16, B, T, st)) return rc;
+    if (int rc = launch_attention(L.qkv, L.attn_out, L.probs, DT_BF16, B, T, st, 0, probs_pitch(T))) return rc;
     if (int rc = run(L.f_out, st)) return rc;
     if (int rc = launch_layernorm(L.xmid, L.ln2, pl->P(f + "0.weight"), pl->P(f + "0.bias"), R, st)) return rc;
     if (int rc = run(L.f_ff1, st)) return rc;
@@ -647,7 +652,7 @@ int hgr_train_backward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const
                               pl->G(a + "to_out.weight"), st))
       return rc;
     if (int rc = run(L.b_dattn, st)) return rc;
-    if (int rc = launch_attention_bwd(L.qkv, L.probs, L.attn_out, pl->dattn, pl->dqkv, B, T, st)) return rc;
+    if (int rc = launch_attention_bwd(L.qkv, L.probs, probs_pitch(T), L.attn_out, pl->dattn, pl->dqkv, B, T, st)) return rc;
     if (int rc = launch_wgrad(pl->dqkv, 3 * kDim, L.ln1, kDim, (int)R, 1, 1, kDim, 3 * kDim, 1, 1, pl->wpartial,
                               pl->G(a + "to_qkv.weight"), st))
       return rc;
@@ -725,7 +730,7 @@ size_t hgr_wgrad_partial_floats(int cout, int cin, int k, long long pixels) {
 
 int hgr_attention_bwd(const void* d_qkv, const void* d_probs, const void* d_o, const void* d_do, void* d_dqkv, int B,
                       int T, void* stream) {
-  return launch_attention_bwd(static_cast<const bf16*>(d_qkv), static_cast<const bf16*>(d_probs),
+  return launch_attention_bwd(static_cast<const bf16*>(d_qkv), static_cast<const bf16*>(d_probs), 0,
                               static_cast<const bf16*>(d_o), static_cast<const bf16*>(d_do), static_cast<bf16*>(d_dqkv),
                               B, T, static_cast<cudaStream_t>(stream));
 }

@@ -3,9 +3,9 @@
 //   class head       (transformer.py:113-116,142-144)
 //   pose head        (transformer.py:118-127,146-150)
 // They run at the 32-crop training batch, where the step is launch- and latency-bound rather than
-// FLOP-bound, so these first versions use the CUDA cores with shared-memory staging, fp32 accumulation and
-// ownership-based accumulation (no atomics: every output element has exactly one writer, so the gradients
-// are bitwise reproducible).
+// FLOP-bound: the attention backward runs on mma.sync tiles, the two heads on the CUDA cores with shared-memory
+// staging; all use fp32 accumulation and ownership-based accumulation (no atomics: every output element has
+// exactly one writer, so the gradients are bitwise reproducible).
 #include "hgr_internal.h"
 #include "ptx.cuh"
 #include "train.h"
@@ -19,98 +19,200 @@ constexpr int kHd = 32;
 constexpr int kDim = 256;
 
 // ---------------------------------------------------------------------------------------------
-// Attention backward for one (image, head).  With P = softmax(S), S = scale * Q K^T, O = P V:
-//   dV = P^T dO,  dP = dO V^T,  dS = P o (dP - D),  D_i = sum_d dO_id O_id,  dQ = scale * dS K,  dK = scale * dS^T Q.
-// P is the bf16 probability map the forward pass stored; query rows are processed in blocks of 32.
-// Shared memory (fp32): Q, K, V, dO [T][33], dK, dV accumulators [T][32], one dS / P block [32][T + 1].
+// Attention backward for one (image, head) on mma.sync m16n8k16.  With P = softmax(S), S = scale * Q K^T, O = P V:
+//   dP = dO V^T,  D_i = sum_d dO_id O_id,  dS = P o (dP - D),  dQ = scale * dS K,  dK = scale * dS^T Q,  dV = P^T dO.
+// Q, K, V, dO (T x 32 each) and the bf16 probability map P the forward pass stored (T x T) are staged in shared
+// memory once.  Pass A: warp per 16-query tile, dP -> dS in registers (accumulator layout == A-fragment layout,
+// the forward kernel's P.V trick) -> dQ.  Pass B: warp per 16-key tile, the TRANSPOSED products
+// dP^T = V dO^T, dS^T = P^T o (dP^T - D) -> dK = dS^T Q and dV = P^T dO, so every output row has one owner and no
+// cross-warp reduction (bitwise reproducible).
 // ---------------------------------------------------------------------------------------------
-constexpr int kRowBlock = 32;
-constexpr int kAThreads = 256;
+constexpr int kBPitch = 40;   // bf16 elements per staged Q/K/V/dO row (80 B: conflict-free ldmatrix)
+constexpr int kBWarps = 5;
+constexpr int kBThreads = kBWarps * 32;
 
-__global__ void __launch_bounds__(kAThreads)
-attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs,
+// 16 x 32 block of A(16 x 32) . B^T where B rows ([n][k], pitch kBPitch) start at b_addr_lane
+__device__ __forceinline__ void mm_block_nt(const uint32_t (&a)[2][4], uint32_t b_addr_lane, float (&c)[4][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    uint32_t bf[4];
+    ldmatrix_x4(bf, b_addr_lane + nt * 8 * kBPitch * 2);
+    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    mma_bf16_16816(c[nt], a[0], bf[0], bf[1]);
+    mma_bf16_16816(c[nt], a[1], bf[2], bf[3]);
+  }
+}
+
+// acc(16 x 32) += A(16 x 32, fragments built from `v`) . B(32 x 32) with B rows ([k][n], pitch kBPitch) at b_addr_lane
+__device__ __forceinline__ void mm_block_nn(const float (&v)[4][4], uint32_t b_addr_lane, float (&acc)[4][4]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16x2(v[2 * j][0], v[2 * j][1]);
+    pa[1] = pack_bf16x2(v[2 * j][2], v[2 * j][3]);
+    pa[2] = pack_bf16x2(v[2 * j + 1][0], v[2 * j + 1][1]);
+    pa[3] = pack_bf16x2(v[2 * j + 1][2], v[2 * j + 1][3]);
+    const uint32_t addr = b_addr_lane + j * 16 * kBPitch * 2;
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bf[4];
+      ldmatrix_x4_trans(bf, addr + np * 32);
+      mma_bf16_16816(acc[2 * np], pa, bf[0], bf[1]);
+      mma_bf16_16816(acc[2 * np + 1], pa, bf[2], bf[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBThreads)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs, int pp,
                      const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
-                     __nv_bfloat16* __restrict__ dqkv, int T, float scale) {
-  extern __shared__ float sm[];
-  const int P33 = 33;
-  float* sq = sm;
-  float* sk = sq + T * P33;
-  float* sv = sk + T * P33;
-  float* sdo = sv + T * P33;
-  float* sdk = sdo + T * P33;          // [T][32]
-  float* sdv = sdk + T * 32;           // [T][32]
-  float* sds = sdv + T * 32;           // [32][T + 1]  dS block
-  float* sp = sds + kRowBlock * (T + 1);  // [32][T + 1]  P block
-  float* sD = sp + kRowBlock * (T + 1);   // [32]
+                     __nv_bfloat16* __restrict__ dqkv, int T, int Tp, float scale) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int spp = Tp + 8;  // staged P pitch (elements)
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smraw);
+  __nv_bfloat16* sk = sq + Tp * kBPitch;
+  __nv_bfloat16* sv = sk + Tp * kBPitch;
+  __nv_bfloat16* sdo = sv + Tp * kBPitch;
+  __nv_bfloat16* sp = sdo + Tp * kBPitch;              // [Tp][spp]
+  float* sD = reinterpret_cast<float*>(sp + Tp * spp);  // [Tp]
   const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
-  const int tid = threadIdx.x;
-  const size_t row_stride = 3 * kDim;
-  const __nv_bfloat16* qb = qkv + (size_t)b * T * row_stride + h * kHd;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t rs = 3 * kDim;
+  const __nv_bfloat16* qb = qkv + (size_t)b * T * rs + h * kHd;
+  const __nv_bfloat16* dob = d_o + (size_t)b * T * kDim + h * kHd;
+  const __nv_bfloat16* ob = o + (size_t)b * T * kDim + h * kHd;
 
-  for (int i = tid; i < T * 32; i += kAThreads) {
-    const int r = i >> 5, d = i & 31;
-    sq[r * P33 + d] = __bfloat162float(qb[(size_t)r * row_stride + d]);
-    sk[r * P33 + d] = __bfloat162float(qb[(size_t)r * row_stride + kDim + d]);
-    sv[r * P33 + d] = __bfloat162float(qb[(size_t)r * row_stride + 2 * kDim + d]);
-    sdo[r * P33 + d] = __bfloat162float(d_o[((size_t)b * T + r) * kDim + h * kHd + d]);
-    sdk[i] = 0.f;
-    sdv[i] = 0.f;
+  // ---- stage Q, K, V, dO (rows >= T zero) ----
+  for (int i = tid; i < 4 * Tp * 4; i += kBThreads) {
+    const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < T)
+      v = part < 3 ? __ldg(reinterpret_cast<const uint4*>(qb + (size_t)row * rs + part * kDim) + c)
+                   : __ldg(reinterpret_cast<const uint4*>(dob + (size_t)row * kDim) + c);
+    *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kBPitch + c * 8) = v;
+  }
+  // ---- stage P (rows / columns >= T zero) ----
+  const __nv_bfloat16* pb = probs + (size_t)(b * kHeads + h) * T * pp;
+  if ((pp & 7) == 0 && pp >= Tp) {
+    const int cpr = Tp >> 3;  // the buffer's pad columns are zero (cleared once by the plan)
+    for (int i = tid; i < Tp * cpr; i += kBThreads) {
+      const int row = i / cpr, c = i % cpr;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row < T) v = __ldg(reinterpret_cast<const uint4*>(pb + (size_t)row * pp) + c);
+      *reinterpret_cast<uint4*>(sp + row * spp + c * 8) = v;
+    }
+  } else {
+    for (int i = tid; i < Tp * Tp; i += kBThreads) {
+      const int row = i / Tp, c = i % Tp;
+      sp[row * spp + c] = (row < T && c < T) ? pb[(size_t)row * pp + c] : __float2bfloat16_rn(0.f);
+    }
+  }
+  // ---- D_i = sum_d dO_id O_id ----
+  for (int r = tid; r < Tp; r += kBThreads) {
+    float dsum = 0.f;
+    if (r < T) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 a4 = __ldg(reinterpret_cast<const uint4*>(dob + (size_t)r * kDim) + c);
+        const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(ob + (size_t)r * kDim) + c);
+        const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dsum = fmaf(bf16_lo(aw[e]), bf16_lo(bw[e]), fmaf(bf16_hi(aw[e]), bf16_hi(bw[e]), dsum));
+      }
+    }
+    sD[r] = dsum;
   }
   __syncthreads();
 
-  const __nv_bfloat16* pb = probs + (size_t)(b * kHeads + h) * T * T;
-  for (int i0 = 0; i0 < T; i0 += kRowBlock) {
-    const int nr = T - i0 < kRowBlock ? T - i0 : kRowBlock;
-    // D_i and the P block
-    if (tid < nr) {
-      const int r = i0 + tid;
-      float dsum = 0.f;
-      for (int d = 0; d < 32; ++d)
-        dsum = fmaf(sdo[r * P33 + d], __bfloat162float(o[((size_t)b * T + r) * kDim + h * kHd + d]), dsum);
-      sD[tid] = dsum;
-    }
-    for (int i = tid; i < nr * T; i += kAThreads) {
-      const int r = i / T, j = i % T;
-      sp[r * (T + 1) + j] = __bfloat162float(pb[(size_t)(i0 + r) * T + j]);
-    }
-    __syncthreads();
-    // dS_ij = P_ij * (sum_d dO_id V_jd - D_i)
-    for (int i = tid; i < nr * T; i += kAThreads) {
-      const int r = i / T, j = i % T;
-      float dp = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < 32; ++d) dp = fmaf(sdo[(i0 + r) * P33 + d], sv[j * P33 + d], dp);
-      sds[r * (T + 1) + j] = sp[r * (T + 1) + j] * (dp - sD[r]);
-    }
-    __syncthreads();
-    // dQ rows of this block: thread (r = tid / 32 + 8 m, d = tid % 32)
-    {
-      const int d = tid & 31;
-      for (int r = tid >> 5; r < nr; r += kAThreads / 32) {
-        float acc = 0.f;
-        for (int j = 0; j < T; ++j) acc = fmaf(sds[r * (T + 1) + j], sk[j * P33 + d], acc);
-        dqkv[((size_t)b * T + i0 + r) * row_stride + h * kHd + d] = __float2bfloat16_rn(acc * scale);
+  const int ntiles = (T + 15) >> 4;
+  const int nblocks = Tp >> 5;  // 32-wide blocks
+  // lane addresses: A fragments of 16 rows (ldmatrix), "n-major" B (rows = n, ldmatrix), "k-major" B (rows = k, .trans)
+  const uint32_t a_off = ((lane & 15) * kBPitch + (lane >> 4) * 8) * 2;
+  const uint32_t bn_off = ((lane & 7) * kBPitch + (lane >> 3) * 8) * 2;
+  const uint32_t bk_off = ((((lane >> 3) & 1) * 8 + (lane & 7)) * kBPitch + (lane >> 4) * 8) * 2;
+  const uint32_t uq = smem_u32(sq), uk = smem_u32(sk), uv = smem_u32(sv), udo = smem_u32(sdo);
+
+  // ================= pass A: dQ, warp per 16-query tile =================
+  for (int mt = warp; mt < ntiles; mt += kBWarps) {
+    uint32_t da[2][4];
+    ldmatrix_x4(da[0], udo + a_off + mt * 16 * kBPitch * 2);
+    ldmatrix_x4(da[1], udo + a_off + mt * 16 * kBPitch * 2 + 32);
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const float D0 = sD[r0], D1 = sD[r1];
+    float acc[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+    for (int kb = 0; kb < nblocks; ++kb) {
+      float ds[4][4];
+      mm_block_nt(da, uv + bn_off + kb * 32 * kBPitch * 2, ds);  // dP block = dO V^T
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int key = kb * 32 + nt * 8 + 2 * t;
+        const uint32_t p0 = *reinterpret_cast<const uint32_t*>(sp + r0 * spp + key);
+        const uint32_t p1 = *reinterpret_cast<const uint32_t*>(sp + r1 * spp + key);
+        ds[nt][0] = bf16_lo(p0) * (ds[nt][0] - D0);
+        ds[nt][1] = bf16_hi(p0) * (ds[nt][1] - D0);
+        ds[nt][2] = bf16_lo(p1) * (ds[nt][2] - D1);
+        ds[nt][3] = bf16_hi(p1) * (ds[nt][3] - D1);
       }
+      mm_block_nn(ds, uk + bk_off + kb * 32 * kBPitch * 2, acc);  // dQ += dS K
     }
-    // dK_j += sum_r dS_rj Q_r,  dV_j += sum_r P_rj dO_r : thread owns (j = tid / 32 + 8 m, d = tid % 32)
-    {
-      const int d = tid & 31;
-      for (int j = tid >> 5; j < T; j += kAThreads / 32) {
-        float ak = sdk[j * 32 + d], av = sdv[j * 32 + d];
-        for (int r = 0; r < nr; ++r) {
-          ak = fmaf(sds[r * (T + 1) + j], sq[(i0 + r) * P33 + d], ak);
-          av = fmaf(sp[r * (T + 1) + j], sdo[(i0 + r) * P33 + d], av);
-        }
-        sdk[j * 32 + d] = ak;
-        sdv[j * 32 + d] = av;
-      }
+    __nv_bfloat16* q0 = dqkv + ((size_t)b * T + r0) * rs + h * kHd + 2 * t;
+    __nv_bfloat16* q1 = dqkv + ((size_t)b * T + r1) * rs + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      if (r0 < T) *reinterpret_cast<uint32_t*>(q0 + nd * 8) = pack_bf16x2(acc[nd][0] * scale, acc[nd][1] * scale);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(q1 + nd * 8) = pack_bf16x2(acc[nd][2] * scale, acc[nd][3] * scale);
     }
-    __syncthreads();
   }
-  for (int i = tid; i < T * 32; i += kAThreads) {
-    const int r = i >> 5, d = i & 31;
-    dqkv[((size_t)b * T + r) * row_stride + kDim + h * kHd + d] = __float2bfloat16_rn(sdk[i] * scale);
-    dqkv[((size_t)b * T + r) * row_stride + 2 * kDim + h * kHd + d] = __float2bfloat16_rn(sdv[i]);
+
+  // ================= pass B: dK, dV, warp per 16-key tile =================
+  const unsigned short* spu = reinterpret_cast<const unsigned short*>(sp);
+  for (int kt = warp; kt < ntiles; kt += kBWarps) {
+    uint32_t va[2][4];
+    ldmatrix_x4(va[0], uv + a_off + kt * 16 * kBPitch * 2);
+    ldmatrix_x4(va[1], uv + a_off + kt * 16 * kBPitch * 2 + 32);
+    const int c0 = kt * 16 + g, c1 = c0 + 8;
+    float ak[4][4], av[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      ak[nd][0] = ak[nd][1] = ak[nd][2] = ak[nd][3] = 0.f;
+      av[nd][0] = av[nd][1] = av[nd][2] = av[nd][3] = 0.f;
+    }
+    for (int qblk = 0; qblk < nblocks; ++qblk) {
+      float dst[4][4], pt[4][4];
+      mm_block_nt(va, udo + bn_off + qblk * 32 * kBPitch * 2, dst);  // dP^T block = V dO^T
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int q = qblk * 32 + nt * 8 + 2 * t;
+        const float Dq0 = sD[q], Dq1 = sD[q + 1];
+        pt[nt][0] = __uint_as_float((uint32_t)spu[q * spp + c0] << 16);
+        pt[nt][1] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c0] << 16);
+        pt[nt][2] = __uint_as_float((uint32_t)spu[q * spp + c1] << 16);
+        pt[nt][3] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c1] << 16);
+        dst[nt][0] = pt[nt][0] * (dst[nt][0] - Dq0);
+        dst[nt][1] = pt[nt][1] * (dst[nt][1] - Dq1);
+        dst[nt][2] = pt[nt][2] * (dst[nt][2] - Dq0);
+        dst[nt][3] = pt[nt][3] * (dst[nt][3] - Dq1);
+      }
+      mm_block_nn(dst, uq + bk_off + qblk * 32 * kBPitch * 2, ak);  // dK += dS^T Q
+      mm_block_nn(pt, udo + bk_off + qblk * 32 * kBPitch * 2, av);  // dV += P^T dO
+    }
+    __nv_bfloat16* k0 = dqkv + ((size_t)b * T + c0) * rs + kDim + h * kHd + 2 * t;
+    __nv_bfloat16* k1 = dqkv + ((size_t)b * T + c1) * rs + kDim + h * kHd + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      if (c0 < T) {
+        *reinterpret_cast<uint32_t*>(k0 + nd * 8) = pack_bf16x2(ak[nd][0] * scale, ak[nd][1] * scale);
+        *reinterpret_cast<uint32_t*>(k0 + kDim + nd * 8) = pack_bf16x2(av[nd][0], av[nd][1]);
+      }
+      if (c1 < T) {
+        *reinterpret_cast<uint32_t*>(k1 + nd * 8) = pack_bf16x2(ak[nd][2] * scale, ak[nd][3] * scale);
+        *reinterpret_cast<uint32_t*>(k1 + kDim + nd * 8) = pack_bf16x2(av[nd][2], av[nd][3]);
+      }
+    }
   }
 }
 
@@ -294,16 +396,18 @@ heat_bias_grad_kernel(const float* __restrict__ dheat, int B, int J, int hw, flo
 
 }  // namespace
 
-int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, const __nv_bfloat16* o,
-                         const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int T, cudaStream_t st) {
-  const size_t floats = (size_t)4 * T * 33 + (size_t)2 * T * 32 + (size_t)2 * kRowBlock * (T + 1) + kRowBlock;
-  const size_t smem = floats * sizeof(float);
+int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, int probs_pitch,
+                         const __nv_bfloat16* o, const __nv_bfloat16* d_o, __nv_bfloat16* dqkv, int B, int T,
+                         cudaStream_t st) {
+  const int Tp = (T + 31) / 32 * 32;
+  const int pp = probs_pitch > 0 ? probs_pitch : T;
+  const size_t smem = ((size_t)4 * Tp * kBPitch + (size_t)Tp * (Tp + 8)) * 2 + (size_t)Tp * sizeof(float);
   if (smem > 227 * 1024) {
-    set_error("attention_bwd: %d tokens do not fit one CTA's shared memory", T);
+    set_error("attention_bwd: %d tokens do not fit one CTA's shared memory (%zu bytes)", T, smem);
     return -1;
   }
   HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_bwd_kernel<<<B * kHeads, kAThreads, smem, st>>>(qkv, probs, o, d_o, dqkv, T, 0.17677669529663687f);
+  attention_bwd_kernel<<<B * kHeads, kBThreads, smem, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, 0.17677669529663687f);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

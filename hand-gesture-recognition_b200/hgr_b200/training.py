@@ -175,7 +175,8 @@ class _TrainFunction(torch.autograd.Function):
         ctx.state, ctx.plan, ctx.x = state, plan, x
         attn = None
         if model.return_attention:
-            attn = plan.buffer(f"l{3}.probs").to(x.dtype)
+            t = model.image_size[0] // 16 * (model.image_size[0] // 16) + 1
+            attn = plan.buffer(f"l{3}.probs")[..., :t].to(x.dtype)  # rows are stored with a padded pitch
             ctx.mark_non_differentiable(attn)
         if x.dtype != torch.float32:
             logits, heat = logits.to(x.dtype), heat.to(x.dtype)
