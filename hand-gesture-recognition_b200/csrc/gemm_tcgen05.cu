@@ -38,11 +38,15 @@ constexpr int kMaxCout = 1024;
 template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * kTileK * 2;
-  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+  // BN = 128 (3x3 convs of cspelan2, conv2) is bound by operand delivery from L2, not by the tensor pipe or HBM:
+  // a k-step is 32 KiB for 256 MMA cycles, so the bytes in flight decide.  It trades the second output
+  // staging buffer of each epilogue group for a fifth pipeline stage.
+  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int kOutBufs = BN == 128 ? 1 : 2;  // staging buffers per epilogue group
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
-  static constexpr int kOffOut = kOffB + kStages * kBBytes;     // [2 groups][2 bufs][16 KiB]
-  static constexpr int kOffScale = kOffOut + 4 * kStageBufBytes;  // scale[kMaxCout], shift[kMaxCout]
+  static constexpr int kOffOut = kOffB + kStages * kBBytes;     // [2 groups][kOutBufs][16 KiB]
+  static constexpr int kOffScale = kOffOut + 2 * kOutBufs * kStageBufBytes;  // scale[kMaxCout], shift[kMaxCout]
   static constexpr int kOffBars = kOffScale + 2 * kMaxCout * 4;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
@@ -381,8 +385,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ================= epilogue groups =================
     const int group = (warp - 4) >> 2;  // accumulator stage this group drains
-    epilogue_group<BN, ACT, RES, 2, ROW>(p, &tmO, tm, smem + C::kOffOut + group * 2 * kStageBufBytes, s_scale, s_shift,
-                                         acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
+    epilogue_group<BN, ACT, RES, C::kOutBufs, ROW>(p, &tmO, tm, smem + C::kOffOut + group * C::kOutBufs * kStageBufBytes,
+                                                   s_scale, s_shift, acc_full_bar, acc_empty_bar, tmem_base, group,
+                                                   total_tiles);
   }
 
   // ---- teardown ---------------------------------------------------------

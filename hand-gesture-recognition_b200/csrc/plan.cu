@@ -979,4 +979,14 @@ int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, 
   return launch_crop_normalize(d_hwc, d_chw, out_dtype, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int hgr_crop_warp_normalize(const uint8_t* d_frames, int F, int Hf, int Wf, const int* d_frame_index,
+                            const double* d_inv_mats, int N, int S, void* d_chw, int out_dtype, void* stream) {
+  if (!d_frames || !d_frame_index || !d_inv_mats || !d_chw) {
+    set_error("hgr_crop_warp_normalize: null argument");
+    return -1;
+  }
+  return launch_crop_warp_normalize(d_frames, F, Hf, Wf, d_frame_index, d_inv_mats, N, S, d_chw, out_dtype,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -184,6 +184,76 @@ crop_normalize_kernel(const uint8_t* __restrict__ hwc, TOut* __restrict__ chw, l
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Crop front-end (reference detect.py:92-117): cv2.warpAffine(frame, trans, (S, S),
+// INTER_LINEAR) of the detector box followed by the crop normalisation, fused - the uint8 crop never exists.
+// OpenCV's warpAffine is integer arithmetic and is reproduced bit for bit: the inverse map is evaluated in
+// double precision exactly as imgwarp.cpp does (no FMA contraction), source coordinates are rounded to 1/1024 px
+// (AB_BITS = 10), reduced to 1/32 px (INTER_BITS = 5), the four taps are weighted with
+// (32 - fx)(32 - fy) * 32, ... out of 2^15 and the result is (sum + 2^14) >> 15; taps outside the frame read 0
+// (BORDER_CONSTANT).  One thread per output pixel, three planes written with coalesced stores.
+// ---------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+crop_warp_normalize_kernel(const uint8_t* __restrict__ frames, int Hf, int Wf, const int* __restrict__ frame_index,
+                           const double* __restrict__ inv_mats, int S, TOut* __restrict__ out) {
+  __shared__ float lut[3][256];
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8, v = i & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), mean[c]), stdv[c]);
+  }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const double* m = inv_mats + (size_t)n * 6;
+  const uint8_t* img = frames + (size_t)frame_index[n] * Hf * Wf * 3;
+  const int hw = S * S;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += gridDim.x * blockDim.x) {
+    const int y = pix / S, x = pix - y * S;
+    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(m[0], (double)x), 1024.0));
+    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(m[3], (double)x), 1024.0));
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[1], (double)y), m[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(m[4], (double)y), m[5]), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    int sx = X >> 5, sy = Y >> 5;
+    sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);  // saturate_cast<short>
+    sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    int acc[3] = {0, 0, 0};
+    const bool x0ok = sx >= 0 && sx < Wf, x1ok = sx + 1 >= 0 && sx + 1 < Wf;
+    const bool y0ok = sy >= 0 && sy < Hf, y1ok = sy + 1 >= 0 && sy + 1 < Hf;
+    if (y0ok) {
+      const uint8_t* row = img + (size_t)sy * Wf * 3;
+      if (x0ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += w00 * row[sx * 3 + c];
+      }
+      if (x1ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += w01 * row[(sx + 1) * 3 + c];
+      }
+    }
+    if (y1ok) {
+      const uint8_t* row = img + (size_t)(sy + 1) * Wf * 3;
+      if (x0ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += w10 * row[sx * 3 + c];
+      }
+      if (x1ok) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += w11 * row[(sx + 1) * 3 + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v = (acc[c] + (1 << 14)) >> 15;
+      store1<TOut>(out + ((size_t)n * 3 + c) * hw + pix, lut[c][v > 255 ? 255 : v]);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw, int width, float* preds,
@@ -214,6 +284,24 @@ int launch_crop_normalize(const uint8_t* hwc, void* chw, int out_dtype, int B, i
   else
     crop_normalize_kernel<__nv_bfloat16>
         <<<blocks, 256, 0, stream>>>(hwc, static_cast<__nv_bfloat16*>(chw), npix, H * W);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_crop_warp_normalize(const uint8_t* frames, int F, int Hf, int Wf, const int* frame_index,
+                               const double* inv_mats, int N, int S, void* out, int out_dtype, cudaStream_t stream) {
+  if (N <= 0) return 0;
+  if (F < 1 || Hf < 1 || Wf < 1 || S < 1 || Hf > 32767 || Wf > 32767) {
+    set_error("crop_warp_normalize: bad shape (frames %d x %d x %d, crop %d)", F, Hf, Wf, S);
+    return -1;
+  }
+  dim3 grid((S * S + 255) / 256, N);
+  if (out_dtype == DT_F32)
+    crop_warp_normalize_kernel<float><<<grid, 256, 0, stream>>>(frames, Hf, Wf, frame_index, inv_mats, S,
+                                                                static_cast<float*>(out));
+  else
+    crop_warp_normalize_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(frames, Hf, Wf, frame_index, inv_mats, S,
+                                                                        static_cast<__nv_bfloat16*>(out));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -89,6 +89,50 @@ class HandPipeline:
         ln.busy = True
         return i
 
+    def submit_frames(self, frames_u8: torch.Tensor, boxes, frame_index=None) -> int:
+        """The whole classifier stage of detect.py:119-155 for `batch` detector boxes: frames (F, Hf, Wf, 3) uint8
+        in HOST memory are copied to the device, every box is warped to the crop size with cv2.warpAffine's
+        arithmetic and normalised in ONE kernel (crop_warp_normalize), then forward + keypoint decode as in submit()."""
+        from .ops import box_to_affine, invert_affine
+        import numpy as np
+        lib = _lib.load()
+        i = self._next
+        self._next = (self._next + 1) % len(self.lanes)
+        ln = self.lanes[i]
+        if ln.busy:
+            raise RuntimeError("lane still holds an uncollected batch; call collect() first")
+        if len(boxes) != self.batch:
+            raise ValueError(f"expected {self.batch} boxes (the plan's batch), got {len(boxes)}")
+        if frames_u8.dtype != torch.uint8 or frames_u8.is_cuda or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+            raise ValueError("expected host uint8 frames (F, Hf, Wf, 3)")
+        m = self.model
+        s = m.image_size[0]
+        idx = np.zeros(self.batch, dtype=np.int32) if frame_index is None else np.asarray(frame_index, dtype=np.int32)
+        inv = np.stack([invert_affine(box_to_affine(b, s)) for b in boxes])
+        dt = _lib.F32 if self.dtype == torch.float32 else _lib.BF16
+        with torch.cuda.device(self.device), torch.cuda.stream(ln.stream):
+            ln.d_frames = frames_u8.contiguous().to(self.device, non_blocking=True)
+            ln.d_inv = torch.from_numpy(np.ascontiguousarray(inv)).to(self.device, non_blocking=True)
+            ln.d_idx = torch.from_numpy(idx).to(self.device, non_blocking=True)
+            st = ln.stream.cuda_stream
+            _lib.check(lib.hgr_crop_warp_normalize(ln.d_frames.data_ptr(), frames_u8.shape[0], frames_u8.shape[1],
+                                                   frames_u8.shape[2], ln.d_idx.data_ptr(), ln.d_inv.data_ptr(),
+                                                   self.batch, s, ln.d_x.data_ptr(), dt, st), "hgr_crop_warp_normalize")
+            _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
+                                       ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
+            _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
+                                             ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
+            ln.h_logits.copy_(ln.d_logits, non_blocking=True)
+            ln.h_preds.copy_(ln.d_preds, non_blocking=True)
+            ln.h_maxvals.copy_(ln.d_maxvals, non_blocking=True)
+            ln.done.record(ln.stream)
+        ln.busy = True
+        return i
+
+    def infer_frames(self, frames_u8: torch.Tensor, boxes, frame_index=None):
+        a, b, c = self.collect(self.submit_frames(frames_u8, boxes, frame_index))
+        return a.clone(), b.clone(), c.clone()
+
     def collect(self, lane: int):
         """Wait for a submitted batch; returns host tensors (logits, preds, maxvals) valid until the lane is reused."""
         ln = self.lanes[lane]

@@ -165,6 +165,13 @@ HGR_API int hgr_get_max_preds(const void* d_heatmaps, int dtype, int B, int J, i
  * ((v / 255) - mean[c]) / std[c], ImageNet constants by channel index. */
 HGR_API int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, int H, int W, void* stream);
 
+/* detect.py:92-117 fused: cv2.warpAffine(frame, trans, (S, S), flags=INTER_LINEAR) (bit-exact fixed-point
+ * arithmetic of OpenCV, constant border 0) + the normalisation above, for N crops out of F frames
+ * (F, Hf, Wf, 3) uint8.  d_inv_mats: N x 6 doubles, the INVERTED affine maps (crop pixel -> frame pixel) exactly
+ * as cv::warpAffine derives them from `trans`; d_frame_index: N ints.  Output (N, 3, S, S). */
+HGR_API int hgr_crop_warp_normalize(const uint8_t* d_frames, int F, int Hf, int Wf, const int* d_frame_index,
+                                    const double* d_inv_mats, int N, int S, void* d_chw, int out_dtype, void* stream);
+
 /* ------------------------------------------------------------------------
  * Training step (BASELINE.json configs[4]; reference train.py:58-108 with
  * libs/loss.py and torch.optim.AdamW).  Parameters, gradients and BatchNorm

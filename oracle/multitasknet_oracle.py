@@ -355,3 +355,97 @@ def adamw_step(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, wd=0
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     denom = v.sqrt() / (bc2 ** 0.5) + eps
     return p - (lr / bc1) * m / denom, m, v
+
+
+# --------------------------------------------------------------------------
+# crop front-end: detect.py:92-117 = get_affine_transform + cv2.warpAffine(INTER_LINEAR) + normalise
+# --------------------------------------------------------------------------
+def get_affine_transform(center, scale, rot, origin_size, output_size):
+    """libs/transforms.py:20-54 with shift = 0, inv = 0, restated without OpenCV: the three point pairs the
+    reference builds (float32, like its np.zeros((3, 2), float32) arrays) and the 2x3 matrix mapping src -> dst
+    (cv2.getAffineTransform solves the same 6x6 system in double precision)."""
+    scale_tmp = np.array([scale, scale], dtype=np.float64) * origin_size
+    src_w = scale_tmp[0]
+    dst_w, dst_h = output_size[0], output_size[1]
+    rot_rad = np.pi * rot / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    src_dir = np.array([0 * cs - (src_w * -0.5) * sn, 0 * sn + (src_w * -0.5) * cs])
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = center
+    src[1, :] = center + src_dir
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + dst_dir
+
+    def third(a, b):
+        d = a - b
+        return b + np.array([-d[1], d[0]], dtype=np.float32)
+
+    src[2, :] = third(src[0, :], src[1, :])
+    dst[2, :] = third(dst[0, :], dst[1, :])
+    a = np.zeros((6, 6))
+    b = np.zeros(6)
+    for i in range(3):
+        a[2 * i] = [src[i, 0], src[i, 1], 1, 0, 0, 0]
+        a[2 * i + 1] = [0, 0, 0, src[i, 0], src[i, 1], 1]
+        b[2 * i], b[2 * i + 1] = dst[i, 0], dst[i, 1]
+    return np.linalg.solve(a, b).reshape(2, 3)
+
+
+def invert_affine(m):
+    """cv::invertAffineTransform's arithmetic as warpAffine applies it (imgwarp.cpp), in float64, same order."""
+    m = np.array(m, dtype=np.float64).reshape(6).copy()
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0] = a11
+    m[1] *= -d
+    m[3] *= -d
+    m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
+
+
+def warp_affine_linear_u8(img, trans, out_w, out_h):
+    """cv2.warpAffine(img, trans, (out_w, out_h), flags=INTER_LINEAR) for uint8 images, border constant 0,
+    restated with OpenCV's fixed-point arithmetic: source coordinates in 1/1024 px (AB_BITS = 10) rounded to
+    1/32 px (INTER_BITS = 5), bilinear weights (32 - fx)(32 - fy) * 32 etc. out of 32768, result
+    (sum + 16384) >> 15."""
+    m = invert_affine(trans)
+    h, w = img.shape[:2]
+    xs = np.arange(out_w, dtype=np.float64)
+    ys = np.arange(out_h, dtype=np.float64)
+    adelta = np.rint(m[0] * xs * 1024.0).astype(np.int64)
+    bdelta = np.rint(m[3] * xs * 1024.0).astype(np.int64)
+    x0 = np.rint((m[1] * ys + m[2]) * 1024.0).astype(np.int64) + 16
+    y0 = np.rint((m[4] * ys + m[5]) * 1024.0).astype(np.int64) + 16
+    xx = (x0[:, None] + adelta[None, :]) >> 5
+    yy = (y0[:, None] + bdelta[None, :]) >> 5
+    sx, sy = xx >> 5, yy >> 5
+    fx, fy = xx & 31, yy & 31
+    src = img.astype(np.int64)
+
+    def tap(yi, xi):
+        ok = (yi >= 0) & (yi < h) & (xi >= 0) & (xi < w)
+        v = src[np.clip(yi, 0, h - 1), np.clip(xi, 0, w - 1)]
+        return v * ok[..., None]
+
+    w00 = ((32 - fx) * (32 - fy) * 32)[..., None]
+    w01 = (fx * (32 - fy) * 32)[..., None]
+    w10 = ((32 - fx) * fy * 32)[..., None]
+    w11 = (fx * fy * 32)[..., None]
+    acc = tap(sy, sx) * w00 + tap(sy, sx + 1) * w01 + tap(sy + 1, sx) * w10 + tap(sy + 1, sx + 1) * w11
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def process_image_for_classification(img, bbox, size):
+    """detect.py:92-117: bbox -> affine crop to size x size -> /255 -> mean/std -> (1, 3, size, size) float32."""
+    x1, y1, x2, y2 = bbox
+    c = np.array([(x1 + x2) / 2, (y1 + y2) / 2], dtype=np.float32)
+    origin_size = max(x2 - x1, y2 - y1) * 1.0
+    trans = get_affine_transform(c, 1, 0, origin_size, [size, size])
+    crop = warp_affine_linear_u8(img, trans, size, size)
+    return crop_normalize(crop), trans

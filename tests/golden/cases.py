@@ -31,3 +31,19 @@ def crop_image():
     img[..., 1] = img[..., 1][::-1]
     img[..., 2] = np.roll(img[..., 2], 7)
     return img
+
+
+def crop_frame():
+    """A 360 x 480 BGR uint8 frame: smooth gradients plus seeded noise (every tap of the bilinear stencil matters)."""
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[0:360, 0:480]
+    base = np.stack([(xx * 255 // 479), (yy * 255 // 359), ((xx + yy) * 255 // 838)], axis=-1)
+    noise = rng.integers(-40, 41, base.shape)
+    return np.clip(base + noise, 0, 255).astype(np.uint8)
+
+
+def crop_boxes():
+    """(detector box (x1, y1, x2, y2), crop size): inside, touching and crossing the frame border, tiny, whole frame."""
+    return [((100, 80, 300, 290), 192), ((0, 0, 200, 150), 192), ((380, 250, 560, 430), 192),
+            ((-40, -30, 90, 100), 192), ((210, 150, 240, 185), 192), ((5, 5, 475, 355), 192),
+            ((120, 60, 360, 330), 256), ((33, 47, 161, 200), 64)]

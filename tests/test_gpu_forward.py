@@ -150,3 +150,26 @@ def test_errors_are_loud():
     from hgr_b200._lib import HgrError
     with pytest.raises(HgrError, match="batch"):
         m(torch.zeros(1, 3, 192, 192, device="cuda"))  # batch statistics need at least two crops
+
+
+def test_hand_pipeline_matches_the_module_and_the_frames_path():
+    """detect.py:119-155 batched: HandPipeline (host uint8 crops -> logits, keypoints, confidences) gives exactly
+    what module.forward + get_max_preds give on the normalised crops, and the frames + boxes path (fused
+    warpAffine) gives exactly what the crops path gives on the crops OpenCV's arithmetic produces."""
+    from hgr_b200 import HandPipeline, crop_normalize, get_max_preds
+    from tests.golden.cases import crop_frame
+    m, _ = build(192, 0)
+    m.return_attention = False
+    frame = crop_frame()
+    boxes = [(100, 80, 300, 290), (0, 0, 200, 150), (380, 250, 560, 430), (-40, -30, 90, 100)]
+    crops = np.stack([O.warp_affine_linear_u8(frame, O.get_affine_transform(
+        np.array([(b[0] + b[2]) / 2, (b[1] + b[3]) / 2], dtype=np.float32), 1, 0, max(b[2] - b[0], b[3] - b[1]) * 1.0,
+        [192, 192]), 192, 192) for b in boxes])
+    pipe = HandPipeline(m, 4, torch.float32)
+    logits, kps, conf = pipe.infer(torch.from_numpy(crops))
+    with torch.no_grad():
+        cls, hm, _ = m(crop_normalize(torch.from_numpy(crops).cuda()))
+    preds, maxvals = get_max_preds(hm)
+    assert torch.equal(logits, cls.cpu()) and torch.equal(kps, preds.cpu()) and torch.equal(conf, maxvals.cpu())
+    l2, k2, c2 = pipe.infer_frames(torch.from_numpy(frame)[None], boxes)
+    assert torch.equal(l2, logits) and torch.equal(k2, kps) and torch.equal(c2, conf)

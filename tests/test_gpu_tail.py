@@ -86,3 +86,42 @@ def test_crop_normalize_golden_and_oracle():
     _same_bits(got, np.concatenate([O.crop_normalize(b) for b in odd], 0))
     with pytest.raises(RuntimeError):
         crop_normalize(torch.from_numpy(img))
+
+
+# ------------------------------------------------------------------ crop front-end ----
+def test_crop_warp_normalize_golden_is_bit_exact():
+    """detect.py:92-117 fused on the device against cv2.warpAffine + the reference's get_affine_transform
+    (golden CRC32 of the fp32 result) and against the oracle's fixed-point restatement, word for word."""
+    import zlib
+    from hgr_b200 import crop_warp_normalize
+    from tests.golden.cases import crop_boxes, crop_frame
+    gold = np.load(GOLD / "crop_warp.npz")
+    frame = crop_frame()
+    dframe = torch.from_numpy(frame).cuda()
+    for i, (bbox, size) in enumerate(crop_boxes()):
+        out = crop_warp_normalize(dframe, [bbox], size=size).cpu().numpy()
+        ref, _ = O.process_image_for_classification(frame, bbox, size)
+        _same_bits(out, ref)
+        assert zlib.crc32(out.tobytes()) == int(gold[f"out_crc_{i}"][0]), i
+        # explicit matrix path (the matrix cv2.getAffineTransform produced inside the reference)
+        out2 = crop_warp_normalize(dframe, None, size=size, trans=[gold[f"trans_{i}"]]).cpu().numpy()
+        _same_bits(out2, ref)
+
+
+def test_crop_warp_normalize_batch_of_frames_and_bf16():
+    from hgr_b200 import crop_warp_normalize
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    boxes = [(10, 20, 90, 100), (-5, -5, 60, 70), (100, 60, 170, 130), (40, 30, 120, 110), (0, 0, 160, 120)]
+    index = [0, 1, 2, 1, 0]
+    out = crop_warp_normalize(torch.from_numpy(frames).cuda(), boxes, frame_index=index, size=64)
+    outb = crop_warp_normalize(torch.from_numpy(frames).cuda(), boxes, frame_index=index, size=64, dtype=torch.bfloat16)
+    for n, (b, f) in enumerate(zip(boxes, index)):
+        ref, _ = O.process_image_for_classification(frames[f], b, 64)
+        _same_bits(out[n: n + 1].cpu().numpy(), ref)
+        assert torch.equal(outb[n].float().cpu(), torch.from_numpy(ref[0]).to(torch.bfloat16).float())
+    assert crop_warp_normalize(torch.from_numpy(frames).cuda(), [], size=64).shape == (0, 3, 64, 64)
+    with pytest.raises(ValueError):
+        crop_warp_normalize(torch.from_numpy(frames).cuda(), boxes, frame_index=[0, 1, 2, 3, 0], size=64)
+    with pytest.raises(RuntimeError):
+        crop_warp_normalize(torch.from_numpy(frames), boxes, size=64)
