@@ -131,6 +131,11 @@ int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw
 
 int launch_crop_normalize(const uint8_t* hwc, void* chw, int out_dtype, int B, int H, int W, cudaStream_t stream);
 
+// libs/metrics.py pose_accuracy on decoded keypoints (B, J, 2) fp32; counts: 2*J ints of scratch; acc: J+1 doubles;
+// avg_cnt: {average accuracy, number of joints with a valid accuracy}
+int launch_pose_accuracy(const float* pred, const float* target, int B, int J, int H, int W, double thr, int* counts,
+                         double* acc, double* avg_cnt, cudaStream_t stream);
+
 // cv2.warpAffine(INTER_LINEAR, constant border 0) + crop normalisation, fused; inv_mats: N x 6 doubles, the
 // INVERTED 2x3 maps (dst -> src) as cv::warpAffine computes them; frame_index: N ints into the F frames.
 int launch_crop_warp_normalize(const uint8_t* frames, int F, int Hf, int Wf, const int* frame_index,

@@ -979,6 +979,16 @@ int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, 
   return launch_crop_normalize(d_hwc, d_chw, out_dtype, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
+int hgr_pose_accuracy(const float* d_pred, const float* d_target, int B, int J, int H, int W, double thr, int* d_counts,
+                      double* d_acc, double* d_avg_cnt, void* stream) {
+  if (!d_pred || !d_target || !d_counts || !d_acc || !d_avg_cnt) {
+    set_error("hgr_pose_accuracy: null argument");
+    return -1;
+  }
+  return launch_pose_accuracy(d_pred, d_target, B, J, H, W, thr, d_counts, d_acc, d_avg_cnt,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int hgr_crop_warp_normalize(const uint8_t* d_frames, int F, int Hf, int Wf, const int* d_frame_index,
                             const double* d_inv_mats, int N, int S, void* d_chw, int out_dtype, void* stream) {
   if (!d_frames || !d_frame_index || !d_inv_mats || !d_chw) {

@@ -254,6 +254,67 @@ crop_warp_normalize_kernel(const uint8_t* __restrict__ frames, int Hf, int Wf, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// PCK-style pose accuracy (reference libs/metrics.py:6-62) on decoded keypoints:
+//   dist[j][n] = || pred[n,j] / norm - target[n,j] / norm ||_2  with norm = (h / 10, w / 10) applied to (x, y)
+//                (the reference's own pairing), -1 where the target keypoint is not > 1 in both coordinates;
+//   acc[j + 1] = #(dist < thr) / #(dist != -1), or -1 when no sample is valid;  acc[0] = mean of the valid joints.
+// Arithmetic in float64 like numpy's (float32 / float64 promotes), one CTA per joint, ordered integer counts.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pck_joint_kernel(const float* __restrict__ pred, const float* __restrict__ target, int B, int J, double nx, double ny,
+                 double thr, int* __restrict__ counts /*[J][2] = valid, hit*/) {
+  __shared__ int s_valid[256], s_hit[256];
+  const int j = blockIdx.x;
+  int valid = 0, hit = 0;
+  for (int n = threadIdx.x; n < B; n += 256) {
+    const float tx = target[((size_t)n * J + j) * 2], ty = target[((size_t)n * J + j) * 2 + 1];
+    if (tx > 1.0f && ty > 1.0f) {
+      const float px = pred[((size_t)n * J + j) * 2], py = pred[((size_t)n * J + j) * 2 + 1];
+      const double dx = __dsub_rn(__ddiv_rn((double)px, nx), __ddiv_rn((double)tx, nx));
+      const double dy = __dsub_rn(__ddiv_rn((double)py, ny), __ddiv_rn((double)ty, ny));
+      const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      ++valid;
+      hit += d < thr ? 1 : 0;
+    }
+  }
+  s_valid[threadIdx.x] = valid;
+  s_hit[threadIdx.x] = hit;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_valid[threadIdx.x] += s_valid[threadIdx.x + o];
+      s_hit[threadIdx.x] += s_hit[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[2 * j] = s_valid[0];
+    counts[2 * j + 1] = s_hit[0];
+  }
+}
+
+// acc (J + 1 doubles), avg_cnt = {avg_acc, cnt}
+__global__ void pck_final_kernel(const int* __restrict__ counts, int J, double* __restrict__ acc,
+                                 double* __restrict__ avg_cnt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sum = 0.0;
+  int cnt = 0;
+  for (int j = 0; j < J; ++j) {
+    const int v = counts[2 * j], h = counts[2 * j + 1];
+    const double a = v > 0 ? (double)h * 1.0 / (double)v : -1.0;
+    acc[j + 1] = a;
+    if (a >= 0) {
+      sum = sum + a;
+      ++cnt;
+    }
+  }
+  const double avg = cnt != 0 ? sum / (double)cnt : 0.0;
+  acc[0] = cnt != 0 ? avg : 0.0;
+  avg_cnt[0] = avg;
+  avg_cnt[1] = (double)cnt;
+}
+
 }  // namespace
 
 int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw, int width, float* preds,
@@ -284,6 +345,19 @@ int launch_crop_normalize(const uint8_t* hwc, void* chw, int out_dtype, int B, i
   else
     crop_normalize_kernel<__nv_bfloat16>
         <<<blocks, 256, 0, stream>>>(hwc, static_cast<__nv_bfloat16*>(chw), npix, H * W);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pose_accuracy(const float* pred, const float* target, int B, int J, int H, int W, double thr, int* counts,
+                         double* acc, double* avg_cnt, cudaStream_t stream) {
+  if (B < 0 || J < 1 || H < 1 || W < 1) {
+    set_error("pose_accuracy: bad shape (%d, %d, %d, %d)", B, J, H, W);
+    return -1;
+  }
+  // norm = np.ones((B, 2)) * np.array([h, w]) / 10: x is divided by h / 10, y by w / 10 (libs/metrics.py:45)
+  pck_joint_kernel<<<J, 256, 0, stream>>>(pred, target, B, J, (double)H / 10.0, (double)W / 10.0, thr, counts);
+  pck_final_kernel<<<1, 32, 0, stream>>>(counts, J, acc, avg_cnt);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -46,6 +46,7 @@ SIGNATURES = {
     "hgr_pose_head": (_i, [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_get_max_preds": (_i, [_vp, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "hgr_crop_normalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hgr_pose_accuracy": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_double, _vp, _vp, _vp, _vp]),
     "hgr_crop_warp_normalize": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     # ---- training step ----
     "hgr_train_param_count": (_i, [_i, _i]),

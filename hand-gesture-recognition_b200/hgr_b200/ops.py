@@ -3,6 +3,7 @@
 get_max_preds         reference libs/utils.py:4-32
 crop_normalize        reference detect.py:106-112 / libs/load.py:46-50
 crop_warp_normalize   reference detect.py:92-117 (get_affine_transform + cv2.warpAffine + normalise)
+pose_accuracy         reference libs/metrics.py:31-62 (PCK on the decoded keypoints)
 """
 from __future__ import annotations
 
@@ -139,3 +140,25 @@ def crop_warp_normalize(frames_u8: torch.Tensor, boxes, frame_index=None, size: 
                                                            _stream(fr.device)), "hgr_crop_warp_normalize")
         out.record_stream(torch.cuda.current_stream(fr.device))
     return out
+
+
+def pose_accuracy(output: torch.Tensor, target: torch.Tensor, thr: float = 0.5):
+    """libs.metrics.pose_accuracy on the device: predicted and ground-truth heatmaps (B, J, H, W) CUDA ->
+    (acc (J + 1,) float64, avg_acc, cnt, pred (B, J, 2)) as CUDA tensors, without the device->host copy of the
+    heatmaps that train.py:71-73 makes every step.  `float(avg_acc)`, `int(cnt)` give the reference's scalars."""
+    if not (isinstance(output, torch.Tensor) and isinstance(target, torch.Tensor) and output.is_cuda and target.is_cuda):
+        raise RuntimeError("pose_accuracy runs on the GPU only: pass CUDA tensors")
+    if output.dim() != 4 or output.shape != target.shape:
+        raise ValueError("output and target must be (B, J, H, W) heatmaps of the same shape")
+    b, j, h, w = output.shape
+    pred, _ = get_max_preds(output.detach())
+    tgt, _ = get_max_preds(target.detach())
+    dev = output.device
+    counts = torch.empty(2 * j, dtype=torch.int32, device=dev)
+    acc = torch.empty(j + 1, dtype=torch.float64, device=dev)
+    avg_cnt = torch.empty(2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().hgr_pose_accuracy(pred.data_ptr(), tgt.data_ptr(), b, j, h, w, float(thr),
+                                                 counts.data_ptr(), acc.data_ptr(), avg_cnt.data_ptr(), _stream(dev)),
+                   "hgr_pose_accuracy")
+    return acc, avg_cnt[0], avg_cnt[1].to(torch.int64), pred

@@ -165,6 +165,13 @@ HGR_API int hgr_get_max_preds(const void* d_heatmaps, int dtype, int B, int J, i
  * ((v / 255) - mean[c]) / std[c], ImageNet constants by channel index. */
 HGR_API int hgr_crop_normalize(const uint8_t* d_hwc, void* d_chw, int out_dtype, int B, int H, int W, void* stream);
 
+/* libs.metrics.pose_accuracy (reference libs/metrics.py:31-62) after the keypoint decode: d_pred / d_target are
+ * the (B, J, 2) fp32 outputs of hgr_get_max_preds on the predicted and the ground-truth heatmaps of size H x W.
+ * d_acc: J + 1 doubles (acc[0] = average over the joints with at least one valid sample, acc[j + 1] per joint, -1
+ * when no sample is valid); d_avg_cnt: {avg_acc, cnt}; d_counts: 2 * J ints of scratch.  thr is 0.5 in the reference. */
+HGR_API int hgr_pose_accuracy(const float* d_pred, const float* d_target, int B, int J, int H, int W, double thr,
+                              int* d_counts, double* d_acc, double* d_avg_cnt, void* stream);
+
 /* detect.py:92-117 fused: cv2.warpAffine(frame, trans, (S, S), flags=INTER_LINEAR) (bit-exact fixed-point
  * arithmetic of OpenCV, constant border 0) + the normalisation above, for N crops out of F frames
  * (F, Hf, Wf, 3) uint8.  d_inv_mats: N x 6 doubles, the INVERTED affine maps (crop pixel -> frame pixel) exactly

@@ -449,3 +449,36 @@ def process_image_for_classification(img, bbox, size):
     trans = get_affine_transform(c, 1, 0, origin_size, [size, size])
     crop = warp_affine_linear_u8(img, trans, size, size)
     return crop_normalize(crop), trans
+
+
+# --------------------------------------------------------------------------
+# metrics tail: libs/metrics.py
+# --------------------------------------------------------------------------
+def pose_accuracy(output, target, thr=0.5):
+    """libs/metrics.py:6-62 restated: PCK on keypoints decoded from predicted and ground-truth heatmaps, distances
+    normalised by (h / 10, w / 10) applied to (x, y) as the reference pairs them, float64 like numpy's promotion.
+    Returns (acc (J + 1,), avg_acc, cnt, pred)."""
+    num_joints = output.shape[1]
+    pred, _ = get_max_preds(output)
+    tgt, _ = get_max_preds(target)
+    h, w = output.shape[2], output.shape[3]
+    norm = np.ones((pred.shape[0], 2)) * np.array([h, w]) / 10
+    dists = np.zeros((num_joints, pred.shape[0]))
+    for n in range(pred.shape[0]):
+        for c in range(num_joints):
+            if tgt[n, c, 0] > 1 and tgt[n, c, 1] > 1:
+                dists[c, n] = np.linalg.norm(pred[n, c, :] / norm[n] - tgt[n, c, :] / norm[n])
+            else:
+                dists[c, n] = -1
+    acc = np.zeros(num_joints + 1)
+    avg_acc, cnt = 0, 0
+    for i in range(num_joints):
+        valid = dists[i] != -1
+        acc[i + 1] = np.less(dists[i][valid], thr).sum() * 1.0 / valid.sum() if valid.sum() > 0 else -1
+        if acc[i + 1] >= 0:
+            avg_acc += acc[i + 1]
+            cnt += 1
+    avg_acc = avg_acc / cnt if cnt != 0 else 0
+    if cnt != 0:
+        acc[0] = avg_acc
+    return acc, avg_acc, cnt, pred

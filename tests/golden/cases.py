@@ -47,3 +47,24 @@ def crop_boxes():
     return [((100, 80, 300, 290), 192), ((0, 0, 200, 150), 192), ((380, 250, 560, 430), 192),
             ((-40, -30, 90, 100), 192), ((210, 150, 240, 185), 192), ((5, 5, 475, 355), 192),
             ((120, 60, 360, 330), 256), ((33, 47, 161, 200), 64)]
+
+
+def metric_cases():
+    """(predicted heatmaps, ground-truth heatmaps) pairs for pose_accuracy: near-miss predictions, exact hits,
+    invisible joints (target peak at x <= 1 or y <= 1), an all-invalid joint, 48x48 and 64x64."""
+    rng = np.random.default_rng(21)
+    out = {}
+    for name, (b, j, h) in {"m48": (16, 21, 48), "m64": (5, 21, 64), "tiny": (2, 3, 8)}.items():
+        tgt = np.zeros((b, j, h, h), dtype=np.float32)
+        prd = rng.standard_normal((b, j, h, h)).astype(np.float32) * 0.05
+        for n in range(b):
+            for c in range(j):
+                ty, tx = rng.integers(0, h, 2)
+                if c == 0:
+                    ty, tx = 0, int(rng.integers(0, h))  # never valid: y <= 1
+                tgt[n, c, ty, tx] = 1.0
+                dy, dx = rng.integers(-4, 5, 2)
+                py, px = np.clip(ty + dy, 0, h - 1), np.clip(tx + dx, 0, h - 1)
+                prd[n, c, py, px] = 1.0 + rng.random()
+        out[name] = (prd, tgt)
+    return out

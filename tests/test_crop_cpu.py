@@ -34,3 +34,13 @@ def test_host_matrix_helpers_match_the_oracle():
         got = box_to_affine(bbox, size)
         assert np.array_equal(got, ref)
         assert np.array_equal(invert_affine(got), O.invert_affine(ref))
+
+
+def test_oracle_pose_accuracy_matches_reference():
+    """libs.metrics.pose_accuracy restated (oracle) against golden vectors from the real reference function."""
+    from tests.golden.cases import metric_cases
+    g = np.load(GOLD / "pose_accuracy.npz")
+    for name, (prd, tgt) in metric_cases().items():
+        acc, avg_acc, cnt, pred = O.pose_accuracy(prd, tgt)
+        assert np.array_equal(acc, g["acc_" + name]) and avg_acc == g["avg_" + name][0] and cnt == g["cnt_" + name][0]
+        assert np.array_equal(pred, g["pred_" + name])

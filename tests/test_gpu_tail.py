@@ -125,3 +125,24 @@ def test_crop_warp_normalize_batch_of_frames_and_bf16():
         crop_warp_normalize(torch.from_numpy(frames).cuda(), boxes, frame_index=[0, 1, 2, 3, 0], size=64)
     with pytest.raises(RuntimeError):
         crop_warp_normalize(torch.from_numpy(frames), boxes, size=64)
+
+
+# ------------------------------------------------------------------ metrics tail ----
+def test_pose_accuracy_matches_reference_golden_exactly():
+    """libs.metrics.pose_accuracy on the device (no heatmap D2H copy): float64 accuracies, count and decoded
+    keypoints identical to the real reference's on the crafted cases and to the oracle on a full training batch."""
+    from hgr_b200 import pose_accuracy
+    from tests.golden.cases import metric_cases
+    g = np.load(GOLD / "pose_accuracy.npz")
+    for name, (prd, tgt) in metric_cases().items():
+        acc, avg, cnt, pred = pose_accuracy(torch.from_numpy(prd).cuda(), torch.from_numpy(tgt).cuda())
+        assert np.array_equal(acc.cpu().numpy(), g["acc_" + name]), name
+        assert float(avg) == g["avg_" + name][0] and int(cnt) == g["cnt_" + name][0]
+        _same_bits(pred.cpu().numpy(), g["pred_" + name])
+    _, target, _ = O.synthetic_targets(32, 192, seed=9)
+    out = target + 0.3 * torch.randn(target.shape, generator=torch.Generator().manual_seed(1))
+    acc, avg, cnt, _ = pose_accuracy(out.cuda(), target.cuda())
+    racc, ravg, rcnt, _ = O.pose_accuracy(out.numpy(), target.numpy())
+    assert np.array_equal(acc.cpu().numpy(), racc) and float(avg) == ravg and int(cnt) == rcnt
+    with pytest.raises(RuntimeError):
+        pose_accuracy(out, target)
