@@ -173,3 +173,23 @@ def test_hand_pipeline_matches_the_module_and_the_frames_path():
     assert torch.equal(logits, cls.cpu()) and torch.equal(kps, preds.cpu()) and torch.equal(conf, maxvals.cpu())
     l2, k2, c2 = pipe.infer_frames(torch.from_numpy(frame)[None], boxes)
     assert torch.equal(l2, logits) and torch.equal(k2, kps) and torch.equal(c2, conf)
+
+
+def test_classifier_session_has_the_onnxruntime_contract():
+    """detect.py:143-155 verbatim against ClassifierSession: same call sequence, (label_pred, heatmap_pred) out."""
+    from hgr_b200 import ClassifierSession
+    from hgr_b200 import get_max_preds
+    m, sd = build(192, 0)
+    classifier = ClassifierSession(m)
+    hand = O.synthetic_images(1, 192, 5).numpy()
+    inname = [i.name for i in classifier.get_inputs()]
+    inp = {inname[0]: hand}
+    label_pred, heatmap_pred = classifier.run(None, inp)
+    assert label_pred.shape == (1, 19) and heatmap_pred.shape == (1, 21, 48, 48) and label_pred.dtype == np.float32
+    cls_ref, hm_ref, _ = O.multitasknet_forward(sd, torch.from_numpy(hand))
+    assert report("session logits", torch.from_numpy(label_pred), cls_ref)[0] <= REL_TOL
+    assert report("session heatmaps", torch.from_numpy(heatmap_pred), hm_ref)[0] <= REL_TOL
+    landmarks_pred, _ = get_max_preds(heatmap_pred)  # numpy in / numpy out, as detect.py:150 calls it
+    assert landmarks_pred.shape == (1, 21, 2)
+    assert [o.name for o in classifier.get_outputs()] == ["label_pred", "heatmap_pred"]
+    assert classifier.run(["heatmap_pred"], inp)[0].shape == (1, 21, 48, 48)
