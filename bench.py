@@ -214,7 +214,6 @@ def run_train(args, rank, world, local_rank):
     import torch.distributed as dist
     from hgr_b200 import DataParallelTrainer, MultiTaskNet
     from hgr_b200.sharding import max_over_ranks
-    from oracle import multitasknet_oracle as O  # synthetic targets only (seeded blobs); no oracle arithmetic is timed
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -236,7 +235,16 @@ def run_train(args, rank, world, local_rank):
     tr = DataParallelTrainer(model, lr=1e-4)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(B, 3, S, S, generator=g, device=dev)
-    labels, target, weight = (t.to(dev) for t in O.synthetic_targets(B, S, seed=3 + rank))
+    # synthetic supervision of the shape train.py feeds: class labels, Gaussian-blob target heatmaps (sigma 2,
+    # libs/load.py:148-206), visibility weights
+    labels = torch.randint(0, 19, (B,), generator=g, device=dev)
+    hs = S // 4
+    cy = torch.rand(B, 21, 1, 1, generator=g, device=dev) * hs
+    cx = torch.rand(B, 21, 1, 1, generator=g, device=dev) * hs
+    yy = torch.arange(hs, device=dev).view(1, 1, hs, 1).float()
+    xx = torch.arange(hs, device=dev).view(1, 1, 1, hs).float()
+    target = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 2.0 ** 2)).contiguous()
+    weight = (torch.rand(B, 21, 1, generator=g, device=dev) > 0.2).float()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -149,12 +149,14 @@ template <bool SILU, bool RES>
 __global__ void __launch_bounds__(kThreads)
 bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int C, const float* __restrict__ scale,
                   const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ctot,
-                  __nv_bfloat16* __restrict__ y, int y_ctot) {
-  const int ncg = C >> 3;
-  const long long total = rows * ncg;
+                  __nv_bfloat16* __restrict__ y, int y_ctot, int cg_log2) {
+  // channel groups per row are a power of two (C = 64 .. 512): row / group come from a shift and a mask
+  const long long total = rows << cg_log2;
+  const int cg_mask = (1 << cg_log2) - 1;
+#pragma unroll 2
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const long long r = i / ncg;
-    const int c0 = (int)(i % ncg) * 8;
+    const long long r = i >> cg_log2;
+    const int c0 = ((int)i & cg_mask) * 8;
     float v[8], rr[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + c0)), v);
     if constexpr (RES) unpack8(__ldg(reinterpret_cast<const uint4*>(res + r * res_ctot + c0)), rr);
@@ -219,12 +221,13 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const __n
                     long long rows, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ c1,
                     const float* __restrict__ c2, const __nv_bfloat16* __restrict__ res, int res_ctot,
-                    __nv_bfloat16* __restrict__ dres, int dres_ctot, __nv_bfloat16* __restrict__ dz) {
-  const int ncg = C >> 3;
-  const long long total = rows * ncg;
+                    __nv_bfloat16* __restrict__ dres, int dres_ctot, __nv_bfloat16* __restrict__ dz, int cg_log2) {
+  const long long total = rows << cg_log2;
+  const int cg_mask = (1 << cg_log2) - 1;
+#pragma unroll 2
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const long long r = i / ncg;
-    const int c0 = (int)(i % ncg) * 8;
+    const long long r = i >> cg_log2;
+    const int c0 = ((int)i & cg_mask) * 8;
     float g[8], v[8], rr[8], dr[8], out[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * dy_ctot + c0)), g);
     unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + c0)), v);
@@ -583,17 +586,28 @@ int launch_bn_stats(const __nv_bfloat16* z, long long rows, int C, const float* 
   return 0;
 }
 
+static int channel_group_log2(int C) {
+  int l = 0;
+  while ((8 << l) < C) ++l;
+  return (8 << l) == C ? l : -1;
+}
+
 int launch_bn_act_fwd(const __nv_bfloat16* z, long long rows, int C, const float* scale, const float* shift, int silu,
                       const __nv_bfloat16* res, int res_ctot, __nv_bfloat16* y, int y_ctot, cudaStream_t st) {
+  const int cgl = channel_group_log2(C);
+  if (cgl < 0) {
+    set_error("bn_act_fwd: channel count %d is not a power of two >= 8", C);
+    return -1;
+  }
   const int blocks = ew_blocks(rows * (C / 8));
   if (silu && res)
-    bn_act_fwd_kernel<true, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot);
+    bn_act_fwd_kernel<true, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
   else if (silu)
-    bn_act_fwd_kernel<true, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot);
+    bn_act_fwd_kernel<true, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
   else if (res)
-    bn_act_fwd_kernel<false, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot);
+    bn_act_fwd_kernel<false, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
   else
-    bn_act_fwd_kernel<false, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot);
+    bn_act_fwd_kernel<false, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -609,6 +623,11 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
   const int nblk = reduce_blocks(rows);
   const size_t sm = kThreads * 16 * sizeof(float);
   const int blocks = ew_blocks(rows * (C / 8));
+  const int cgl = channel_group_log2(C);
+  if (cgl < 0) {
+    set_error("bn_bwd: channel count %d is not a power of two >= 8", C);
+    return -1;
+  }
   float* c1 = c1c2;
   float* c2 = c1c2 + C;
 #define HGR_BN_BWD(S, R)                                                                                           \
@@ -617,7 +636,7 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
                                                             res_ctot, partial);                                    \
     bn_bwd_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, rows, dgamma, dbeta, c1, c2);            \
     bn_bwd_apply_kernel<S, R><<<blocks, kThreads, 0, st>>>(dy, dy_ctot, z, rows, C, scale, shift, mean, rstd, c1,   \
-                                                           c2, res, res_ctot, dres, dres_ctot, dz);                \
+                                                           c2, res, res_ctot, dres, dres_ctot, dz, cgl);           \
   } while (0)
   if (silu && res) HGR_BN_BWD(true, true);
   else if (silu) HGR_BN_BWD(true, false);

@@ -3,9 +3,10 @@
 // i.e. a GEMM whose reduction runs over PIXELS while both operands are stored channel-contiguous (NHWC), so
 // both are "MN-major" from the tensor core's point of view.  This first version runs on mma.sync m16n8k16
 // (ldmatrix.trans turns the pixel-major shared-memory tiles into K-major fragments) with split-K over pixel
-// chunks: grid = (co-tile x ci-tile, tap, chunk), fp32 partial tiles, and a fixed-order reduction kernel that
-// also writes PyTorch's (Cout, Cin, kh, kw) layout.  At the 32-crop training batch the whole backward wgrad is
-// 140 GFLOP; a tcgen05 MN-major version is the follow-up once the step is no longer launch-bound.
+// chunks: grid = (co-tile x ci-tile, tap, chunk), 128 x 64 (or 64 x 64) CTA tiles with 64 x 32 (32 x 32) warp
+// tiles, fp32 partial tiles, and a fixed-order reduction kernel that also writes PyTorch's (Cout, Cin, kh, kw)
+// layout.  At the 32-crop training batch the whole backward wgrad is 140 GFLOP; a tcgen05 MN-major version is the
+// follow-up once the step is no longer latency-bound.
 #include "hgr_internal.h"
 #include "ptx.cuh"
 #include "train.h"
@@ -14,11 +15,10 @@ namespace hgr {
 
 namespace {
 
-constexpr int kWThreads = 128;     // 4 warps: warp w owns co rows [16 w, 16 w + 16) of the 64 x 64 tile
-constexpr int kPix = 64;           // pixels (K) per pipeline stage
-constexpr int kPitchB = 144;       // bytes per smem row: 64 bf16 + 16 B pad -> conflict-free ldmatrix
+constexpr int kWThreads = 128;  // 4 warps as 2 (co) x 2 (ci)
+constexpr int kPix = 64;        // pixels (K) per pipeline stage
 constexpr int kStages = 3;
-constexpr int kTileBytes = kPix * kPitchB;  // 9216
+constexpr int kXPitch = 144;    // bytes per staged X row: 64 bf16 + 16 B pad -> conflict-free ldmatrix
 
 struct WgradParams {
   const __nv_bfloat16* g;  // [P][g_ctot], channel offset applied
@@ -28,102 +28,132 @@ struct WgradParams {
   int Cout, Cin;
   int B, H, W, Ho, Wo;  // input map H x W, output map Ho x Wo
   int k, s;             // kernel size (1 or 3), stride
-  long long P;          // B * Ho * Wo
-  long long per_chunk;  // pixels per chunk (multiple of kPix)
+  int P;                // B * Ho * Wo
+  int per_chunk;        // pixels per chunk (multiple of kPix)
 };
 
+// CTA tile = (32 MT) output channels x 64 input channels; warp tile = (16 MT) x 32.
+// MT = 4 (Cout multiple of 128): 6 ldmatrix feed 16 MMAs per k-step; MT = 2 (Cout = 64): 4 feed 8.
+template <int MT>
 __global__ void __launch_bounds__(kWThreads)
 wgrad_kernel(const WgradParams p) {
+  constexpr int BM = 32 * MT;
+  constexpr int kGPitch = BM * 2 + 16;  // bytes per staged G row
+  constexpr int kGTile = kPix * kGPitch, kXTile = kPix * kXPitch;
   extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* sg = smem;                         // [kStages][kPix][kPitchB]
-  uint8_t* sx = smem + kStages * kTileBytes;  // [kStages][kPix][kPitchB]
+  uint8_t* sg = smem;                     // [kStages][kPix][kGPitch]
+  uint8_t* sx = smem + kStages * kGTile;  // [kStages][kPix][kXPitch]
 
   const int ci_tiles = p.Cin >> 6;
-  const int co0 = (blockIdx.x / ci_tiles) << 6;
+  const int co0 = (blockIdx.x / ci_tiles) * BM;
   const int ci0 = (blockIdx.x % ci_tiles) << 6;
   const int tap = blockIdx.y;
   const int kh = tap / p.k, kw = tap % p.k;
   const int pad = p.k >> 1;
-  const long long p_begin = (long long)blockIdx.z * p.per_chunk;
-  long long p_end = p_begin + p.per_chunk;
-  if (p_end > p.P) p_end = p.P;
-  const int nsteps = p_end > p_begin ? (int)((p_end - p_begin + kPix - 1) / kPix) : 0;
+  const int p_begin = blockIdx.z * p.per_chunk;
+  const int p_end = p_begin + p.per_chunk < p.P ? p_begin + p.per_chunk : p.P;
+  const int nsteps = p_end > p_begin ? (p_end - p_begin + kPix - 1) / kPix : 0;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // loader: thread owns 16-byte chunk `lc` of pixels lp, lp + 16, lp + 32, lp + 48
+  const int wm = warp >> 1, wn = warp & 1;
+  // loader: thread owns 16-byte chunk column lc of pixel rows lp, lp + 16, lp + 32, lp + 48 of every stage.
+  // Its first pixel is decomposed into (n, oh, ow) ONCE; afterwards the coordinates advance incrementally.
   const int lc = tid & 7, lp = tid >> 3;
-
-  auto load_stage = [&](int stage, int step) {
-    const long long base = p_begin + (long long)step * kPix;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pr = lp + i * 16;
-      const long long pix = base + pr;
-      const bool in_range = pix < p_end;
-      const long long pc = in_range ? pix : p_begin;
-      const __nv_bfloat16* gsrc = p.g + pc * p.g_ctot + co0 + lc * 8;
-      cp_async_16(sg + stage * kTileBytes + pr * kPitchB + lc * 16, gsrc, in_range ? 16u : 0u);
-      const int ow = (int)(pc % p.Wo);
-      const long long t = pc / p.Wo;
-      const int oh = (int)(t % p.Ho);
-      const long long n = t / p.Ho;
-      const int ih = oh * p.s + kh - pad, iw = ow * p.s + kw - pad;
-      const bool ok = in_range && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
-      const __nv_bfloat16* xsrc = ok ? p.x + ((n * p.H + ih) * p.W + iw) * p.x_ctot + ci0 + lc * 8 : p.x;
-      cp_async_16(sx + stage * kTileBytes + pr * kPitchB + lc * 16, xsrc, ok ? 16u : 0u);
+  int pix = p_begin + lp;
+  int ow = pix % p.Wo, oh = (pix / p.Wo) % p.Ho, n = pix / (p.Wo * p.Ho);
+  auto advance16 = [&]() {
+    pix += 16;
+    ow += 16;
+    while (ow >= p.Wo) {
+      ow -= p.Wo;
+      if (++oh == p.Ho) {
+        oh = 0;
+        ++n;
+      }
     }
   };
 
-  float acc[8][4];
+  auto load_stage = [&](int stage) {
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const int pr = lp + i * 16;
+      const bool in_range = pix < p_end;
+      const int ih = oh * p.s + kh - pad, iw = ow * p.s + kw - pad;
+      const bool ok = in_range && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+      const __nv_bfloat16* xsrc = ok ? p.x + (((size_t)n * p.H + ih) * p.W + iw) * p.x_ctot + ci0 + lc * 8 : p.x;
+      cp_async_16(sx + stage * kXTile + pr * kXPitch + lc * 16, xsrc, ok ? 16u : 0u);
+      const __nv_bfloat16* grow = p.g + (size_t)(in_range ? pix : p_begin) * p.g_ctot + co0 + lc * 8;
+#pragma unroll
+      for (int c = 0; c < BM / 64; ++c)
+        cp_async_16(sg + stage * kGTile + pr * kGPitch + (lc + 8 * c) * 16, grow + 64 * c, in_range ? 16u : 0u);
+      advance16();
+    }
+  };
 
+  float acc[MT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+
+  int loaded = 0;
   for (int s = 0; s < kStages - 1; ++s) {
-    if (s < nsteps) load_stage(s, s);
+    if (loaded < nsteps) {
+      load_stage(loaded % kStages);
+      ++loaded;
+    }
     cp_async_commit();
   }
-  // ldmatrix.trans lane addresses.  Stored tiles are [pixel (k)][channel]; after .trans a thread holds
-  // (channel = g, pixels 2t, 2t+1), which is the A fragment (m = co, k = pixel) and the B fragment (k = pixel, n = ci).
+  // ldmatrix.trans lane addresses.  Staged tiles are [pixel (k)][channel]; after .trans a thread holds
+  // (channel = g, pixels 2t, 2t+1): the A fragment (m = co, k = pixel) and the B fragment (k = pixel, n = ci).
   //  A x4: matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15)
   const int a_row = (lane & 7) + ((lane >> 4) << 3);
-  const int a_col = warp * 16 + (((lane >> 3) & 1) << 3);
+  const int a_col = wm * (16 * MT) + (((lane >> 3) & 1) << 3);
   //  B x4: matrices (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15)
   const int b_row = (lane & 7) + (((lane >> 3) & 1) << 3);
-  const int b_col = (lane >> 4) << 3;
+  const int b_col = wn * 32 + ((lane >> 4) << 3);
 
   for (int step = 0; step < nsteps; ++step) {
     cp_async_wait<kStages - 2>();
     __syncthreads();
-    {
-      const int nxt = step + kStages - 1;
-      if (nxt < nsteps) load_stage(nxt % kStages, nxt);
-      cp_async_commit();
+    if (loaded < nsteps) {
+      load_stage(loaded % kStages);
+      ++loaded;
     }
-    const uint32_t g_base = smem_u32(sg + (step % kStages) * kTileBytes);
-    const uint32_t x_base = smem_u32(sx + (step % kStages) * kTileBytes);
+    cp_async_commit();
+    const uint32_t g_base = smem_u32(sg + (step % kStages) * kGTile);
+    const uint32_t x_base = smem_u32(sx + (step % kStages) * kXTile);
 #pragma unroll
     for (int kk = 0; kk < kPix / 16; ++kk) {
-      uint32_t a[4];
-      ldmatrix_x4_trans(a, g_base + (kk * 16 + a_row) * kPitchB + a_col * 2);
+      uint32_t a[MT][4], b[2][4];
 #pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b[4];
-        ldmatrix_x4_trans(b, x_base + (kk * 16 + b_row) * kPitchB + (np * 16 + b_col) * 2);
-        mma_bf16_16816(acc[2 * np], a, b[0], b[1]);
-        mma_bf16_16816(acc[2 * np + 1], a, b[2], b[3]);
-      }
+      for (int mt = 0; mt < MT; ++mt)
+        ldmatrix_x4_trans(a[mt], g_base + (kk * 16 + a_row) * kGPitch + (a_col + mt * 16) * 2);
+#pragma unroll
+      for (int np = 0; np < 2; ++np)
+        ldmatrix_x4_trans(b[np], x_base + (kk * 16 + b_row) * kXPitch + (b_col + np * 16) * 2);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          mma_bf16_16816(acc[mt][2 * np], a[mt], b[np][0], b[np][1]);
+          mma_bf16_16816(acc[mt][2 * np + 1], a[mt], b[np][2], b[np][3]);
+        }
     }
   }
   cp_async_wait<0>();
 
   // partial[chunk][tap][co][ci]
   const int g = lane >> 2, t = lane & 3;
-  float* out = p.partial + (((size_t)blockIdx.z * gridDim.y + tap) * p.Cout + co0 + warp * 16) * p.Cin + ci0;
+  float* out = p.partial + (((size_t)blockIdx.z * gridDim.y + tap) * p.Cout + co0 + wm * (16 * MT)) * p.Cin + ci0 + wn * 32;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<float2*>(out + (size_t)g * p.Cin + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
-    *reinterpret_cast<float2*>(out + (size_t)(g + 8) * p.Cin + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
-  }
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float* o = out + (size_t)(mt * 16 + g) * p.Cin + nt * 8 + 2 * t;
+      *reinterpret_cast<float2*>(o) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(o + (size_t)8 * p.Cin) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
 }
 
 // dW[(co * Cin + ci) * taps + tap] = sum_chunk partial[chunk][tap][co][ci]   (PyTorch's (Cout, Cin, kh, kw))
@@ -222,9 +252,11 @@ __global__ void partial_sum_kernel(const float* __restrict__ partial, int nparts
 
 }  // namespace
 
+static int wgrad_bm(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
+
 size_t wgrad_partial_floats(int Cout, int Cin, int k, long long P, int* chunks_out) {
   const int taps = k * k;
-  const long long tiles = (long long)(Cout / 64) * (Cin / 64) * taps;
+  const long long tiles = (long long)(Cout / wgrad_bm(Cout)) * (Cin / 64) * taps;
   long long chunks = (148 * 4 + tiles - 1) / tiles;
   const long long max_chunks = (P + 4 * kPix - 1) / (4 * kPix);  // at least 256 pixels per chunk
   if (chunks > max_chunks) chunks = max_chunks;
@@ -233,10 +265,30 @@ size_t wgrad_partial_floats(int Cout, int Cin, int k, long long P, int* chunks_o
   return (size_t)chunks * taps * Cout * Cin;
 }
 
+template <int MT>
+static int launch_wgrad_impl(const WgradParams& p, int chunks, cudaStream_t st) {
+  constexpr int BM = 32 * MT;
+  constexpr int smem = kStages * kPix * ((BM * 2 + 16) + kXPitch);
+  static bool configured = false;
+  if (!configured) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Cout / BM) * (p.Cin / 64), p.k * p.k, chunks);
+  wgrad_kernel<MT><<<grid, kWThreads, smem, st>>>(p);
+  HGR_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int x_ctot, int B, int H, int W, int Cin,
                  int Cout, int k, int s, float* partial, float* dw, cudaStream_t st) {
   if (Cin % 64 != 0 || Cout % 64 != 0 || !(k == 1 || k == 3) || !(s == 1 || s == 2) || g_ctot % 8 || x_ctot % 8) {
     set_error("wgrad: unsupported shape cin %d cout %d k %d s %d", Cin, Cout, k, s);
+    return -1;
+  }
+  const long long P = (long long)B * (H / s) * (W / s);
+  if (P <= 0 || P > 0x7fffff00LL) {
+    set_error("wgrad: %lld output pixels out of range", P);
     return -1;
   }
   WgradParams p;
@@ -254,20 +306,13 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
   p.Wo = W / s;
   p.k = k;
   p.s = s;
-  p.P = (long long)B * p.Ho * p.Wo;
+  p.P = (int)P;
   int chunks = 1;
-  wgrad_partial_floats(Cout, Cin, k, p.P, &chunks);
-  long long per = (p.P + chunks - 1) / chunks;
+  wgrad_partial_floats(Cout, Cin, k, P, &chunks);
+  long long per = (P + chunks - 1) / chunks;
   per = (per + kPix - 1) / kPix * kPix;
-  p.per_chunk = per;
-  static bool configured = false;
-  const int smem = 2 * kStages * kTileBytes;
-  if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  dim3 grid((Cout / 64) * (Cin / 64), k * k, chunks);
-  wgrad_kernel<<<grid, kWThreads, smem, st>>>(p);
+  p.per_chunk = (int)per;
+  if (int rc = wgrad_bm(Cout) == 128 ? launch_wgrad_impl<4>(p, chunks, st) : launch_wgrad_impl<2>(p, chunks, st)) return rc;
   const long long total = (long long)Cout * Cin * k * k;
   int rb = (int)((total + 255) / 256);
   if (rb > 148 * 8) rb = 148 * 8;
