@@ -289,29 +289,34 @@ cls_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __res
 // once per pixel (by the CTA with y0 == ty) into a per-CTA partial.  Thread c = channel c.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxJ = 24;
-constexpr int kPhases = 4;  // pixel phases per CTA: thread (c, q) handles output columns ox = q (mod 4)
+constexpr int kPhases = 2;  // pixel phases per CTA: thread (c, q) handles output columns ox = q (mod 2)
 
+// Shared-memory traffic decides this kernel (42 loads per pixel and channel in the naive form), so the weight
+// column of a thread lives in registers and the dheat row is staged TRANSPOSED ([ox][24 joints]) so that the 21
+// joint values of a pixel arrive as six broadcast 128-bit loads.
 __global__ void __launch_bounds__(256 * kPhases, 1)
 pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __restrict__ w /*[J][256] fp32*/,
                      const float* __restrict__ dheat, int F, int J, __nv_bfloat16* __restrict__ dtokens,
                      float* __restrict__ dw_partial) {
-  extern __shared__ float smp[];
+  extern __shared__ __align__(16) float smp[];
   const int So = 4 * F;
-  float* sdx = smp;                        // [kPhases][F][256]  per-phase accumulators of this token row
-  float* sdh = sdx + kPhases * F * kDim;   // [J][So]            dheat of the current output row
-  float* sw = sdh + kMaxJ * So;            // [J][256]           bf16-rounded weights (as the forward used them)
+  float* sdx = smp;                       // [kPhases][F][256]  per-phase accumulators of this token row
+  float* sdh = sdx + kPhases * F * kDim;  // [So][kMaxJ]        dheat of the current output row, joint-contiguous
   const int b = blockIdx.y, ty = blockIdx.x;
   const int c = threadIdx.x & 255, q = threadIdx.x >> 8;
   const int T = F * F + 1;
   const float scale = (float)(F - 1) / (float)(So - 1);
   const __nv_bfloat16* tok = tokens + ((size_t)b * T + 1) * kDim;
 
-  float dwacc[kMaxJ];
+  float wr[kMaxJ], dwacc[kMaxJ];
 #pragma unroll
-  for (int j = 0; j < kMaxJ; ++j) dwacc[j] = 0.f;
-  for (int i = threadIdx.x; i < J * kDim; i += 256 * kPhases) sw[i] = __bfloat162float(__float2bfloat16_rn(w[i]));
+  for (int j = 0; j < kMaxJ; ++j) {
+    wr[j] = j < J ? __bfloat162float(__float2bfloat16_rn(w[(size_t)j * kDim + c])) : 0.f;  // the forward used bf16 weights
+    dwacc[j] = 0.f;
+  }
   float* mydx = sdx + q * F * kDim;
   for (int x = 0; x < F; ++x) mydx[x * kDim + c] = 0.f;
+  for (int i = threadIdx.x; i < So * kMaxJ; i += 256 * kPhases) sdh[i] = 0.f;  // joints >= J stay zero
 
   for (int oy = 0; oy < So; ++oy) {
     const float sy = scale * (float)oy;
@@ -324,7 +329,7 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
     __syncthreads();
     for (int i = threadIdx.x; i < J * So; i += 256 * kPhases) {
       const int j = i / So, ox = i % So;
-      sdh[i] = dheat[(((size_t)b * J + j) * So + oy) * So + ox];
+      sdh[ox * kMaxJ + j] = dheat[(((size_t)b * J + j) * So + oy) * So + ox];
     }
     __syncthreads();
     for (int ox = q; ox < So; ox += kPhases) {
@@ -339,13 +344,17 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
       const float up = l0 * (m0 * t00 + m1 * t01) + l1 * (m0 * t10 + m1 * t11);
       if (up > 0.f) {
         float dup = 0.f;
+        const float4* dh4 = reinterpret_cast<const float4*>(sdh + ox * kMaxJ);
 #pragma unroll
-        for (int j = 0; j < kMaxJ; ++j)
-          if (j < J) {
-            const float dh = sdh[j * So + ox];
-            dup = fmaf(dh, sw[j * kDim + c], dup);
-            if (owner) dwacc[j] = fmaf(dh, up, dwacc[j]);
+        for (int j4 = 0; j4 < kMaxJ / 4; ++j4) {
+          const float4 d = dh4[j4];
+          const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dup = fmaf(dv[e], wr[4 * j4 + e], dup);
+            if (owner) dwacc[4 * j4 + e] = fmaf(dv[e], up, dwacc[4 * j4 + e]);
           }
+        }
         const float v = wy * dup;
         mydx[x0 * kDim + c] = fmaf(m0, v, mydx[x0 * kDim + c]);
         mydx[x1 * kDim + c] = fmaf(m1, v, mydx[x1 * kDim + c]);
@@ -353,7 +362,7 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
     }
   }
   __syncthreads();
-  // fold the phases in a fixed order: token-row gradient, then the weight-gradient partial (through sdh / sw space)
+  // fold the phases in a fixed order: token-row gradient, then the weight-gradient partial
   if (q == 0)
     for (int x = 0; x < F; ++x) {
       float s = 0.f;
@@ -435,7 +444,7 @@ int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const floa
   const int So = 4 * F;
   size_t accf = (size_t)kPhases * F * kDim;
   if (accf < (size_t)kMaxJ * kDim) accf = (size_t)kMaxJ * kDim;  // the phase fold re-uses this space as [J][256]
-  const size_t smem = (accf + (size_t)kMaxJ * So + (size_t)kMaxJ * kDim) * sizeof(float);
+  const size_t smem = (accf + (size_t)kMaxJ * So) * sizeof(float);
   if (smem > 227 * 1024) {
     set_error("pose_head_bwd: feature side %d does not fit shared memory", F);
     return -1;

@@ -3,9 +3,9 @@
 tag=${1:-trainprof}; batch=${2:-32}
 out=gpurun_out/$tag
 mkdir -p $out
-CMD="python bench.py --workload train --batch $batch --steps 2 --warmup 3"
+CMD="python bench.py --workload train --batch $batch --steps 1 --warmup 3"
 timeout 600 $CMD > $out/plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/train_launches.csv $CMD > $out/ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 --csv --log-file $out/train_launches.csv $CMD > $out/ncu.log 2>&1
 echo "ncu exit $?" | tee $out/summary.txt
 python - <<PY
 import csv, collections
@@ -13,7 +13,7 @@ rows=[r for r in csv.reader(open("$out/train_launches.csv")) if len(r)>10 and r[
 names=[r[4] for r in rows]; t=[float(r[-1]) for r in rows]
 # last step = everything after the last but one adamw_kernel
 idx=[i for i,n in enumerate(names) if "adamw_kernel" in n]
-a,b=idx[-2]+1, idx[-1]+1
+a,b=idx[-2]+1, idx[-1]+1  # the last complete step
 agg=collections.OrderedDict()
 for n,v in zip(names[a:b],t[a:b]):
     k=n.split("(")[0].replace("void hgr::<unnamed>::","").replace("void ","")[:60]
