@@ -8,8 +8,11 @@ kernel), run through the MultiTaskNet plan, decoded on the device
 (get_max_preds kernel) and only the logits, keypoints and their confidences
 travel back - 19*4 + 21*3*4 bytes per hand instead of a 194 KB heatmap.
 
-Two lanes (stream + buffers + plan each) are used alternately so that the
-host->device copy of batch i+1 overlaps the kernels of batch i.
+Two lanes (copy stream + buffers + plan each) are used alternately so that the
+host->device copy of batch i+1 and the device->host copy of batch i-1 overlap
+the kernels of batch i.  ALL kernels run on one compute stream: the persistent
+GEMM kernels of two batches never interleave (each would otherwise take every
+SM and double the tail effects), only the copies run beside them.
 """
 from __future__ import annotations
 
@@ -36,6 +39,8 @@ class _Lane:
         self.h_logits = torch.empty(batch, model.num_classes, dtype=torch.float32).pin_memory()
         self.h_preds = torch.empty(batch, model.num_joints, 2, dtype=torch.float32).pin_memory()
         self.h_maxvals = torch.empty(batch, model.num_joints, 1, dtype=torch.float32).pin_memory()
+        self.h2d_done = torch.cuda.Event()
+        self.compute_done = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.busy = False
 
@@ -50,12 +55,31 @@ class HandPipeline:
         self.model, self.batch, self.device, self.dtype = model, batch, p.device, compute_dtype
         with torch.cuda.device(self.device):
             self.lanes = [_Lane(model, batch, self.device, compute_dtype) for _ in range(lanes)]
+            self.compute = torch.cuda.Stream(self.device)
         self._next = 0
         self.h2d_bytes = self.lanes[0].h_crops.numel()
         self.d2h_bytes = 4 * (self.lanes[0].h_logits.numel() + self.lanes[0].h_preds.numel()
                               + self.lanes[0].h_maxvals.numel())
         # crop_normalize + the plan's launches + get_max_preds
         self.launches_per_batch = self.lanes[0].plan.launches() + 2
+
+    def _forward_decode(self, ln, dt, st):
+        """forward + keypoint decode of lane `ln` on the compute stream `st`."""
+        lib, m = _lib.load(), self.model
+        s = m.image_size[0]
+        _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
+                                   ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
+        _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
+                                         ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
+
+    def _copy_back(self, ln):
+        """results device -> pinned host on the lane's copy stream, after the compute stream is done with them."""
+        with torch.cuda.stream(ln.stream):
+            ln.stream.wait_event(ln.compute_done)
+            ln.h_logits.copy_(ln.d_logits, non_blocking=True)
+            ln.h_preds.copy_(ln.d_preds, non_blocking=True)
+            ln.h_maxvals.copy_(ln.d_maxvals, non_blocking=True)
+            ln.done.record(ln.stream)
 
     def submit(self, crops_u8: torch.Tensor, after: torch.cuda.Event | None = None) -> int:
         """Queue one batch of (B, S, S, 3) uint8 host crops; returns the lane to collect from."""
@@ -70,22 +94,21 @@ class HandPipeline:
         dt = _lib.F32 if self.dtype == torch.float32 else _lib.BF16
         m = self.model
         s = m.image_size[0]
-        with torch.cuda.device(self.device), torch.cuda.stream(ln.stream):
-            if after is not None:
-                ln.stream.wait_event(after)
-            src = crops_u8 if crops_u8.is_pinned() else ln.h_crops.copy_(crops_u8)
-            ln.d_crops.copy_(src, non_blocking=True)
-            st = ln.stream.cuda_stream
-            _lib.check(lib.hgr_crop_normalize(ln.d_crops.data_ptr(), ln.d_x.data_ptr(), dt, self.batch, s, s, st),
-                       "hgr_crop_normalize")
-            _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
-                                       ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
-            _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
-                                             ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
-            ln.h_logits.copy_(ln.d_logits, non_blocking=True)
-            ln.h_preds.copy_(ln.d_preds, non_blocking=True)
-            ln.h_maxvals.copy_(ln.d_maxvals, non_blocking=True)
-            ln.done.record(ln.stream)
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(ln.stream):
+                if after is not None:
+                    ln.stream.wait_event(after)
+                src = crops_u8 if crops_u8.is_pinned() else ln.h_crops.copy_(crops_u8)
+                ln.d_crops.copy_(src, non_blocking=True)
+                ln.h2d_done.record(ln.stream)
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(ln.h2d_done)
+                st = self.compute.cuda_stream
+                _lib.check(lib.hgr_crop_normalize(ln.d_crops.data_ptr(), ln.d_x.data_ptr(), dt, self.batch, s, s, st),
+                           "hgr_crop_normalize")
+                self._forward_decode(ln, dt, st)
+                ln.compute_done.record(self.compute)
+            self._copy_back(ln)
         ln.busy = True
         return i
 
@@ -110,22 +133,22 @@ class HandPipeline:
         idx = np.zeros(self.batch, dtype=np.int32) if frame_index is None else np.asarray(frame_index, dtype=np.int32)
         inv = np.stack([invert_affine(box_to_affine(b, s)) for b in boxes])
         dt = _lib.F32 if self.dtype == torch.float32 else _lib.BF16
-        with torch.cuda.device(self.device), torch.cuda.stream(ln.stream):
-            ln.d_frames = frames_u8.contiguous().to(self.device, non_blocking=True)
-            ln.d_inv = torch.from_numpy(np.ascontiguousarray(inv)).to(self.device, non_blocking=True)
-            ln.d_idx = torch.from_numpy(idx).to(self.device, non_blocking=True)
-            st = ln.stream.cuda_stream
-            _lib.check(lib.hgr_crop_warp_normalize(ln.d_frames.data_ptr(), frames_u8.shape[0], frames_u8.shape[1],
-                                                   frames_u8.shape[2], ln.d_idx.data_ptr(), ln.d_inv.data_ptr(),
-                                                   self.batch, s, ln.d_x.data_ptr(), dt, st), "hgr_crop_warp_normalize")
-            _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
-                                       ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
-            _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
-                                             ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
-            ln.h_logits.copy_(ln.d_logits, non_blocking=True)
-            ln.h_preds.copy_(ln.d_preds, non_blocking=True)
-            ln.h_maxvals.copy_(ln.d_maxvals, non_blocking=True)
-            ln.done.record(ln.stream)
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(ln.stream):
+                ln.d_frames = frames_u8.contiguous().to(self.device, non_blocking=True)
+                ln.d_inv = torch.from_numpy(np.ascontiguousarray(inv)).to(self.device, non_blocking=True)
+                ln.d_idx = torch.from_numpy(idx).to(self.device, non_blocking=True)
+                ln.h2d_done.record(ln.stream)
+            with torch.cuda.stream(self.compute):
+                self.compute.wait_event(ln.h2d_done)
+                st = self.compute.cuda_stream
+                _lib.check(lib.hgr_crop_warp_normalize(ln.d_frames.data_ptr(), frames_u8.shape[0], frames_u8.shape[1],
+                                                       frames_u8.shape[2], ln.d_idx.data_ptr(), ln.d_inv.data_ptr(),
+                                                       self.batch, s, ln.d_x.data_ptr(), dt, st),
+                           "hgr_crop_warp_normalize")
+                self._forward_decode(ln, dt, st)
+                ln.compute_done.record(self.compute)
+            self._copy_back(ln)
         ln.busy = True
         return i
 
