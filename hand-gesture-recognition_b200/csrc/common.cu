@@ -34,6 +34,19 @@ bool pdl_enabled() {
   return on;
 }
 
+int prefetch_distance() {
+  static const int d = [] {
+    const char* v = getenv("HGR_PREFETCH");
+    return (v && *v) ? atoi(v) : 0;  // measured on B200: distances 1, 2, 4 are 1-5 % SLOWER than none
+  }();
+  return d;
+}
+
+bool cluster_enabled() {
+  static const bool on = env_flag("HGR_CLUSTER", true);
+  return on;
+}
+
 bool zigzag_enabled() {
   static const bool on = env_flag("HGR_ZIGZAG", true);
   return on;

@@ -35,14 +35,17 @@ constexpr int kABytes = kTileM * kTileK * 2;     // 16 KiB
 constexpr int kStageBufBytes = kTileM * 64 * 2;  // one 64-channel output chunk, 16 KiB
 constexpr int kMaxCout = 1024;
 
-template <int BN>
+// CL = 1: one CTA per tile (tcgen05.mma cta_group::1).  CL = 2: a CTA PAIR works on two neighbouring M tiles of
+// the same N tile with cta_group::2 MMAs (M = 256): every CTA stages its own 128 rows of A and only HALF of the
+// weight tile, so a pipeline stage is smaller and - what decides - shared-memory traffic per MMA cycle drops:
+// with cta_group::1 a BN = 256 k-step reads 12 KiB and TMA writes 48 KiB per 512 MMA cycles (192 B/clk against
+// the SM's 128 B/clk, measured as 70-77 % tensor-pipe utilisation at best, 50 % for BN = 128); the pair needs
+// 128 B/clk (BN = 256).
+template <int BN, int CL = 1>
 struct Cfg {
-  static constexpr int kBBytes = BN * kTileK * 2;
-  // BN = 128 (3x3 convs of cspelan2, conv2) is bound by operand delivery from L2, not by the tensor pipe or HBM:
-  // a k-step is 32 KiB for 256 MMA cycles, so the bytes in flight decide.  It trades the second output
-  // staging buffer of each epilogue group for a fifth pipeline stage.
-  static constexpr int kStages = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
-  static constexpr int kOutBufs = BN == 128 ? 1 : 2;  // staging buffers per epilogue group
+  static constexpr int kBBytes = BN * kTileK * 2 / CL;  // weight bytes THIS CTA stages per k-step
+  static constexpr int kStages = CL == 2 ? (BN == 256 ? 5 : 7) : (BN == 256 ? 3 : (BN == 128 ? 5 : 6));
+  static constexpr int kOutBufs = (BN == 128 || CL == 2) ? 1 : 2;  // staging buffers per epilogue group
   static constexpr int kOffA = 0;
   static constexpr int kOffB = kStages * kABytes;
   static constexpr int kOffOut = kOffB + kStages * kBBytes;     // [2 groups][kOutBufs][16 KiB]
@@ -52,6 +55,7 @@ struct Cfg {
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmemPtr + 16;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
+  static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan exceeds one CTA");
 };
 
 // Fast activations for the epilogue.  The epilogue runs with ONE warp per SM
@@ -87,10 +91,12 @@ __device__ __forceinline__ float apply_act(float v) {
 struct TileMap {
   int tiles_w, tiles_h, tiles_nout, bw, bh, bimg, bn;
   int last;  // >= 0: walk the grid back to front (tile -> last - tile)
+  int cl, rank;  // cluster size and this CTA's rank: a cluster walks (M-tile group, N-tile) work items together,
+                 // rank r takes M tile cl * group + r (it may lie beyond the map: TMA clips loads and stores)
   __device__ __forceinline__ void coords(int tile, int& w0, int& h0, int& n0, int& noff) const {
     if (last >= 0) tile = last - tile;
     const int nt = tile % tiles_nout;
-    int mt = tile / tiles_nout;
+    int mt = (tile / tiles_nout) * cl + rank;
     const int tw = mt % tiles_w;
     mt /= tiles_w;
     const int th = mt % tiles_h;
@@ -111,7 +117,8 @@ template <int BN, int ACT, bool RES, int NBUF, int ROW = ROW_NONE>
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtensorMap* tmO, const TileMap& tm,
                                                uint8_t* out_bufs, const float* s_scale, const float* s_shift,
                                                uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t tmem_base,
-                                               int group, int total_tiles) {
+                                               int group, int total_tiles, int first, int stride,
+                                               int pair_rank = -1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;         // TMEM lane quarter this warp may touch
   const int row = q * 32 + lane;  // pixel row inside the tile == TMEM lane
@@ -123,7 +130,7 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
   const uint32_t sw = static_cast<uint32_t>(row & 7);
   uint32_t store_count = 0;
   int iter = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+  for (int tile = first; tile < total_tiles; tile += stride, ++iter) {
     if ((iter & 1) != group) continue;
     const uint32_t acc_phase = (iter >> 1) & 1;
     int w0, h0, n0, noff;
@@ -179,7 +186,9 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       tmem_ld_wait();
       if (j == BN / 64 - 1) {
         tc_fence_before();
-        mbar_arrive(&acc_empty_bar[group]);
+        // pair mode: the accumulator stage belongs to the leader's MMA thread, which waits for BOTH CTAs' readers
+        if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);
+        else mbar_arrive_cluster(&acc_empty_bar[group], 0);
       }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -260,11 +269,15 @@ __device__ __forceinline__ void load_affine(const GemmParams& p, float* s_scale,
   }
 }
 
-template <int BN, int ACT, bool RES, int ROW = ROW_NONE>
+// CL = 2: the kernel runs as clusters of two CTAs that work on the same N tile and k-steps of two neighbouring M
+// tiles.  Each CTA fetches HALF of every weight tile and multicasts it into both shared memories, which halves the
+// weight traffic from L2 - the bound of these layers is operand delivery (about 74 B/clk/SM), not the tensor pipe.
+// A pipeline slot is released by BOTH MMA warps (multicast tcgen05.commit), because either producer writes both.
+template <int BN, int ACT, bool RES, int ROW = ROW_NONE, int CL = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CL>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
   const int warp = threadIdx.x >> 5;
@@ -296,39 +309,61 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 128);
+      mbar_init(&acc_empty_bar[i], 128 * CL);  // pair mode: the readers of both CTAs release the leader's stage
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CL == 2) {
+      tmem_alloc_2sm(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   load_affine<ACT>(p, s_scale, s_shift);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above touched only parameters; from here on the previous kernel's output is read
   pdl_launch_dependents();
   pdl_wait();
 
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = tiles_m * p.tiles_nout;
+  const int total_tiles = ((tiles_m + CL - 1) / CL) * p.tiles_nout;  // work items of one cluster-wide walk
   const int ksteps = p.num_taps * p.chunks_per_tap;
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
   const int bimg = kTileM >> (p.bw_log2 + p.bh_log2);
+  const int first = blockIdx.x / CL, stride = gridDim.x / CL;
 
-  const TileMap tm{p.tiles_w, p.tiles_h, p.tiles_nout, bw, bh, bimg, BN, p.reverse ? total_tiles - 1 : -1};
+  const TileMap tm{p.tiles_w, p.tiles_h, p.tiles_nout, bw, bh, bimg, BN, p.reverse ? total_tiles - 1 : -1, CL,
+                   (int)cta_rank};
 
   if (warp == 0) {
     // ================= TMA producer =================
     if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < total_tiles; tile += stride) {
         int w0, h0, n0, noff;
         tm.coords(tile, w0, h0, n0, noff);
+        if (p.prefetch_dist > 0) {
+          // L2 prefetch of the A tile this CTA will need `prefetch_dist` tiles from now (centre tap, every channel
+          // chunk): the activations were written by the previous kernel and mostly come from HBM on first touch
+          const int ahead = tile + p.prefetch_dist * stride;
+          if (ahead < total_tiles) {
+            int pw0, ph0, pn0, pnoff;
+            tm.coords(ahead, pw0, ph0, pn0, pnoff);
+            const int ct = p.num_taps >> 1;
+            for (int chunk = 0; chunk < p.chunks_per_tap; ++chunk)
+              tma_prefetch_5d(&tmA, p.a_c_off + p.tap_dc[ct] + chunk * kTileK, pw0 + p.tap_dw[ct], p.tap_p[ct],
+                              ph0 + p.tap_dh[ct], pn0);
+          }
+        }
         int ks = 0;
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int cw = w0 + p.tap_dw[tap];
@@ -337,10 +372,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int cc = p.a_c_off + p.tap_dc[tap];
           for (int chunk = 0; chunk < p.chunks_per_tap; ++chunk, ++ks) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], kABytes + C::kBBytes);
-            tma_load_5d(smem + C::kOffA + stage * kABytes, &tmA, &full_bar[stage], cc + chunk * kTileK, cw, cp, ch,
-                        n0);
-            tma_load_2d(smem + C::kOffB + stage * C::kBBytes, &tmW, &full_bar[stage], ks * kTileK, noff);
+            if constexpr (CL == 1) {
+              mbar_expect_tx(&full_bar[stage], kABytes + C::kBBytes);
+              tma_load_5d(smem + C::kOffA + stage * kABytes, &tmA, &full_bar[stage], cc + chunk * kTileK, cw, cp, ch,
+                          n0);
+              tma_load_2d(smem + C::kOffB + stage * C::kBBytes, &tmW, &full_bar[stage], ks * kTileK, noff);
+            } else {
+              // the leader's barrier counts the bytes both CTAs of the pair bring in
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CL * (kABytes + C::kBBytes));
+              tma_load_5d_2sm(smem + C::kOffA + stage * kABytes, &tmA, &full_bar[stage], cc + chunk * kTileK, cw, cp,
+                              ch, n0);
+              tma_load_2d_2sm(smem + C::kOffB + stage * C::kBBytes, &tmW, &full_bar[stage], ks * kTileK,
+                              noff + (int)cta_rank * (BN / CL));
+            }
             if (++stage == C::kStages) {
               stage = 0;
               phase ^= 1;
@@ -349,13 +393,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+  } else if (warp == 1 && (CL == 1 || cta_rank == 0)) {
+    // ================= MMA issuer (pair mode: the leader only) =================
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM * CL, BN);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = first; tile < total_tiles; tile += stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
@@ -370,10 +414,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint64_t b_base = umma_desc_sw128(smem_u32(smem + C::kOffB + stage * C::kBBytes), 1024);
         if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k)
-            umma_bf16_ss(tmem_d, a_base + 2 * k, b_base + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (ks == ksteps - 1) umma_commit(&acc_full_bar[acc]);
+          for (int k = 0; k < kTileK / 16; ++k) {
+            if constexpr (CL == 1) umma_bf16_ss(tmem_d, a_base + 2 * k, b_base + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss_2sm(tmem_d, a_base + 2 * k, b_base + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CL == 1) {
+            umma_commit(&empty_bar[stage]);
+            if (ks == ksteps - 1) umma_commit(&acc_full_bar[acc]);
+          } else {
+            umma_commit_2sm(&empty_bar[stage], 0b11);
+            if (ks == ksteps - 1) umma_commit_2sm(&acc_full_bar[acc], 0b11);
+          }
         }
         __syncwarp();
         if (++stage == C::kStages) {
@@ -387,13 +438,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int group = (warp - 4) >> 2;  // accumulator stage this group drains
     epilogue_group<BN, ACT, RES, C::kOutBufs, ROW>(p, &tmO, tm, smem + C::kOffOut + group * C::kOutBufs * kStageBufBytes,
                                                    s_scale, s_shift, acc_full_bar, acc_empty_bar, tmem_base, group,
-                                                   total_tiles);
+                                                   total_tiles, first, stride, CL == 2 ? (int)cta_rank : -1);
   }
 
   // ---- teardown ---------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -481,7 +536,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();
 
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN, p.reverse ? total_tiles - 1 : -1};
+  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN, p.reverse ? total_tiles - 1 : -1, 1, 0};
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -545,7 +600,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     const int group = (warp - 4) >> 2;
     epilogue_group<BN, ACT, RES, 1>(p, &tmO, tm, smem + C::kOffOut + group * kStageBufBytes, s_scale, s_shift,
-                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles);
+                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles, (int)blockIdx.x,
+                                    (int)gridDim.x);
   }
 
   tc_fence_before();
@@ -569,21 +625,52 @@ int launch_halo_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUten
   return 0;
 }
 
-template <int BN, int ACT, bool RES, int ROW = ROW_NONE>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
-                int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int BN, int ACT, bool RES, int ROW, int CL>
+int launch_impl_cl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                   int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT, RES, ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, ACT, RES, ROW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::kSmemBytes));
     configured = true;
   }
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.tiles_nout;
-  const int grid = total < num_sms ? total : num_sms;
-  HGR_CHECK_CUDA(launch_pdl(gemm_kernel<BN, ACT, RES, ROW>, dim3(grid), dim3(kThreads), C::kSmemBytes, stream, tmA, tmW, tmO,
-                            p));
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int items = ((tiles_m + CL - 1) / CL) * p.tiles_nout;
+  int grid = items * CL < num_sms ? items * CL : num_sms;
+  grid -= grid % CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  HGR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, ACT, RES, ROW, CL>, tmA, tmW, tmO, p));
   return 0;
+}
+
+template <int BN, int ACT, bool RES, int ROW = ROW_NONE>
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                int num_sms, cudaStream_t stream) {
+  if constexpr (BN >= 128) {
+    if (p.cluster == 2) return launch_impl_cl<BN, ACT, RES, ROW, 2>(tmA, tmW, tmO, p, num_sms, stream);
+  }
+  return launch_impl_cl<BN, ACT, RES, ROW, 1>(tmA, tmW, tmO, p, num_sms, stream);
 }
 
 template <int BN>

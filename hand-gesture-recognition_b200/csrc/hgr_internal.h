@@ -33,6 +33,10 @@ const char* last_error();
 bool pdl_enabled();
 // HGR_ZIGZAG=0 disables the alternating tile order of plan.cu.
 bool zigzag_enabled();
+// HGR_CLUSTER=0 disables the CTA-pair (cta_group::2) mode of the implicit-GEMM kernel.
+bool cluster_enabled();
+// HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
+int prefetch_distance();
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -75,6 +79,8 @@ struct GemmParams {
   int cout;              // channels produced by this layer (length of scale/shift)
   int act;
   int reverse;           // walk the tile grid back to front (see plan.cu: zig-zag order for L2 reuse)
+  int prefetch_dist;     // > 0: L2-prefetch the A tile needed that many tiles ahead (HGR_PREFETCH, default 2)
+  int cluster;           // 1, or 2 = CTA-pair mode, cta_group::2 MMAs (the W map's box then holds BN / 2 rows)
   const float* scale;  // nullable: 1
   const float* shift;  // nullable: 0
   const __nv_bfloat16* res;  // nullable; element strides below

@@ -40,6 +40,11 @@ int ilog2(int v) {
   return l;
 }
 
+// CTA-pair mode (cta_group::2, gemm_tcgen05.cu) pays off where the tensor pipe is the bound: measured on B200
+// (gpurun r2g, batch 1024) the K >= 576 layers gain 10-20 % (down1 1464 TF/s, cspelan3 3x3 1440 TF/s), the HBM-
+// and epilogue-bound K <= 512 layers (1x1 convs of cspelan1/2, ViT linears) lose up to 25 %.
+bool use_pair_mode(int bn, int K) { return bn >= 128 && K >= 576 && cluster_enabled(); }
+
 // Pixel box (bw x bh x bi = 128 pixels) for a W x H feature map.
 void pick_box(int W, int H, int& bw, int& bh, int& bi) {
   bw = 16;
@@ -126,7 +131,9 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
     const uint64_t K = (uint64_t)k * k * cin;
     const uint64_t dims[2] = {K, (uint64_t)cout};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    p.cluster = use_pair_mode(op.bn, k * k * cin) && !op.halo ? 2 : 1;
+    p.prefetch_dist = prefetch_distance();
+    const uint32_t box[2] = {64, (uint32_t)(op.bn / p.cluster)};
     if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
   }
   {
@@ -186,7 +193,9 @@ int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const vo
   {
     const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)cout};
     const uint64_t strides[1] = {(uint64_t)cin * 2};
-    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    p.cluster = use_pair_mode(op.bn, cin) ? 2 : 1;
+    p.prefetch_dist = prefetch_distance();
+    const uint32_t box[2] = {64, (uint32_t)(op.bn / p.cluster)};
     if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
   }
   {
@@ -247,7 +256,9 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
   {
     const uint64_t dims[2] = {(uint64_t)cin, (uint64_t)kDim};
     const uint64_t strides[1] = {(uint64_t)cin * 2};
-    const uint32_t box[2] = {64, 256};
+    p.cluster = use_pair_mode(256, cin) ? 2 : 1;
+    p.prefetch_dist = prefetch_distance();
+    const uint32_t box[2] = {64, (uint32_t)(256 / p.cluster)};
     if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
   }
   {
@@ -320,7 +331,9 @@ int build_dgrad_s2_op(GemmOp& op, const void* dz, int B, int H, int W, int cout_
     const uint64_t K = (uint64_t)p.num_taps * cout_fwd;
     const uint64_t dims[2] = {K, (uint64_t)cin_fwd};
     const uint64_t strides[1] = {K * 2};
-    const uint32_t box[2] = {64, (uint32_t)op.bn};
+    p.cluster = use_pair_mode(op.bn, (int)K) ? 2 : 1;
+    p.prefetch_dist = prefetch_distance();
+    const uint32_t box[2] = {64, (uint32_t)(op.bn / p.cluster)};
     if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
   }
   {
