@@ -17,10 +17,10 @@ echo "reference arm exit $?" | tee -a $out/summary.txt
 SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
 OURS="regex:gemm_kernel|halo_kernel|conv1_kernel|attention_kernel|pose_head_kernel|cls_head_kernel|fill_cls_kernel"
 timeout 600 $SHORT > $out/plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s 162 -c 108 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s 138 -c 92 --csv \
     --log-file $out/launches.csv $SHORT > $out/ncu_list.log 2>&1
 echo "ncu list exit $?" | tee -a $out/summary.txt
-timeout 1500 ncu --set full --clock-control none -k "$OURS" -s 162 -c 54 -o $out/step_full $SHORT > $out/ncu_full.log 2>&1
+timeout 1500 ncu --set full --clock-control none -k "$OURS" -s 138 -c 46 -o $out/step_full $SHORT > $out/ncu_full.log 2>&1
 echo "ncu full exit $?" | tee -a $out/summary.txt
 ncu -i $out/step_full.ncu-rep --page raw --csv > $out/step_full_raw.csv 2>> $out/ncu_full.log
 ls -la $out
