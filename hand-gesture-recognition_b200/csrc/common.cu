@@ -42,6 +42,11 @@ int prefetch_distance() {
   return d;
 }
 
+bool halo_pair_enabled() {
+  static const bool on = env_flag("HGR_HALO_PAIR", false);  // measured: 0.168 -> 0.192 ms per layer, slower
+  return on && cluster_enabled();
+}
+
 bool cluster_enabled() {
   static const bool on = env_flag("HGR_CLUSTER", true);
   return on;

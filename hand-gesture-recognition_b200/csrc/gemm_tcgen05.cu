@@ -464,12 +464,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // (tools/umma_probe.cu: any 128 B-aligned start and any stride byte offset with base_offset = 0).
 // All nine 64x64 weight tiles (72 KiB) stay resident in smem for the whole kernel, so the
 // per-tile operand traffic drops from 216 KiB to 22.5 KiB.
+template <int CL>
 struct HaloCfg {
   static constexpr int kPatchRows = 10 * 18;
   static constexpr int kPatchBytes = kPatchRows * 128;     // 23040, what one TMA box delivers
   static constexpr int kPatchStride = 23 * 1024;           // stage pitch, keeps 1024-byte alignment
-  static constexpr int kStages = 4;
-  static constexpr int kWBytes = 9 * 64 * 128;             // nine [64 x 64] bf16 weight tiles
+  static constexpr int kStages = CL == 2 ? 5 : 4;
+  static constexpr int kTapBytes = 64 * 128 / CL;          // this CTA's rows of one tap's [64 x 64] weight tile
+  static constexpr int kWBytes = 9 * kTapBytes;
   static constexpr int kOffW = 0;
   static constexpr int kOffA = kWBytes;
   static constexpr int kOffOut = kOffA + kStages * kPatchStride;  // [2 groups][1 buf][16 KiB]
@@ -479,13 +481,17 @@ struct HaloCfg {
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmemPtr + 16;
   static constexpr int kTmemCols = 128;
+  static_assert(kOffA % 1024 == 0 && kSmemBytes <= 227 * 1024, "halo shared-memory plan");
 };
 
-template <int ACT, bool RES>
+// CL = 2: CTA-pair mode, same protocol as gemm_kernel<..., 2>: two neighbouring 8 x 16 tiles form one M = 256 MMA,
+// every CTA stages its own halo patch and keeps only HALF of each tap's weight rows resident.  A 64-channel MMA is
+// bound by shared-memory reads (4 KiB of A + 2 KiB of B per 32 MMA cycles = 192 B/clk); the pair reads 4 + 1 KiB.
+template <int ACT, bool RES, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
-  using C = HaloCfg;
+  using C = HaloCfg<CL>;
   constexpr int BN = 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -517,54 +523,75 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 128);
+      mbar_init(&acc_empty_bar[i], 128 * CL);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CL == 2) {
+      tmem_alloc_2sm(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   load_affine<ACT>(p, s_scale, s_shift);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above touched only parameters; from here on the previous kernel's output is read
   pdl_launch_dependents();
   pdl_wait();
 
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN, p.reverse ? total_tiles - 1 : -1, 1, 0};
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = (tiles_m + CL - 1) / CL;  // work items of one cluster-wide walk
+  const int first = blockIdx.x / CL, stride = gridDim.x / CL;
+  const TileMap tm{p.tiles_w, p.tiles_h, 1, 8, 16, 1, BN, p.reverse ? total_tiles - 1 : -1, CL, (int)cta_rank};
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      // resident weights: tap t is rows [0, 64) x K columns [64 t, 64 t + 64)
-      mbar_expect_tx(w_bar, C::kWBytes);
-      for (int t = 0; t < 9; ++t) tma_load_2d(smem + C::kOffW + t * 8192, &tmW, w_bar, t * 64, 0);
+      // resident weights: tap t is rows [0, 64) x K columns [64 t, 64 t + 64); a pair CTA keeps rows [32 rank, +32)
+      if constexpr (CL == 1) {
+        mbar_expect_tx(w_bar, C::kWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(smem + C::kOffW + t * C::kTapBytes, &tmW, w_bar, t * 64, 0);
+      } else {
+        if (cta_rank == 0) mbar_expect_tx(w_bar, CL * C::kWBytes);
+        for (int t = 0; t < 9; ++t)
+          tma_load_2d_2sm(smem + C::kOffW + t * C::kTapBytes, &tmW, w_bar, t * 64, (int)cta_rank * (BN / CL));
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < total_tiles; tile += stride) {
         int w0, h0, n0, noff;
         tm.coords(tile, w0, h0, n0, noff);
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], C::kPatchBytes);
-        tma_load_5d(smem + C::kOffA + stage * C::kPatchStride, &tmA, &full_bar[stage], p.a_c_off, w0 - 1, 0, h0 - 1,
-                    n0);
+        if constexpr (CL == 1) {
+          mbar_expect_tx(&full_bar[stage], C::kPatchBytes);
+          tma_load_5d(smem + C::kOffA + stage * C::kPatchStride, &tmA, &full_bar[stage], p.a_c_off, w0 - 1, 0, h0 - 1,
+                      n0);
+        } else {
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CL * C::kPatchBytes);
+          tma_load_5d_2sm(smem + C::kOffA + stage * C::kPatchStride, &tmA, &full_bar[stage], p.a_c_off, w0 - 1, 0,
+                          h0 - 1, n0);
+        }
         if (++stage == C::kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+  } else if (warp == 1 && (CL == 1 || cta_rank == 0)) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM * CL, BN);
     mbar_wait(w_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = first; tile < total_tiles; tile += stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
@@ -583,12 +610,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t ad = a_base + static_cast<uint64_t>((((tap / 3) * 10 + (tap % 3)) * 128 + k * 32) >> 4);
-              const uint64_t bd = b_base + static_cast<uint64_t>((tap * 8192 + k * 32) >> 4);
-              umma_bf16_ss(tmem_d, ad, bd, idesc, (tap | k) != 0 ? 1u : 0u);
+              const uint64_t bd = b_base + static_cast<uint64_t>((tap * C::kTapBytes + k * 32) >> 4);
+              if constexpr (CL == 1) umma_bf16_ss(tmem_d, ad, bd, idesc, (tap | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss_2sm(tmem_d, ad, bd, idesc, (tap | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&acc_full_bar[acc]);
+          if constexpr (CL == 1) {
+            umma_commit(&empty_bar[stage]);
+            umma_commit(&acc_full_bar[acc]);
+          } else {
+            umma_commit_2sm(&empty_bar[stage], 0b11);
+            umma_commit_2sm(&acc_full_bar[acc], 0b11);
+          }
         }
       }
       __syncwarp();
@@ -600,29 +633,63 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     const int group = (warp - 4) >> 2;
     epilogue_group<BN, ACT, RES, 1>(p, &tmO, tm, smem + C::kOffOut + group * kStageBufBytes, s_scale, s_shift,
-                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles, (int)blockIdx.x,
-                                    (int)gridDim.x);
+                                    acc_full_bar, acc_empty_bar, tmem_base, group, total_tiles, first, stride,
+                                    CL == 2 ? (int)cta_rank : -1);
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  if constexpr (CL > 1) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 2) {
+    if constexpr (CL == 2) tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int ACT, bool RES, int CL>
+int launch_halo_cl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
+                   int num_sms, cudaStream_t stream) {
+  using C = HaloCfg<CL>;
+  static bool configured = false;
+  if (!configured) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<ACT, RES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::kSmemBytes));
+    configured = true;
+  }
+  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int items = (tiles_m + CL - 1) / CL;
+  int grid = items * CL < num_sms ? items * CL : num_sms;
+  grid -= grid % CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  HGR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<ACT, RES, CL>, tmA, tmW, tmO, p));
+  return 0;
 }
 
 template <int ACT, bool RES>
 int launch_halo_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                      int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        HaloCfg::kSmemBytes));
-    configured = true;
-  }
-  const int total = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int grid = total < num_sms ? total : num_sms;
-  HGR_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<ACT, RES>, dim3(grid), dim3(kThreads), HaloCfg::kSmemBytes, stream, tmA, tmW,
-                            tmO, p));
-  return 0;
+  if (p.cluster == 2) return launch_halo_cl<ACT, RES, 2>(tmA, tmW, tmO, p, num_sms, stream);
+  return launch_halo_cl<ACT, RES, 1>(tmA, tmW, tmO, p, num_sms, stream);
 }
 
 template <int BN, int ACT, bool RES, int ROW, int CL>

@@ -35,6 +35,8 @@ bool pdl_enabled();
 bool zigzag_enabled();
 // HGR_CLUSTER=0 disables the CTA-pair (cta_group::2) mode of the implicit-GEMM kernel.
 bool cluster_enabled();
+// HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.
+bool halo_pair_enabled();
 // HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
 int prefetch_distance();
 

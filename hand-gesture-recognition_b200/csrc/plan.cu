@@ -131,7 +131,7 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
     const uint64_t K = (uint64_t)k * k * cin;
     const uint64_t dims[2] = {K, (uint64_t)cout};
     const uint64_t strides[1] = {K * 2};
-    p.cluster = use_pair_mode(op.bn, k * k * cin) && !op.halo ? 2 : 1;
+    p.cluster = (op.halo ? halo_pair_enabled() : use_pair_mode(op.bn, k * k * cin)) ? 2 : 1;
     p.prefetch_dist = prefetch_distance();
     const uint32_t box[2] = {64, (uint32_t)(op.bn / p.cluster)};
     if (int r = make_tensor_map_bf16(&op.w, wgt, 2, dims, strides, box)) return r;
