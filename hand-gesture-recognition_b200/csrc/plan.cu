@@ -2,6 +2,7 @@
 // per-layer tensor maps, and the launch sequence that realises
 // MultiTaskNet.forward (reference model/multitasknet.py:24-29 ->
 // model/gelan.py:165-176 -> model/transformer.py:129-152).
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -27,6 +28,9 @@ int device_sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       n = 148;
+    // HGR_SM_LIMIT=<k> caps the persistent grids at k CTAs (experiments with two half-batch streams side by side)
+    const char* v = getenv("HGR_SM_LIMIT");
+    if (v && *v && atoi(v) > 0 && atoi(v) < n) n = atoi(v);
   }
   return n;
 }

@@ -193,3 +193,18 @@ def test_classifier_session_has_the_onnxruntime_contract():
     assert landmarks_pred.shape == (1, 21, 2)
     assert [o.name for o in classifier.get_outputs()] == ["label_pred", "heatmap_pred"]
     assert classifier.run(["heatmap_pred"], inp)[0].shape == (1, 21, 48, 48)
+
+
+@pytest.mark.parametrize("size,batch", [(64, 1), (64, 5), (128, 3), (320, 2), (192, 7)])
+def test_forward_odd_shapes_vs_oracle(size, batch):
+    """Ragged tile grids: odd batches and small / large maps leave CTA pairs with an out-of-range second tile,
+    partially filled 128-pixel boxes and multi-image boxes; TMA clipping has to make all of that invisible."""
+    m, sd = build(size, 2)
+    x = O.synthetic_images(batch, size, 9)
+    with torch.no_grad():
+        cls, hm, attn = m(x.cuda())
+    cls_ref, hm_ref, attn_ref = O.multitasknet_forward(sd, x)
+    r1, m1 = report(f"odd logits {size}/{batch}", cls, cls_ref)
+    r2, m2 = report(f"odd heat {size}/{batch}", hm, hm_ref)
+    r3, _ = report(f"odd attn {size}/{batch}", attn, attn_ref)
+    assert max(r1, r2) <= REL_TOL and max(m1, m2) <= MAX_TOL and r3 <= 5e-2
