@@ -116,13 +116,15 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = 16 * (i >> 2) + 2 * t + (i & 1) + ((i >> 1) & 1) * 8;
-    if (k < 27) {
-      const int c = k % 3, kw = (k / 3) % 3, kh = k / 9;
-      koff[i] = (c * kRowsIn + kh) * pitch + kw + (kLeft - 1);
-    } else {
-      koff[i] = -1;
-    }
+    // slots k >= 27 multiply zero weight columns, so they may read ANY staged (finite) element: point them at tap 0
+    const int kk = k < 27 ? k : 0;
+    const int c = kk % 3, kw = (kk / 3) % 3, kh = kk / 9;
+    koff[i] = (c * kRowsIn + kh) * pitch + kw + (kLeft - 1);
   }
+  // staging swizzle of this lane, per 8-channel group: ((nt ^ g) & 7) * 8 elements
+  int swz[8];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) swz[nt] = (((nt ^ g) & 7) << 3) + 2 * t;
 
   __nv_bfloat16* st = stage + warp * 16 * 64;
   const int mtiles_per_row = So >> 4;
@@ -138,9 +140,14 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
     }
     __syncthreads();
     const int oh0 = (rb0 + it) * kRowsOut;
-    for (int mt = warp; mt < mtiles; mt += kWarps) {
-      const int orow = mt / mtiles_per_row;
-      const int ow0 = (mt % mtiles_per_row) << 4;
+    // (orow, tcol) walk the 16-pixel tiles of this warp without divisions
+    int orow = warp / mtiles_per_row, tcol = warp % mtiles_per_row;
+    for (int mt = warp; mt < mtiles; mt += kWarps, tcol += kWarps) {
+      while (tcol >= mtiles_per_row) {
+        tcol -= mtiles_per_row;
+        ++orow;
+      }
+      const int ow0 = tcol << 4;
       // pixel (orow, ow0+g) and (orow, ow0+g+8): patch offset of tap (0,0), channel 0
       const int base0 = (2 * orow) * pitch + 2 * (ow0 + g);
       const int base1 = base0 + 16;
@@ -151,8 +158,8 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ko = koff[s * 4 + i];
-          e[i] = ko >= 0 ? pu[base0 + ko] : (unsigned short)0;
-          e[4 + i] = ko >= 0 ? pu[base1 + ko] : (unsigned short)0;
+          e[i] = pu[base0 + ko];
+          e[4 + i] = pu[base1 + ko];
         }
         a[s][0] = (uint32_t)e[0] | ((uint32_t)e[1] << 16);  // row g,   k 2t,2t+1
         a[s][1] = (uint32_t)e[4] | ((uint32_t)e[5] << 16);  // row g+8, k 2t,2t+1
@@ -178,8 +185,8 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
           for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
         }
         // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
-        *reinterpret_cast<uint32_t*>(st + g * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[0], h[1]);
-        *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + (((nt ^ g) & 7) << 3) + 2 * t) = pack_bf16x2(h[2], h[3]);
+        *reinterpret_cast<uint32_t*>(st + g * 64 + swz[nt]) = pack_bf16x2(h[0], h[1]);
+        *reinterpret_cast<uint32_t*>(st + (g + 8) * 64 + swz[nt]) = pack_bf16x2(h[2], h[3]);
       }
       __syncwarp();
       // 16 pixels x 128 B are contiguous in NHWC: 4 fully coalesced 512-byte stores
