@@ -63,6 +63,9 @@ __device__ __forceinline__ void mm_block_nn(const float (&v)[4][4], uint32_t b_a
   }
 }
 
+// PSMEM = false (T > 256 tokens, e.g. 257 at 256x256): the probability map does not fit next to Q/K/V/dO, so it is
+// read straight from global memory (L2-resident, 150 KB per head) with explicit bounds instead of zero padding.
+template <bool PSMEM>
 __global__ void __launch_bounds__(kBThreads)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs, int pp,
                      const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
@@ -73,8 +76,8 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   __nv_bfloat16* sk = sq + Tp * kBPitch;
   __nv_bfloat16* sv = sk + Tp * kBPitch;
   __nv_bfloat16* sdo = sv + Tp * kBPitch;
-  __nv_bfloat16* sp = sdo + Tp * kBPitch;              // [Tp][spp]
-  float* sD = reinterpret_cast<float*>(sp + Tp * spp);  // [Tp]
+  __nv_bfloat16* sp = sdo + Tp * kBPitch;  // [Tp][spp] (PSMEM only)
+  float* sD = reinterpret_cast<float*>(sp + (PSMEM ? Tp * spp : 0));  // [Tp]
   const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -94,7 +97,9 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   }
   // ---- stage P (rows / columns >= T zero) ----
   const __nv_bfloat16* pb = probs + (size_t)(b * kHeads + h) * T * pp;
-  if ((pp & 7) == 0 && pp >= Tp) {
+  if constexpr (!PSMEM) {
+    // nothing to stage
+  } else if ((pp & 7) == 0 && pp >= Tp) {
     const int cpr = Tp >> 3;  // the buffer's pad columns are zero (cleared once by the plan)
     for (int i = tid; i < Tp * cpr; i += kBThreads) {
       const int row = i / cpr, c = i % cpr;
@@ -126,6 +131,9 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   }
   __syncthreads();
 
+  auto ldp = [&](int row, int col) -> float {
+    return (row < T && col < T) ? __bfloat162float(pb[(size_t)row * pp + col]) : 0.f;
+  };
   const int ntiles = (T + 15) >> 4;
   const int nblocks = Tp >> 5;  // 32-wide blocks
   // lane addresses: A fragments of 16 rows (ldmatrix), "n-major" B (rows = n, ldmatrix), "k-major" B (rows = k, .trans)
@@ -150,12 +158,24 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int key = kb * 32 + nt * 8 + 2 * t;
-        const uint32_t p0 = *reinterpret_cast<const uint32_t*>(sp + r0 * spp + key);
-        const uint32_t p1 = *reinterpret_cast<const uint32_t*>(sp + r1 * spp + key);
-        ds[nt][0] = bf16_lo(p0) * (ds[nt][0] - D0);
-        ds[nt][1] = bf16_hi(p0) * (ds[nt][1] - D0);
-        ds[nt][2] = bf16_lo(p1) * (ds[nt][2] - D1);
-        ds[nt][3] = bf16_hi(p1) * (ds[nt][3] - D1);
+        float p00, p01, p10, p11;
+        if constexpr (PSMEM) {
+          const uint32_t p0 = *reinterpret_cast<const uint32_t*>(sp + r0 * spp + key);
+          const uint32_t p1 = *reinterpret_cast<const uint32_t*>(sp + r1 * spp + key);
+          p00 = bf16_lo(p0);
+          p01 = bf16_hi(p0);
+          p10 = bf16_lo(p1);
+          p11 = bf16_hi(p1);
+        } else {
+          p00 = ldp(r0, key);
+          p01 = ldp(r0, key + 1);
+          p10 = ldp(r1, key);
+          p11 = ldp(r1, key + 1);
+        }
+        ds[nt][0] = p00 * (ds[nt][0] - D0);
+        ds[nt][1] = p01 * (ds[nt][1] - D0);
+        ds[nt][2] = p10 * (ds[nt][2] - D1);
+        ds[nt][3] = p11 * (ds[nt][3] - D1);
       }
       mm_block_nn(ds, uk + bk_off + kb * 32 * kBPitch * 2, acc);  // dQ += dS K
     }
@@ -188,10 +208,17 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
       for (int nt = 0; nt < 4; ++nt) {
         const int q = qblk * 32 + nt * 8 + 2 * t;
         const float Dq0 = sD[q], Dq1 = sD[q + 1];
-        pt[nt][0] = __uint_as_float((uint32_t)spu[q * spp + c0] << 16);
-        pt[nt][1] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c0] << 16);
-        pt[nt][2] = __uint_as_float((uint32_t)spu[q * spp + c1] << 16);
-        pt[nt][3] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c1] << 16);
+        if constexpr (PSMEM) {
+          pt[nt][0] = __uint_as_float((uint32_t)spu[q * spp + c0] << 16);
+          pt[nt][1] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c0] << 16);
+          pt[nt][2] = __uint_as_float((uint32_t)spu[q * spp + c1] << 16);
+          pt[nt][3] = __uint_as_float((uint32_t)spu[(q + 1) * spp + c1] << 16);
+        } else {
+          pt[nt][0] = ldp(q, c0);
+          pt[nt][1] = ldp(q + 1, c0);
+          pt[nt][2] = ldp(q, c1);
+          pt[nt][3] = ldp(q + 1, c1);
+        }
         dst[nt][0] = pt[nt][0] * (dst[nt][0] - Dq0);
         dst[nt][1] = pt[nt][1] * (dst[nt][1] - Dq1);
         dst[nt][2] = pt[nt][2] * (dst[nt][2] - Dq0);
@@ -410,13 +437,20 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, i
                          cudaStream_t st) {
   const int Tp = (T + 31) / 32 * 32;
   const int pp = probs_pitch > 0 ? probs_pitch : T;
-  const size_t smem = ((size_t)4 * Tp * kBPitch + (size_t)Tp * (Tp + 8)) * 2 + (size_t)Tp * sizeof(float);
-  if (smem > 227 * 1024) {
-    set_error("attention_bwd: %d tokens do not fit one CTA's shared memory (%zu bytes)", T, smem);
+  const size_t base = (size_t)4 * Tp * kBPitch * 2 + (size_t)Tp * sizeof(float);
+  const size_t with_p = base + (size_t)Tp * (Tp + 8) * 2;
+  if (base > 227 * 1024) {
+    set_error("attention_bwd: %d tokens do not fit one CTA's shared memory (%zu bytes)", T, base);
     return -1;
   }
-  HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_bwd_kernel<<<B * kHeads, kBThreads, smem, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, 0.17677669529663687f);
+  const float scale = 0.17677669529663687f;
+  if (with_p <= 227 * 1024) {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_p));
+    attention_bwd_kernel<true><<<B * kHeads, kBThreads, with_p, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, scale);
+  } else {
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
+    attention_bwd_kernel<false><<<B * kHeads, kBThreads, base, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, scale);
+  }
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

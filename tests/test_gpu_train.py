@@ -98,7 +98,7 @@ def test_dgrad_stride2(lib, cin, cout, h, b):
     assert r <= 1e-2
 
 
-@pytest.mark.parametrize("b,t", [(3, 145), (2, 17)])
+@pytest.mark.parametrize("b,t", [(3, 145), (2, 17), (2, 257)])
 def test_attention_bwd(lib, b, t):
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(t)
@@ -176,7 +176,7 @@ def _setup(size, seed, batch):
     return sd, m, x, labels, target, weight
 
 
-@pytest.mark.parametrize("size,seed,batch", [(64, 5, 4), (192, 11, 4)])
+@pytest.mark.parametrize("size,seed,batch", [(64, 5, 4), (192, 11, 4), (256, 13, 2)])
 def test_train_forward_backward_vs_oracle(size, seed, batch):
     from hgr_b200 import loss_and_grads
     from hgr_b200.training import backward_train, forward_train, train_state
