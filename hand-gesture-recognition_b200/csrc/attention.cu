@@ -327,6 +327,168 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
   }
 }
 
+// Online-softmax variant for launches that do not return the probabilities (every layer but the last, and the
+// last one too when the attention map is switched off).  A warp owns 32 query rows (two m16 tiles) and walks the
+// key blocks once: the K and V fragments of a block are fetched from shared memory ONCE for both tiles, which
+// halves the ldmatrix traffic that bounds the strip-in-registers kernel above (ncu: l1tex 74 %, tensor 35 %), and
+// only one 32-key block of scores is live at a time, so the rescaled running output (flash-attention recurrence)
+// costs fewer registers than the 16 x T strip did.
+template <int NKB>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
+                        float scale_log2e, int reverse) {
+  constexpr int Tp = NKB * kKeyBlock;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __nv_bfloat16* sk = sq + Tp * kPitch;
+  __nv_bfloat16* sv = sk + Tp * kPitch;
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int bid = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int b = bid / kHeads, h = bid % kHeads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const __nv_bfloat16* base = qkv + (size_t)b * T * (3 * kHeads * kHd) + h * kHd;
+  {
+    constexpr int kTotal = 3 * Tp * 4;            // 16-byte chunks of Q, K and V
+    constexpr int kBatch = 12;                    // requests in flight per thread
+    for (int i0 = 0; i0 < kTotal; i0 += kBatch * kWarps * 32) {
+      uint4 v[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = i0 + tid + k * kWarps * 32;
+        const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (i < kTotal && row < T)
+          v[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * kHeads * kHd) + part * kHeads * kHd) + c);
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = i0 + tid + k * kWarps * 32;
+        const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+        if (i < kTotal) *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v[k];
+      }
+    }
+  }
+  __syncthreads();
+
+  const int mpairs = (T + 31) >> 5;
+  const uint32_t q_lane = smem_u32(sq) + ((lane & 15) * kPitch + (lane >> 4) * 8) * 2;
+  const uint32_t k_lane = smem_u32(sk) + ((lane & 7) * kPitch + (lane >> 3) * 8) * 2;
+  const uint32_t v_lane = smem_u32(sv) + ((((lane >> 3) & 1) * 8 + (lane & 7)) * kPitch + (lane >> 4) * 8) * 2;
+
+  for (int mp = warp; mp < mpairs; mp += kWarps) {
+    uint32_t qa[2][2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ldmatrix_x4(qa[u][0], q_lane + (mp * 32 + u * 16) * kPitch * 2);
+      ldmatrix_x4(qa[u][1], q_lane + (mp * 32 + u * 16) * kPitch * 2 + 32);
+    }
+    float o[2][4][4];
+    float m[2][2], l[2][2];  // running max (already in exp2 units) and partial row sums: [tile][row g / g + 8]
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      m[u][0] = m[u][1] = -INFINITY;
+      l[u][0] = l[u][1] = 0.f;
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) o[u][nd][0] = o[u][nd][1] = o[u][nd][2] = o[u][nd][3] = 0.f;
+    }
+
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      float s[2][4][4];
+      {
+        uint32_t kf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) ldmatrix_x4(kf[nt], k_lane + (kb * kKeyBlock + nt * 8) * kPitch * 2);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            s[u][nt][0] = s[u][nt][1] = s[u][nt][2] = s[u][nt][3] = 0.f;
+            mma_bf16_16816(s[u][nt], qa[u][0], kf[nt][0], kf[nt][1]);
+            mma_bf16_16816(s[u][nt], qa[u][1], kf[nt][2], kf[nt][3]);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          if (kb == NKB - 1) {  // only the last key block can hold padding keys (checked at launch)
+            const int key = kb * kKeyBlock + nt * 8 + 2 * t;
+            if (key >= T) s[u][nt][0] = s[u][nt][2] = -INFINITY;
+            if (key + 1 >= T) s[u][nt][1] = s[u][nt][3] = -INFINITY;
+          }
+          bm0 = fmaxf(bm0, fmaxf(s[u][nt][0], s[u][nt][1]));
+          bm1 = fmaxf(bm1, fmaxf(s[u][nt][2], s[u][nt][3]));
+        }
+        // key 0 is always valid, so the running max is finite from the first block on
+        const float n0 = fmaxf(m[u][0], quad_max(bm0) * scale_log2e);
+        const float n1 = fmaxf(m[u][1], quad_max(bm1) * scale_log2e);
+        const float a0 = ex2(m[u][0] - n0), a1 = ex2(m[u][1] - n1);
+        m[u][0] = n0;
+        m[u][1] = n1;
+        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          s[u][nt][0] = ex2(fmaf(s[u][nt][0], scale_log2e, -n0));
+          s[u][nt][1] = ex2(fmaf(s[u][nt][1], scale_log2e, -n0));
+          s[u][nt][2] = ex2(fmaf(s[u][nt][2], scale_log2e, -n1));
+          s[u][nt][3] = ex2(fmaf(s[u][nt][3], scale_log2e, -n1));
+          p0 += s[u][nt][0] + s[u][nt][1];
+          p1 += s[u][nt][2] + s[u][nt][3];
+        }
+        l[u][0] = fmaf(l[u][0], a0, p0);
+        l[u][1] = fmaf(l[u][1], a1, p1);
+        if (kb > 0) {
+#pragma unroll
+          for (int nd = 0; nd < 4; ++nd) {
+            o[u][nd][0] *= a0;
+            o[u][nd][1] *= a0;
+            o[u][nd][2] *= a1;
+            o[u][nd][3] *= a1;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {  // two 16-key k-steps per block
+        uint32_t vb[2][4];
+        const uint32_t vaddr = v_lane + (kb * kKeyBlock + j * 16) * kPitch * 2;
+        ldmatrix_x4_trans(vb[0], vaddr);
+        ldmatrix_x4_trans(vb[1], vaddr + 32);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16x2(s[u][2 * j][0], s[u][2 * j][1]);
+          pa[1] = pack_bf16x2(s[u][2 * j][2], s[u][2 * j][3]);
+          pa[2] = pack_bf16x2(s[u][2 * j + 1][0], s[u][2 * j + 1][1]);
+          pa[3] = pack_bf16x2(s[u][2 * j + 1][2], s[u][2 * j + 1][3]);
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {
+            mma_bf16_16816(o[u][2 * np], pa, vb[np][0], vb[np][1]);
+            mma_bf16_16816(o[u][2 * np + 1], pa, vb[np][2], vb[np][3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float inv0 = 1.0f / quad_sum(l[u][0]), inv1 = 1.0f / quad_sum(l[u][1]);
+      const int row0 = mp * 32 + u * 16 + g, row1 = row0 + 8;
+      __nv_bfloat16* orow0 = out + ((size_t)b * T + row0) * (kHeads * kHd) + h * kHd + 2 * t;
+      __nv_bfloat16* orow1 = out + ((size_t)b * T + row1) * (kHeads * kHd) + h * kHd + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        if (row0 < T) *reinterpret_cast<uint32_t*>(orow0 + nd * 8) = pack_bf16x2(o[u][nd][0] * inv0, o[u][nd][1] * inv0);
+        if (row1 < T) *reinterpret_cast<uint32_t*>(orow1 + nd * 8) = pack_bf16x2(o[u][nd][2] * inv1, o[u][nd][3] * inv1);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
@@ -341,6 +503,22 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   // softmax(x * d^-0.5) evaluated as exp2((x - max) * d^-0.5 * log2(e))
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
   const unsigned grid = (unsigned)B * kHeads;
+  if (attn_probs == nullptr && attention_online_enabled()) {
+    // no probabilities to return: online-softmax kernel, K/V fragments shared by two query tiles per warp
+    const int nkb = Tp / kKeyBlock;
+    if (nkb == 5) {
+      HGR_CHECK_CUDA(launch_pdl(attention_kernel_online<5>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T,
+                                scale_log2e, reverse));
+      return 0;
+    }
+    if (nkb == 9) {
+      HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel_online<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+      HGR_CHECK_CUDA(launch_pdl(attention_kernel_online<9>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T,
+                                scale_log2e, reverse));
+      return 0;
+    }
+  }
   if (T <= 5 * kKeyBlock && T > 4 * kKeyBlock) {
     const size_t smem1 = (size_t)3 * 5 * kKeyBlock * kPitch * 2;
     if (attn_probs != nullptr && probs_dtype == DT_BF16)

@@ -42,6 +42,16 @@ int prefetch_distance() {
   return d;
 }
 
+bool attention_online_enabled() {
+  static const bool on = env_flag("HGR_ATTN_ONLINE", true);
+  return on;
+}
+
+bool vit_fused_enabled() {
+  static const bool on = env_flag("HGR_VIT_FUSED", true);
+  return on;
+}
+
 bool halo_pair_enabled() {
   static const bool on = env_flag("HGR_HALO_PAIR", false);  // measured: 0.168 -> 0.192 ms per layer, slower
   return on && cluster_enabled();

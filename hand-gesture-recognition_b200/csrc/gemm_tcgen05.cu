@@ -23,6 +23,7 @@
 
 #include "hgr_internal.h"
 #include "ptx.cuh"
+#include "epilogue_math.cuh"
 
 namespace hgr {
 
@@ -57,35 +58,6 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
   static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan exceeds one CTA");
 };
-
-// Fast activations for the epilogue.  The epilogue runs with ONE warp per SM
-// sub-partition and accumulator stage, so its cost is counted in issue slots:
-// everything that can be decided at compile time (activation, residual) is a
-// template parameter, which also keeps the loop body inside the instruction cache.
-template <int ACT>
-__device__ __forceinline__ float apply_act(float v) {
-  if constexpr (ACT == ACT_SILU) {
-    // v arrives pre-halved (scale and shift are stored * 0.5): x*sigmoid(x) = h + h*tanh(h), h = x/2
-    return fmaf(v, tanh_approx(v), v);
-  } else if constexpr (ACT == ACT_GELU) {
-    // exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): two MUFU ops
-    const float ax = fabsf(v) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
-    const float erf_abs = fmaf(-poly, e, 1.0f);
-    const float hv = 0.5f * v;
-    return fmaf(hv, copysignf(erf_abs, v), hv);
-  } else {
-    return v;
-  }
-}
 
 // tile index -> pixel-box origin and output-channel offset
 struct TileMap {

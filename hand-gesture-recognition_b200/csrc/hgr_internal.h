@@ -35,6 +35,8 @@ bool pdl_enabled();
 bool zigzag_enabled();
 // HGR_CLUSTER=0 disables the CTA-pair (cta_group::2) mode of the implicit-GEMM kernel.
 bool cluster_enabled();
+// HGR_ATTN_ONLINE=0 falls back to the strip-in-registers attention kernels when no probabilities are returned.
+bool attention_online_enabled();
 // HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.
 bool halo_pair_enabled();
 // HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
@@ -103,6 +105,36 @@ int gemm_smem_bytes(int bn);
 // 3x3 s1 64->64 layer with the input halo staged once per 8x16 tile (A map box = (64, 10, 1, 18, 1)).
 int launch_conv3x3_halo(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmO, const GemmParams& p,
                         int num_sms, cudaStream_t stream);
+
+// ------------------------------------------- fused ViT layer tail (vit_block.cu) ----
+// x2 = FeedForward(LN(x1)) + x1 with x1 = attn_out . Wout^T + x0, one chained tcgen05 kernel per layer
+// (transformer.py:75, :93, :29-42, :94).  HGR_VIT_FUSED=0 keeps the three separate GEMM launches.
+bool vit_fused_enabled();
+
+struct VitBlockParams {
+  long long rows;             // tokens (B * T)
+  const __nv_bfloat16* a0;    // attn_out (rows, 256): the A operand of G0 (also reached through the tensor map)
+  const __nv_bfloat16* x0;    // residual stream entering the layer tail, (rows, 256)
+  const float* c1;            // folded LayerNorm: c[j] = sum_k W1'[j][k]
+  const float* d1;            //                   d[j] = sum_k beta[k] W1[j][k] + b1[j]
+  const float* b2;            // net.4 bias
+  float2* stats_out;          // nullable: (mean, rstd) of every x2 row for the next layer's folded LayerNorm
+  int reverse;                // walk the tiles back to front (zig-zag order, see plan.cu)
+  long long* trace;           // nullable: [trace_tiles][16] clock64 marks of CTA 0 (hgr_vit_block_trace)
+  int trace_tiles;
+};
+
+struct VitBlockOp {
+  CUtensorMap a, w0, w1, w2, o;
+  VitBlockParams p;
+  double flops, bytes;
+};
+
+// x2 may alias x0 (every CTA reads the x0 rows of a tile before it stores the same rows of x2).
+int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, long long rows, const void* w_out,
+                       const void* w1, const float* c1, const float* d1, const void* w2, const float* b2, void* x2,
+                       float* stats_out);
+int launch_vit_block(const VitBlockOp& op, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------ tensor maps ----
 // rank <= 5; dims innermost first; strides in bytes for dims 1..rank-1.

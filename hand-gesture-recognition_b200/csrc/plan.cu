@@ -535,6 +535,8 @@ struct hgr_plan {
   std::vector<GemmOp> convs;        // kNumConvs backbone layers
   GemmOp proj;
   GemmOp qkv[kDepth], out[kDepth], ff1[kDepth], ff2[kDepth];
+  VitBlockOp blk[kDepth];  // to_out + residual + FeedForward + residual as one chained kernel (vit_block.cu)
+  bool vit_fused = false;
   // launch sequence of one forward pass
   struct Io {
     const void* x;
@@ -735,7 +737,13 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
       rc = build_linear_op(pl->ff2[l], pl->bp("hidden"), rows, kDim, pl->pp<void>(f + "4.w"), nullptr,
                            pl->pp<float>(f + "4.bias"), ACT_NONE, pl->bp("tokens_b"), pl->bp("tokens"), kDim, nullptr,
                            stats);
+    // the same three layers as ONE chained kernel; x2 overwrites x0 in place, x1 and h stay in shared memory
+    if (!rc)
+      rc = build_vit_block_op(pl->blk[l], pl->bp("attn_out"), pl->bp("tokens"), rows, pl->pp<void>(a + "to_out.w"),
+                              pl->pp<void>(f + "1.w"), pl->pp<float>(f + "1.c"), pl->pp<float>(f + "1.d"),
+                              pl->pp<void>(f + "4.w"), pl->pp<float>(f + "4.bias"), pl->bp("tokens"), stats);
   }
+  pl->vit_fused = vit_fused_enabled();
   if (rc) {
     delete pl;
     return rc;
@@ -783,9 +791,17 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
           return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st,
                                   attn_dir);
         });
-    add_gemm(a + "to_out+residual", &pl->out[l]);
-    add_gemm(f + "0+1+gelu", &pl->ff1[l]);
-    add_gemm(f + "4+residual", &pl->ff2[l]);
+    if (pl->vit_fused) {
+      dir = zig ? !dir : 0;
+      VitBlockOp* blk = &pl->blk[l];
+      blk->p.reverse = dir;
+      add(a + "to_out+residual+feedforward+residual", 0, blk->flops, blk->bytes,
+          [blk](cudaStream_t st, const Io&) { return launch_vit_block(*blk, device_sm_count(), st); });
+    } else {
+      add_gemm(a + "to_out+residual", &pl->out[l]);
+      add_gemm(f + "0+1+gelu", &pl->ff1[l]);
+      add_gemm(f + "4+residual", &pl->ff2[l]);
+    }
   }
   add("decoder.mlp_head", 2, 2.0 * dB * kDim * C, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io& io) {
     return launch_cls_head(pl->bp("tokens"), pl->pp<float>("decoder.mlp_head.0.weight"),
@@ -951,6 +967,28 @@ int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const 
                                d_row_stats_out))
     return rc;
   return run_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_vit_block(const void* d_attn_out, const void* d_x0, long long rows, const void* d_w_out, const void* d_w1,
+                  const float* d_c1, const float* d_d1, const void* d_w2, const float* d_b2, void* d_x2,
+                  float* d_row_stats_out, void* stream) {
+  VitBlockOp op;
+  if (int rc = build_vit_block_op(op, d_attn_out, d_x0, rows, d_w_out, d_w1, d_c1, d_d1, d_w2, d_b2, d_x2,
+                                  d_row_stats_out))
+    return rc;
+  return launch_vit_block(op, device_sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+int hgr_vit_block_trace(const void* d_attn_out, const void* d_x0, long long rows, const void* d_w_out, const void* d_w1,
+                        const float* d_c1, const float* d_d1, const void* d_w2, const float* d_b2, void* d_x2,
+                        float* d_row_stats_out, long long* d_trace, int trace_tiles, void* stream) {
+  VitBlockOp op;
+  if (int rc = build_vit_block_op(op, d_attn_out, d_x0, rows, d_w_out, d_w1, d_c1, d_d1, d_w2, d_b2, d_x2,
+                                  d_row_stats_out))
+    return rc;
+  op.p.trace = d_trace;
+  op.p.trace_tiles = trace_tiles;
+  return launch_vit_block(op, device_sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 int hgr_conv1(const void* d_x, int x_dtype, int B, int S, const void* d_w, const float* d_shift, void* d_out,

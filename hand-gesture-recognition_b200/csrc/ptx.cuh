@@ -162,6 +162,12 @@ __device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, in
                : "memory");
 }
 
+// L2 prefetch of a contiguous global block (16-byte aligned, size a multiple of 16).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),

@@ -135,6 +135,25 @@ HGR_API int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w
                        const float* d_bias, int act, const void* d_res, void* d_y, int cout,
                        const float* d_row_stats_in, float* d_row_stats_out, void* stream);
 
+/* Second half of a ViT layer as one chained kernel (reference model/transformer.py:75 to_out, :93 residual,
+ * :29-42 FeedForward, :94 residual):
+ *     x1 = attn_out W_out^T + x0;   h = GELU(LayerNorm(x1) W1^T + b1);   x2 = h W2^T + b2 + x1
+ * attn_out, x0, x2 (rows, 256) bf16 (x2 may alias x0); W_out, W1', W2 (256, 256) bf16 with the LayerNorm folded
+ * into W1' = gamma (.) W1, d_c1[n] = sum_k W1'[n,k], d_d1[n] = sum_k beta[k] W1[n,k] + b1[n] (as in hgr_linear);
+ * d_row_stats_out (rows, 2) fp32, nullable: (mean, rstd) of every x2 row for the next layer's folded LayerNorm.
+ * x1 and h are rounded to bf16 exactly where the three separate hgr_linear launches store them. */
+HGR_API int hgr_vit_block(const void* d_attn_out, const void* d_x0, long long rows, const void* d_w_out,
+                          const void* d_w1, const float* d_c1, const float* d_d1, const void* d_w2,
+                          const float* d_b2, void* d_x2, float* d_row_stats_out, void* stream);
+
+/* Profiling twin of hgr_vit_block: CTA 0 also writes clock64 marks of its first `trace_tiles` tiles into
+ * d_trace[trace_tiles][16] (int64): 0 G0 done, 1 E0 done, 2 G1 done, 3 E1 done, 4 G2 done, 5 E2 done / store
+ * issued, 8..10 the MMA warp's view of "operand of G0/G1/G2 ready" (tools/vit_block_trace.py). */
+HGR_API int hgr_vit_block_trace(const void* d_attn_out, const void* d_x0, long long rows, const void* d_w_out,
+                                const void* d_w1, const float* d_c1, const float* d_d1, const void* d_w2,
+                                const float* d_b2, void* d_x2, float* d_row_stats_out, long long* d_trace,
+                                int trace_tiles, void* stream);
+
 /* encoder.conv1: NCHW (fp32|bf16) -> NHWC bf16 (B, S/2, S/2, 64).
  * d_w bf16 [64][32] (k = (kh*3+kw)*3+c, BN scale folded, zero padded). */
 HGR_API int hgr_conv1(const void* d_x, int x_dtype, int B, int S, const void* d_w, const float* d_shift, void* d_out,

@@ -189,6 +189,60 @@ def test_linear_with_folded_layernorm(lib, rows, cout, act):
     del packing
 
 
+@pytest.mark.parametrize("rows", [1160, 128 * 148 * 2 + 77, 77])
+@pytest.mark.parametrize("inplace", [False, True], ids=["out", "inplace"])
+def test_vit_block(lib, rows, inplace):
+    """to_out + residual -> LayerNorm -> Linear -> GELU -> Linear -> residual (reference model/transformer.py:75, 93,
+    29-42, 94) as one chained kernel, against the fp32 operators and against the three separate hgr_linear launches
+    it replaces (same rounding points, so the two CUDA paths agree to bf16 rounding of the last layer)."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows)
+    a = bf16_round(torch.randn(rows, 256, generator=g))
+    x0 = bf16_round(torch.randn(rows, 256, generator=g) * 2 + 0.3)
+    wo = bf16_round(torch.randn(256, 256, generator=g) / 16)
+    gamma, beta = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    w1 = torch.randn(256, 256, generator=g) / 16
+    b1 = torch.randn(256, generator=g) * 0.2
+    w2 = bf16_round(torch.randn(256, 256, generator=g) / 16)
+    b2 = torch.randn(256, generator=g) * 0.2
+    w1p = (w1 * gamma[None, :]).to(torch.bfloat16)
+    c1, d1 = w1p.float().sum(1), w1 @ beta + b1
+    ad, x0d, wod, w2d = (t.to(dev, torch.bfloat16) for t in (a, x0, wo, w2))
+    w1d, c1d, d1d, b2d = w1p.to(dev), c1.to(dev), d1.to(dev), b2.to(dev)
+    # fused
+    xin = x0d.clone()
+    x2 = xin if inplace else torch.full((rows, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    stats = torch.full((rows, 2), 7.0, dtype=torch.float32, device=dev)
+    _chk(lib.hgr_vit_block(ad.data_ptr(), xin.data_ptr(), rows, wod.data_ptr(), w1d.data_ptr(), c1d.data_ptr(),
+                           d1d.data_ptr(), w2d.data_ptr(), b2d.data_ptr(), x2.data_ptr(), stats.data_ptr(), _stream()),
+         "hgr_vit_block")
+    torch.cuda.synchronize()
+    # the three separate launches
+    x1 = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
+    h = torch.empty_like(x1)
+    y = torch.empty_like(x1)
+    st1 = torch.empty(rows, 2, dtype=torch.float32, device=dev)
+    st2 = torch.empty_like(st1)
+    _chk(lib.hgr_linear(ad.data_ptr(), rows, 256, wod.data_ptr(), None, None, 0, x0d.data_ptr(), x1.data_ptr(), 256,
+                        None, st1.data_ptr(), _stream()), "to_out")
+    _chk(lib.hgr_linear(x1.data_ptr(), rows, 256, w1d.data_ptr(), c1d.data_ptr(), d1d.data_ptr(), 2, None,
+                        h.data_ptr(), 256, st1.data_ptr(), None, _stream()), "net.1")
+    _chk(lib.hgr_linear(h.data_ptr(), rows, 256, w2d.data_ptr(), None, b2d.data_ptr(), 0, x1.data_ptr(), y.data_ptr(),
+                        256, None, st2.data_ptr(), _stream()), "net.4")
+    torch.cuda.synchronize()
+    # fp32 operators
+    x1_ref = F.linear(a, wo) + x0
+    h_ref = F.gelu(F.linear(F.layer_norm(x1_ref, (256,), gamma, beta, 1e-5), w1, b1))
+    x2_ref = F.linear(h_ref, w2, b2) + x1_ref
+    r, m = report(f"vit_block rows={rows} vs fp32 operators", x2, x2_ref)
+    assert r <= 6e-3 and m <= 3 * MAX_TOL
+    r3, m3 = report(f"vit_block rows={rows} vs three launches", x2, y.float().cpu())
+    assert r3 <= 2e-3
+    mean_ref, var_ref = x2_ref.mean(1), x2_ref.var(1, unbiased=False)
+    torch.testing.assert_close(stats[:, 0].cpu(), mean_ref, rtol=0, atol=4e-3)
+    torch.testing.assert_close(stats[:, 1].cpu(), torch.rsqrt(var_ref + 1e-5), rtol=4e-3, atol=0)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("size", [64, 192])
 def test_conv1(lib, dtype, size):
