@@ -16,8 +16,10 @@
 // 3 x 32 KiB ring of [256 x 64] weight k-blocks streamed from L2 | 2 KiB row-statistic exchange | barriers.
 // TMEM: 512 columns = two 256-column accumulators used alternately by the chain (GEMM n -> accumulator n & 1).
 //
-// Warps: 0 weight producer (TMA), 3 attn_out producer (TMA), 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue
-// (warp w touches TMEM lanes 32 (w % 4)..; warps 4-7 take columns 0-127, warps 8-11 columns 128-255).
+// Warps: 0 weight producer (TMA), 3 attn_out producer (TMA), 1 MMA issuer, 2 TMEM allocator, 4-19 epilogue
+// (warp w touches TMEM lanes 32 (w % 4)..; the four warps of a lane quarter split every 64-column chunk).
+// G1 / G2 start on k-block kb as soon as the epilogue has produced chunk kb of x1 / h, so the tensor core runs
+// underneath the epilogue; tools/vit_block_trace.py prints the resulting timeline.
 #include <cstdio>
 #include <cstring>
 
@@ -29,7 +31,7 @@ namespace hgr {
 
 namespace {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;  // 4 service warps + 16 epilogue warps
 constexpr int kChunkBytes = 128 * 64 * 2;      // one 64-column k-block of a 128-row bf16 tile
 constexpr int kActBytes = 4 * kChunkBytes;     // 128 x 256 bf16
 constexpr int kWBytes = 256 * 64 * 2;          // one k-block of a [256 x 256] weight matrix
@@ -86,7 +88,7 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(p_free, 1);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&chunk_done[i], 8);  // one arrival per epilogue warp
+    for (int i = 0; i < 4; ++i) mbar_init(&chunk_done[i], 16);  // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -133,9 +135,8 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = 0; i < my_tiles; ++i, tile += step) {
         if (i > 0) mbar_wait(p_free, (i - 1) & 1);
         mbar_expect_tx(a_full, kActBytes);
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d(smem + kOffP + kb * kChunkBytes, &tmA, a_full, kb * 64, tile * 128);
+        // ONE request for the whole tile: the map's third dimension walks the four 64-column k-blocks
+        tma_load_5d(smem + kOffP, &tmA, a_full, 0, tile * 128, 0, 0, 0);
         // Every CTA of the grid reaches its load phase at about the same time; without help the whole wave then
         // waits on HBM (128 KiB per CTA, measured ~5 000 cycles per tile).  The NEXT tile's attn_out and x0 rows
         // (two contiguous 64 KiB blocks) are pulled into L2 now, a whole tile period ahead.
@@ -192,22 +193,24 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue: 256 threads work through the four 64-column chunks of a tile together;
-    // thread = (row, 32-column half of the chunk), so every chunk is complete - and its k-block can be issued -
-    // after a quarter of the epilogue =================
+    // ================= epilogue: 512 threads (four warps per scheduler, so one warp's TMEM / MUFU / shared-memory
+    // latencies hide behind the others) work through the four 64-column chunks of a tile together; thread =
+    // (row, 16-column quarter of the chunk), so a chunk is complete - and its k-block can be issued - after a
+    // quarter of the epilogue =================
     const int ew = warp - 4;
-    const int q = ew & 3;
-    const int ch = ew >> 2;
+    const int q = ew & 3;     // TMEM lane quarter this warp may touch
+    const int cq = ew >> 2;   // 16-column quarter of every chunk
     const int row = q * 32 + lane;
     const int etid = threadIdx.x - 128;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 32;
-    // byte offset of this thread's four 16-byte pieces inside a chunk buffer: row * 128 + ((ch * 4 + v) ^ sw) * 16
-    const uint32_t row_off = row * 128;
-    float2* s_part = reinterpret_cast<float2*>(smem + kOffStats);
-    const float4* c1v = reinterpret_cast<const float4*>(p.c1 + ch * 32);
-    const float4* d1v = reinterpret_cast<const float4*>(p.d1 + ch * 32);
-    const float4* b2v = reinterpret_cast<const float4*>(p.b2 + ch * 32);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cq * 16;
+    // this thread's two 16-byte pieces inside a chunk buffer: row * 128 + ((cq * 2 + v) ^ sw) * 16
+    const uint32_t off0 = row * 128 + ((static_cast<uint32_t>(cq * 2) ^ sw) * 16);
+    const uint32_t off1 = row * 128 + ((static_cast<uint32_t>(cq * 2 + 1) ^ sw) * 16);
+    float2* s_buf = reinterpret_cast<float2*>(smem + kOffStats);  // [2][128]
+    const float4* c1v = reinterpret_cast<const float4*>(p.c1 + cq * 16);
+    const float4* d1v = reinterpret_cast<const float4*>(p.d1 + cq * 16);
+    const float4* b2v = reinterpret_cast<const float4*>(p.b2 + cq * 16);
     uint32_t n = 0;
     int tile = first;
     for (int i = 0; i < my_tiles; ++i, tile += step) {
@@ -215,96 +218,112 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = grow < p.rows;
 
       // ---------------- E0: x1 = acc + x0 -> Q, row statistics of x1 ----------------
-      // x0 of chunk j: 32 columns = 4 x 16 bytes at row * 512 + j * 128 + ch * 64; two chunks are kept in flight
-      const uint4* res_row = valid ? reinterpret_cast<const uint4*>(p.x0 + grow * 256 + ch * 32) : nullptr;
-      uint4 ra[4], rb[4];
+      // x0 comes in row-coalesced (a warp reads one 512-byte token row per request; a thread reading its own row
+      // costs one 32-byte sector per request and stalled E0 for ~2 300 cycles) and is handed to the row owners
+      // through Q, in the chunk layout, where x1 then replaces it in place.
+      uint4 xs[8];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        ra[v] = res_row ? __ldg(res_row + v) : make_uint4(0, 0, 0, 0);
-        rb[v] = res_row ? __ldg(res_row + 8 + v) : make_uint4(0, 0, 0, 0);
+      for (int it = 0; it < 8; ++it) {
+        const long long gr = (long long)tile * 128 + it * 16 + ew;
+        xs[it] = gr < p.rows ? __ldg(reinterpret_cast<const uint4*>(p.x0 + gr * 256) + lane) : make_uint4(0, 0, 0, 0);
       }
       if (etid == 0) trace_mark(p, i, 6);  // epilogue is back at the top of the chain
       mbar_wait(&acc_full[n & 1], (n >> 1) & 1);
       tc_fence_after();
       if (etid == 0) trace_mark(p, i, 0);  // G0 done
-      // the TMA store of the previous tile must have finished reading Q before x1 goes there
+      // the TMA store of the previous tile must have finished reading Q
       if (etid == 0) tma_store_wait_read<0>();
-      bar_sync(1, 256);
+      bar_sync(1, 512);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 16 + ew;
+        *reinterpret_cast<uint4*>(smem + kOffQ + (lane >> 3) * kChunkBytes + r * 128 +
+                                  ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(r & 7)) * 16)) = xs[it];
+      }
+      bar_sync(1, 512);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint4 rcur[4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) rcur[v] = (j & 1) ? rb[v] : ra[v];
-        if (j < 2) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint4 nx = res_row ? __ldg(res_row + (j + 2) * 8 + v) : make_uint4(0, 0, 0, 0);
-            if (j & 1) rb[v] = nx;
-            else ra[v] = nx;
-          }
-        }
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_lane + (n & 1) * 256 + j * 64, acc);
+        uint8_t* buf = smem + kOffQ + j * kChunkBytes;
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        uint4 x0v[2];
+        x0v[0] = *reinterpret_cast<const uint4*>(buf + off0);
+        x0v[1] = *reinterpret_cast<const uint4*>(buf + off1);
         tmem_ld_wait();
-        uint32_t packed[16];
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rcur);
+        uint32_t packed[8];
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(x0v);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
+        for (int e = 0; e < 16; e += 2) {
           const float v0 = __uint_as_float(acc[e]) + bf16_lo(rw[e >> 1]);
           const float v1 = __uint_as_float(acc[e + 1]) + bf16_hi(rw[e >> 1]);
           s1 += v0 + v1;
           s2 = fmaf(v0, v0, fmaf(v1, v1, s2));
           packed[e >> 1] = pack_bf16x2(v0, v1);
         }
-        uint8_t* buf = smem + kOffQ + j * kChunkBytes + row_off;
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(ch * 4 + v) ^ sw) * 16)) =
-              make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        *reinterpret_cast<uint4*>(buf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(buf + off1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&chunk_done[j]);
       }
-      s_part[ch * 128 + row] = make_float2(s1, s2);
       ++n;
       if (etid == 0) trace_mark(p, i, 1);  // E0 done (this thread)
-      bar_sync(1, 256);
+      // row totals over the four column quarters, always summed as (q0 + q2) + (q1 + q3); the 2 KiB exchange
+      // buffer is all the shared memory that is left, hence the three rounds
       float rstd, rmean;
       {
-        const float2 a = s_part[row], b = s_part[128 + row];
-        const float mean = (a.x + b.x) * (1.0f / 256);
-        const float var = fmaxf(fmaf(a.y + b.y, 1.0f / 256, -mean * mean), 0.0f);
-        rstd = rsqrtf(var + 1e-5f);
-        rmean = mean * rstd;
+        if (cq >= 2) s_buf[(cq - 2) * 128 + row] = make_float2(s1, s2);
+        bar_sync(1, 512);
+        if (cq < 2) {
+          const float2 o = s_buf[cq * 128 + row];
+          s1 += o.x;
+          s2 += o.y;
+          if (cq == 1) s_buf[128 + row] = make_float2(s1, s2);
+        }
+        bar_sync(1, 512);
+        if (cq == 0) {
+          const float2 o = s_buf[128 + row];
+          const float mean = (s1 + o.x) * (1.0f / 256);
+          const float var = fmaxf(fmaf(s2 + o.y, 1.0f / 256, -mean * mean), 0.0f);
+          const float rs = rsqrtf(var + 1e-5f);
+          s_buf[row] = make_float2(rs, mean * rs);
+        }
+        bar_sync(1, 512);
+        const float2 st = s_buf[row];
+        rstd = st.x;
+        rmean = st.y;
       }
 
       // ---------------- E1: h = GELU(rstd * acc - rstd * mean * c + d) -> P ----------------
       mbar_wait(&acc_full[n & 1], (n >> 1) & 1);
       tc_fence_after();
       if (etid == 0) trace_mark(p, i, 2);  // G1 done
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_lane + (n & 1) * 256 + j * 64, acc);
-        tmem_ld_wait();
-        uint32_t packed[16];
+        uint8_t* buf = smem + kOffP + j * kChunkBytes;
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        float4 sc[4], sh[4];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 sc = __ldg(c1v + j * 16 + (e >> 2)), sh = __ldg(d1v + j * 16 + (e >> 2));
-          const float v0 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[e]), rstd, fmaf(-rmean, sc.x, sh.x)));
-          const float v1 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[e + 1]), rstd, fmaf(-rmean, sc.y, sh.y)));
-          const float v2 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[e + 2]), rstd, fmaf(-rmean, sc.z, sh.z)));
-          const float v3 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[e + 3]), rstd, fmaf(-rmean, sc.w, sh.w)));
-          packed[e >> 1] = pack_bf16x2(v0, v1);
-          packed[(e >> 1) + 1] = pack_bf16x2(v2, v3);
+        for (int e = 0; e < 4; ++e) {
+          sc[e] = __ldg(c1v + j * 16 + e);
+          sh[e] = __ldg(d1v + j * 16 + e);
         }
-        uint8_t* buf = smem + kOffP + j * kChunkBytes + row_off;
+        tmem_ld_wait();
+        uint32_t packed[8];
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(ch * 4 + v) ^ sw) * 16)) =
-              make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[4 * e]), rstd, fmaf(-rmean, sc[e].x, sh[e].x)));
+          const float v1 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[4 * e + 1]), rstd, fmaf(-rmean, sc[e].y, sh[e].y)));
+          const float v2 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[4 * e + 2]), rstd, fmaf(-rmean, sc[e].z, sh[e].z)));
+          const float v3 = apply_act<ACT_GELU>(fmaf(__uint_as_float(acc[4 * e + 3]), rstd, fmaf(-rmean, sc[e].w, sh[e].w)));
+          packed[2 * e] = pack_bf16x2(v0, v1);
+          packed[2 * e + 1] = pack_bf16x2(v2, v3);
+        }
+        *reinterpret_cast<uint4*>(buf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(buf + off1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -319,51 +338,58 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (etid == 0) trace_mark(p, i, 4);  // G2 done
       s1 = 0.f;
       s2 = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        uint8_t* buf = smem + kOffQ + j * kChunkBytes + row_off;
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(t_lane + (n & 1) * 256 + j * 64, acc);
-        uint4 x1[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          x1[v] = *reinterpret_cast<const uint4*>(buf + ((static_cast<uint32_t>(ch * 4 + v) ^ sw) * 16));
+      for (int j = 0; j < 4; ++j) {
+        uint8_t* buf = smem + kOffQ + j * kChunkBytes;
+        uint32_t acc[16];
+        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        uint4 x1[2];
+        x1[0] = *reinterpret_cast<const uint4*>(buf + off0);
+        x1[1] = *reinterpret_cast<const uint4*>(buf + off1);
+        float4 bb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bb[e] = __ldg(b2v + j * 16 + e);
         tmem_ld_wait();
-        uint32_t packed[16];
+        uint32_t packed[8];
         const uint32_t* rw = reinterpret_cast<const uint32_t*>(x1);
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 bb = __ldg(b2v + j * 16 + (e >> 2));
-          const float v0 = (__uint_as_float(acc[e]) + bb.x) + bf16_lo(rw[e >> 1]);
-          const float v1 = (__uint_as_float(acc[e + 1]) + bb.y) + bf16_hi(rw[e >> 1]);
-          const float v2 = (__uint_as_float(acc[e + 2]) + bb.z) + bf16_lo(rw[(e >> 1) + 1]);
-          const float v3 = (__uint_as_float(acc[e + 3]) + bb.w) + bf16_hi(rw[(e >> 1) + 1]);
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = (__uint_as_float(acc[4 * e]) + bb[e].x) + bf16_lo(rw[2 * e]);
+          const float v1 = (__uint_as_float(acc[4 * e + 1]) + bb[e].y) + bf16_hi(rw[2 * e]);
+          const float v2 = (__uint_as_float(acc[4 * e + 2]) + bb[e].z) + bf16_lo(rw[2 * e + 1]);
+          const float v3 = (__uint_as_float(acc[4 * e + 3]) + bb[e].w) + bf16_hi(rw[2 * e + 1]);
           s1 += (v0 + v1) + (v2 + v3);
           s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
-          packed[e >> 1] = pack_bf16x2(v0, v1);
-          packed[(e >> 1) + 1] = pack_bf16x2(v2, v3);
+          packed[2 * e] = pack_bf16x2(v0, v1);
+          packed[2 * e + 1] = pack_bf16x2(v2, v3);
         }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          *reinterpret_cast<uint4*>(buf + ((static_cast<uint32_t>(ch * 4 + v) ^ sw) * 16)) =
-              make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        *reinterpret_cast<uint4*>(buf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(buf + off1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
-      s_part[ch * 128 + row] = make_float2(s1, s2);
+      if (cq >= 2) s_buf[(cq - 2) * 128 + row] = make_float2(s1, s2);
       fence_proxy_async_smem();
       tc_fence_before();
       ++n;
-      bar_sync(1, 256);
+      bar_sync(1, 512);
       if (etid == 0) {
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_store_4d(&tmO, smem + kOffQ + kb * kChunkBytes, kb * 64, tile * 128, 0, 0);
+        tma_store_4d(&tmO, smem + kOffQ, 0, tile * 128, 0, 0);  // all four chunk buffers in one request
         tma_store_commit();
         trace_mark(p, i, 5);  // E2 done, store issued
       }
-      if (ch == 0 && valid && p.stats_out != nullptr) {
-        const float2 a = s_part[row], b = s_part[128 + row];
-        const float mean = (a.x + b.x) * (1.0f / 256);
-        const float var = fmaxf(fmaf(a.y + b.y, 1.0f / 256, -mean * mean), 0.0f);
-        p.stats_out[grow] = make_float2(mean, rsqrtf(var + 1e-5f));
+      if (p.stats_out != nullptr) {
+        if (cq < 2) {
+          const float2 o = s_buf[cq * 128 + row];
+          s1 += o.x;
+          s2 += o.y;
+          if (cq == 1) s_buf[128 + row] = make_float2(s1, s2);
+        }
+        bar_sync(1, 512);
+        if (cq == 0 && valid) {
+          const float2 o = s_buf[128 + row];
+          const float mean = (s1 + o.x) * (1.0f / 256);
+          const float var = fmaxf(fmaf(s2 + o.y, 1.0f / 256, -mean * mean), 0.0f);
+          p.stats_out[grow] = make_float2(mean, rsqrtf(var + 1e-5f));
+        }
       }
     }
     if (etid == 0) tma_store_wait_all();
@@ -394,11 +420,12 @@ int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, lon
                        const void* w1, const float* c1, const float* d1, const void* w2, const float* b2, void* x2,
                        float* stats_out) {
   memset(&op, 0, sizeof(op));
+  // (rows, 256) seen as (64 columns, rows, 4 k-blocks): one box = the four [128 x 64] SWIZZLE_128B chunk buffers
   {
-    const uint64_t dims[2] = {256, (uint64_t)rows};
-    const uint64_t strides[1] = {512};
-    const uint32_t box[2] = {64, 128};
-    if (int r = make_tensor_map_bf16(&op.a, attn_out, 2, dims, strides, box)) return r;
+    const uint64_t dims[5] = {64, (uint64_t)rows, 4, 1, 1};
+    const uint64_t strides[4] = {512, 128, 512 * (uint64_t)rows, 512 * (uint64_t)rows};
+    const uint32_t box[5] = {64, 128, 4, 1, 1};
+    if (int r = make_tensor_map_bf16(&op.a, attn_out, 5, dims, strides, box)) return r;
   }
   const void* ws[3] = {w_out, w1, w2};
   CUtensorMap* wm[3] = {&op.w0, &op.w1, &op.w2};
@@ -409,9 +436,9 @@ int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, lon
     if (int r = make_tensor_map_bf16(wm[g], ws[g], 2, dims, strides, box)) return r;
   }
   {
-    const uint64_t dims[4] = {256, (uint64_t)rows, 1, 1};
-    const uint64_t strides[3] = {512, 512 * (uint64_t)rows, 512 * (uint64_t)rows};
-    const uint32_t box[4] = {64, 128, 1, 1};
+    const uint64_t dims[4] = {64, (uint64_t)rows, 4, 1};
+    const uint64_t strides[3] = {512, 128, 512 * (uint64_t)rows};
+    const uint32_t box[4] = {64, 128, 4, 1};
     if (int r = make_tensor_map_bf16(&op.o, x2, 4, dims, strides, box)) return r;
   }
   op.p.rows = rows;
