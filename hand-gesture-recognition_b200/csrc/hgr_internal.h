@@ -125,7 +125,7 @@ struct VitBlockParams {
 };
 
 struct VitBlockOp {
-  CUtensorMap a, w0, w1, w2, o;
+  CUtensorMap a, w0, w1, w2, x, o;
   VitBlockParams p;
   double flops, bytes;
 };

@@ -12,14 +12,23 @@
 // the ones of the separate launches (x1 and h are rounded to bf16 exactly where they used to be stored), so the
 // results are the same numbers.
 //
-// Shared memory (one CTA per SM):  P 64 KiB (attn_out tile, later h) | Q 64 KiB (x1, later the x2 staging) |
-// 3 x 32 KiB ring of [256 x 64] weight k-blocks streamed from L2 | 2 KiB row-statistic exchange | barriers.
-// TMEM: 512 columns = two 256-column accumulators used alternately by the chain (GEMM n -> accumulator n & 1).
+// Shared memory (one CTA per SM):  P 64 KiB (attn_out tile, later h) | Q 64 KiB (x0, replaced in place by x1, replaced
+// in place by x2 = the store staging) | 3 x 32 KiB ring of [256 x 64] weight k-blocks streamed from L2 | 2 KiB
+// row-statistic exchange | barriers.  TMEM: 512 columns = two 256-column accumulators used alternately by the chain
+// (GEMM n -> accumulator n & 1).
 //
-// Warps: 0 weight producer (TMA), 3 attn_out producer (TMA), 1 MMA issuer, 2 TMEM allocator, 4-19 epilogue
-// (warp w touches TMEM lanes 32 (w % 4)..; the four warps of a lane quarter split every 64-column chunk).
-// G1 / G2 start on k-block kb as soon as the epilogue has produced chunk kb of x1 / h, so the tensor core runs
-// underneath the epilogue; tools/vit_block_trace.py prints the resulting timeline.
+// Warps (640 threads): 0 weight producer (TMA), 3 activation traffic (attn_out / x0 loads, x2 stores, L2 prefetch of
+// the next tile), 1 MMA issuer, 2 TMEM allocator, 4-19 epilogue (warp w touches TMEM lanes 32 (w % 4)..; the four
+// warps of a lane quarter split every 64-column chunk).
+//
+// What the timeline (tools/vit_block_trace.py) showed and the structure answers:
+//  * the chain is EPILOGUE-bound (the three GEMMs need 3 x 2 350 cycles per tile, the epilogues ~13 000), so G1 / G2
+//    start on k-block kb as soon as the epilogue has produced the 64-column chunk kb of x1 / h and run underneath
+//    E0 / E1; G0 of the next tile runs underneath E2;
+//  * sixteen epilogue warps (four per scheduler) instead of eight: 0.121 -> 0.094 ms per layer at batch 1024;
+//  * all CTAs reach their load phase together, so the next tile's inputs are prefetched into L2 one tile ahead;
+//  * x0 read by the row owners through the LSU cost one 32-byte sector per request (~2 300 stalled cycles per
+//    tile): it comes in by TMA, straight into Q, chunk by chunk as the previous tile's store releases Q.
 #include <cstdio>
 #include <cstring>
 
@@ -41,7 +50,7 @@ constexpr int kOffQ = kActBytes;
 constexpr int kOffW = 2 * kActBytes;
 constexpr int kOffStats = kOffW + kWStages * kWBytes;  // float2 [2 halves][128 rows]
 constexpr int kOffBars = kOffStats + 2 * 128 * 8;
-constexpr int kNumBars = 2 * kWStages + 8;
+constexpr int kNumBars = 2 * kWStages + 16;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 227 * 1024, "vit_block shared-memory plan exceeds one CTA");
@@ -54,7 +63,8 @@ __device__ __forceinline__ void trace_mark(const VitBlockParams& p, int tile_ite
 __global__ void __launch_bounds__(kThreads, 1)
 vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmO, const VitBlockParams p) {
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmO,
+                 const VitBlockParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,6 +76,8 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* p_free = bars + 2 * kWStages + 1;    // G2 has finished reading P
   uint64_t* acc_full = bars + 2 * kWStages + 2;  // [2]
   uint64_t* chunk_done = bars + 2 * kWStages + 4;  // [4] E0 / E1 wrote 64-column chunk kb of x1 / h (256 arrivals)
+  uint64_t* x_full = bars + 2 * kWStages + 8;      // [4] chunk j of x0 landed in Q (issued once the store of chunk j has read Q)
+  uint64_t* out_ready = bars + 2 * kWStages + 12;  // [4] E2 staged chunk j of x2 in Q (one arrival per epilogue warp)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -77,6 +89,7 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tensormap(&tmW0);
     prefetch_tensormap(&tmW1);
     prefetch_tensormap(&tmW2);
+    prefetch_tensormap(&tmX);
     prefetch_tensormap(&tmO);
   }
   if (warp == 1 && lane == 0) {
@@ -88,6 +101,10 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(p_free, 1);
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&out_ready[i], 16);
+    }
     for (int i = 0; i < 4; ++i) mbar_init(&chunk_done[i], 16);  // one arrival per epilogue warp
     fence_barrier_init();
   }
@@ -129,24 +146,57 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 3) {
-    // ================= attn_out producer: one 128 x 256 tile into P per tile =================
+    // ================= activation traffic: attn_out tile -> P, x0 tile -> Q, x2 tile Q -> global =================
+    // One thread owns every bulk copy of the activations.  Q is recycled chunk by chunk: E2 hands over chunk j of
+    // x2 as soon as it is staged, its store is issued at once, and as soon as that store has READ the chunk the
+    // same 16 KiB take chunk j of the next tile's x0 - so the store of a tile and the x0 load of the next one run
+    // underneath E2 instead of after it (as one 64 KiB store + load they cost ~4 700 cycles between two tiles).
     if (elect_one_sync()) {
       int tile = first;
-      for (int i = 0; i < my_tiles; ++i, tile += step) {
-        if (i > 0) mbar_wait(p_free, (i - 1) & 1);
+      if (my_tiles > 0) {
         mbar_expect_tx(a_full, kActBytes);
-        // ONE request for the whole tile: the map's third dimension walks the four 64-column k-blocks
         tma_load_5d(smem + kOffP, &tmA, a_full, 0, tile * 128, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mbar_expect_tx(&x_full[j], kChunkBytes);
+          tma_load_5d(smem + kOffQ + j * kChunkBytes, &tmX, &x_full[j], 0, tile * 128, j, 0, 0);
+        }
+      }
+      for (int i = 0; i < my_tiles; ++i, tile += step) {
+        const bool more = i + 1 < my_tiles;
         // Every CTA of the grid reaches its load phase at about the same time; without help the whole wave then
         // waits on HBM (128 KiB per CTA, measured ~5 000 cycles per tile).  The NEXT tile's attn_out and x0 rows
-        // (two contiguous 64 KiB blocks) are pulled into L2 now, a whole tile period ahead.
-        if (i + 1 < my_tiles) {
+        // (two contiguous 64 KiB blocks) are pulled into L2 a whole tile period ahead.
+        if (more) {
           const long long r0 = (long long)(tile + step) * 128;
           const long long nrows = p.rows - r0 < 128 ? p.rows - r0 : 128;
           bulk_prefetch_l2(p.a0 + r0 * 256, (uint32_t)(nrows * 512));
           bulk_prefetch_l2(p.x0 + r0 * 256, (uint32_t)(nrows * 512));
         }
+        mbar_wait(p_free, i & 1);  // G2 of this tile has read h: P may take the next attn_out tile
+        if (more) {
+          mbar_expect_tx(a_full, kActBytes);
+          tma_load_5d(smem + kOffP, &tmA, a_full, 0, (tile + step) * 128, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mbar_wait(&out_ready[j], i & 1);  // chunk j of x2 is staged in Q
+          tma_store_4d(&tmO, smem + kOffQ + j * kChunkBytes, 0, tile * 128, j, 0);
+          tma_store_commit();
+          if (more && j > 0) {
+            tma_store_wait_read<1>();  // the store of chunk j - 1 has read its 16 KiB
+            mbar_expect_tx(&x_full[j - 1], kChunkBytes);
+            tma_load_5d(smem + kOffQ + (j - 1) * kChunkBytes, &tmX, &x_full[j - 1], 0, (tile + step) * 128, j - 1, 0, 0);
+          }
+        }
+        trace_mark(p, i, 5);  // last store issued
+        if (more) {
+          tma_store_wait_read<0>();
+          mbar_expect_tx(&x_full[3], kChunkBytes);
+          tma_load_5d(smem + kOffQ + 3 * kChunkBytes, &tmX, &x_full[3], 0, (tile + step) * 128, 3, 0, 0);
+        }
       }
+      tma_store_wait_all();
     }
   } else if (warp == 1) {
     // ================= MMA issuer: G0, G1, G2 of every tile =================
@@ -218,39 +268,27 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool valid = grow < p.rows;
 
       // ---------------- E0: x1 = acc + x0 -> Q, row statistics of x1 ----------------
-      // x0 comes in row-coalesced (a warp reads one 512-byte token row per request; a thread reading its own row
-      // costs one 32-byte sector per request and stalled E0 for ~2 300 cycles) and is handed to the row owners
-      // through Q, in the chunk layout, where x1 then replaces it in place.
-      uint4 xs[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const long long gr = (long long)tile * 128 + it * 16 + ew;
-        xs[it] = gr < p.rows ? __ldg(reinterpret_cast<const uint4*>(p.x0 + gr * 256) + lane) : make_uint4(0, 0, 0, 0);
-      }
+      // x0 is already in Q in the chunk layout (TMA, warp 3); x1 replaces it in place
       if (etid == 0) trace_mark(p, i, 6);  // epilogue is back at the top of the chain
       mbar_wait(&acc_full[n & 1], (n >> 1) & 1);
       tc_fence_after();
       if (etid == 0) trace_mark(p, i, 0);  // G0 done
-      // the TMA store of the previous tile must have finished reading Q
-      if (etid == 0) tma_store_wait_read<0>();
-      bar_sync(1, 512);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 16 + ew;
-        *reinterpret_cast<uint4*>(smem + kOffQ + (lane >> 3) * kChunkBytes + r * 128 +
-                                  ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(r & 7)) * 16)) = xs[it];
-      }
-      bar_sync(1, 512);
+      bar_sync(1, 512);  // every thread is done with the previous tile's statistics exchange
       float s1 = 0.f, s2 = 0.f;
+      // the accumulator columns of chunk j + 1 are already on their way out of TMEM while chunk j is computed
+      uint32_t accb[2][16];
+      tmem_ld_32x32b_x16(t_lane + (n & 1) * 256, accb[0]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint8_t* buf = smem + kOffQ + j * kChunkBytes;
-        uint32_t acc[16];
-        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        const uint32_t(&acc)[16] = accb[j & 1];
+        mbar_wait(&x_full[j], i & 1);  // chunk j of x0 is in Q (so the previous tile's store of it has read Q)
+        if (etid == 0 && j == 0) trace_mark(p, i, 7);
         uint4 x0v[2];
         x0v[0] = *reinterpret_cast<const uint4*>(buf + off0);
         x0v[1] = *reinterpret_cast<const uint4*>(buf + off1);
         tmem_ld_wait();
+        if (j < 3) tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + (j + 1) * 64, accb[(j + 1) & 1]);
         uint32_t packed[8];
         const uint32_t* rw = reinterpret_cast<const uint32_t*>(x0v);
 #pragma unroll
@@ -300,11 +338,11 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&acc_full[n & 1], (n >> 1) & 1);
       tc_fence_after();
       if (etid == 0) trace_mark(p, i, 2);  // G1 done
+      tmem_ld_32x32b_x16(t_lane + (n & 1) * 256, accb[0]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint8_t* buf = smem + kOffP + j * kChunkBytes;
-        uint32_t acc[16];
-        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        const uint32_t(&acc)[16] = accb[j & 1];
         float4 sc[4], sh[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -312,6 +350,7 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sh[e] = __ldg(d1v + j * 16 + e);
         }
         tmem_ld_wait();
+        if (j < 3) tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + (j + 1) * 64, accb[(j + 1) & 1]);
         uint32_t packed[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -338,11 +377,11 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (etid == 0) trace_mark(p, i, 4);  // G2 done
       s1 = 0.f;
       s2 = 0.f;
+      tmem_ld_32x32b_x16(t_lane + (n & 1) * 256, accb[0]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint8_t* buf = smem + kOffQ + j * kChunkBytes;
-        uint32_t acc[16];
-        tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + j * 64, acc);
+        const uint32_t(&acc)[16] = accb[j & 1];
         uint4 x1[2];
         x1[0] = *reinterpret_cast<const uint4*>(buf + off0);
         x1[1] = *reinterpret_cast<const uint4*>(buf + off1);
@@ -350,6 +389,7 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 4; ++e) bb[e] = __ldg(b2v + j * 16 + e);
         tmem_ld_wait();
+        if (j < 3) tmem_ld_32x32b_x16(t_lane + (n & 1) * 256 + (j + 1) * 64, accb[(j + 1) & 1]);
         uint32_t packed[8];
         const uint32_t* rw = reinterpret_cast<const uint32_t*>(x1);
 #pragma unroll
@@ -365,18 +405,15 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         *reinterpret_cast<uint4*>(buf + off0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         *reinterpret_cast<uint4*>(buf + off1) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&out_ready[j]);  // warp 3 stores the chunk once all sixteen warps are here
       }
-      if (cq >= 2) s_buf[(cq - 2) * 128 + row] = make_float2(s1, s2);
-      fence_proxy_async_smem();
-      tc_fence_before();
       ++n;
-      bar_sync(1, 512);
-      if (etid == 0) {
-        tma_store_4d(&tmO, smem + kOffQ, 0, tile * 128, 0, 0);  // all four chunk buffers in one request
-        tma_store_commit();
-        trace_mark(p, i, 5);  // E2 done, store issued
-      }
+      if (cq >= 2) s_buf[(cq - 2) * 128 + row] = make_float2(s1, s2);
       if (p.stats_out != nullptr) {
+        bar_sync(1, 512);
         if (cq < 2) {
           const float2 o = s_buf[cq * 128 + row];
           s1 += o.x;
@@ -392,7 +429,6 @@ vit_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (etid == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -412,7 +448,7 @@ int launch_vit_block(const VitBlockOp& op, int num_sms, cudaStream_t stream) {
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
   if (grid <= 0) return 0;
   HGR_CHECK_CUDA(launch_pdl(vit_block_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, op.a, op.w0, op.w1,
-                            op.w2, op.o, op.p));
+                            op.w2, op.x, op.o, op.p));
   return 0;
 }
 
@@ -427,6 +463,12 @@ int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, lon
     const uint32_t box[5] = {64, 128, 4, 1, 1};
     if (int r = make_tensor_map_bf16(&op.a, attn_out, 5, dims, strides, box)) return r;
   }
+  {
+    const uint64_t dims[5] = {64, (uint64_t)rows, 4, 1, 1};
+    const uint64_t strides[4] = {512, 128, 512 * (uint64_t)rows, 512 * (uint64_t)rows};
+    const uint32_t box[5] = {64, 128, 1, 1, 1};  // one chunk per request (Q is recycled chunk by chunk)
+    if (int r = make_tensor_map_bf16(&op.x, x0, 5, dims, strides, box)) return r;
+  }
   const void* ws[3] = {w_out, w1, w2};
   CUtensorMap* wm[3] = {&op.w0, &op.w1, &op.w2};
   for (int g = 0; g < 3; ++g) {
@@ -438,7 +480,7 @@ int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, lon
   {
     const uint64_t dims[4] = {64, (uint64_t)rows, 4, 1};
     const uint64_t strides[3] = {512, 128, 512 * (uint64_t)rows};
-    const uint32_t box[4] = {64, 128, 4, 1};
+    const uint32_t box[4] = {64, 128, 1, 1};
     if (int r = make_tensor_map_bf16(&op.o, x2, 4, dims, strides, box)) return r;
   }
   op.p.rows = rows;

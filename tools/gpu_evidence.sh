@@ -2,7 +2,7 @@
 # Round evidence in one gpurun call: GPU parity suites, the default bench line (with cpu_baseline),
 # the ncu launch list of one short bench run, and one `ncu --set full` capture of every launch of one
 # forward pass (exported to CSV on the box; the .ncu-rep of the whole step is too large to bring back).
-# Usage: tools/gpu_evidence.sh <tag>
+# Usage: tools/gpu_evidence.sh <tag> [launches per forward]
 tag=${1:-evidence}
 out=gpurun_out/$tag
 mkdir -p $out
@@ -15,12 +15,13 @@ cat $out/bench.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err
 echo "reference arm exit $?" | tee -a $out/summary.txt
 SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-OURS="regex:gemm_kernel|halo_kernel|conv1_kernel|attention_kernel|pose_head_kernel|cls_head_kernel|fill_cls_kernel"
+OURS="regex:gemm_kernel|halo_kernel|vit_block_kernel|conv1_kernel|attention_kernel|pose_head_kernel|cls_head_kernel|fill_cls_kernel"
+NL=${2:-38}  # launches per forward (46 with HGR_VIT_FUSED=0)
 timeout 600 $SHORT > $out/plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s 138 -c 92 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s $((3 * NL)) -c $((2 * NL)) --csv \
     --log-file $out/launches.csv $SHORT > $out/ncu_list.log 2>&1
 echo "ncu list exit $?" | tee -a $out/summary.txt
-timeout 1500 ncu --set full --clock-control none -k "$OURS" -s 138 -c 46 -o $out/step_full $SHORT > $out/ncu_full.log 2>&1
+timeout 1500 ncu --set full --clock-control none -k "$OURS" -s $((3 * NL)) -c $NL -o $out/step_full $SHORT > $out/ncu_full.log 2>&1
 echo "ncu full exit $?" | tee -a $out/summary.txt
 ncu -i $out/step_full.ncu-rep --page raw --csv > $out/step_full_raw.csv 2>> $out/ncu_full.log
 ls -la $out

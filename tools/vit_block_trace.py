@@ -27,9 +27,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = trace.cpu()
 base = int(t[0, 8])
-names = {6: "epi at top", 11: "w0", 12: "w1", 13: "w2", 14: "w3", 8: "G0 operand ready", 0: "G0 done", 1: "E0 done", 9: "G1 start", 2: "G1 done", 3: "E1 done", 10: "G2 start",
+names = {6: "epi at top", 11: "w0", 12: "w1", 13: "w2", 14: "w3", 8: "G0 operand ready", 0: "G0 done", 7: "x0 landed", 1: "E0 done", 9: "G1 start", 2: "G1 done", 3: "E1 done", 10: "G2 start",
          4: "G2 done", 5: "E2 done"}
-order = [6, 8, 11, 12, 13, 14, 0, 1, 9, 2, 3, 10, 4, 5]
+order = [6, 8, 14, 0, 7, 1, 9, 2, 3, 10, 4, 5]
 for i in range(nt):
     prev = None
     parts = []
