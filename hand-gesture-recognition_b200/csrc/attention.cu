@@ -333,8 +333,8 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 // halves the ldmatrix traffic that bounds the strip-in-registers kernel above (ncu: l1tex 74 %, tensor 35 %), and
 // only one 32-key block of scores is live at a time, so the rescaled running output (flash-attention recurrence)
 // costs fewer registers than the 16 x T strip did.
-template <int NKB>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+template <int NKB, int MT>
+__global__ void __launch_bounds__(kWarps * 32, (MT == 2 || NKB > 5) ? 3 : 5)
 attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
                         float scale_log2e, int reverse) {
   constexpr int Tp = NKB * kKeyBlock;
@@ -374,22 +374,22 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   }
   __syncthreads();
 
-  const int mpairs = (T + 31) >> 5;
+  const int mgroups = (T + 16 * MT - 1) / (16 * MT);
   const uint32_t q_lane = smem_u32(sq) + ((lane & 15) * kPitch + (lane >> 4) * 8) * 2;
   const uint32_t k_lane = smem_u32(sk) + ((lane & 7) * kPitch + (lane >> 3) * 8) * 2;
   const uint32_t v_lane = smem_u32(sv) + ((((lane >> 3) & 1) * 8 + (lane & 7)) * kPitch + (lane >> 4) * 8) * 2;
 
-  for (int mp = warp; mp < mpairs; mp += kWarps) {
-    uint32_t qa[2][2][4];
+  for (int mp = warp; mp < mgroups; mp += kWarps) {
+    uint32_t qa[MT][2][4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      ldmatrix_x4(qa[u][0], q_lane + (mp * 32 + u * 16) * kPitch * 2);
-      ldmatrix_x4(qa[u][1], q_lane + (mp * 32 + u * 16) * kPitch * 2 + 32);
+    for (int u = 0; u < MT; ++u) {
+      ldmatrix_x4(qa[u][0], q_lane + (mp * 16 * MT + u * 16) * kPitch * 2);
+      ldmatrix_x4(qa[u][1], q_lane + (mp * 16 * MT + u * 16) * kPitch * 2 + 32);
     }
-    float o[2][4][4];
-    float m[2][2], l[2][2];  // running max (already in exp2 units) and partial row sums: [tile][row g / g + 8]
+    float o[MT][4][4];
+    float m[MT][2], l[MT][2];  // running max (already in exp2 units) and partial row sums: [tile][row g / g + 8]
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < MT; ++u) {
       m[u][0] = m[u][1] = -INFINITY;
       l[u][0] = l[u][1] = 0.f;
 #pragma unroll
@@ -398,13 +398,13 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 
 #pragma unroll
     for (int kb = 0; kb < NKB; ++kb) {
-      float s[2][4][4];
+      float s[MT][4][4];
       {
         uint32_t kf[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) ldmatrix_x4(kf[nt], k_lane + (kb * kKeyBlock + nt * 8) * kPitch * 2);
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < MT; ++u)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             s[u][nt][0] = s[u][nt][1] = s[u][nt][2] = s[u][nt][3] = 0.f;
@@ -413,7 +413,7 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
           }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < MT; ++u) {
         float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -460,7 +460,7 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
         ldmatrix_x4_trans(vb[0], vaddr);
         ldmatrix_x4_trans(vb[1], vaddr + 32);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < MT; ++u) {
           uint32_t pa[4];
           pa[0] = pack_bf16x2(s[u][2 * j][0], s[u][2 * j][1]);
           pa[1] = pack_bf16x2(s[u][2 * j][2], s[u][2 * j][3]);
@@ -475,9 +475,9 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < MT; ++u) {
       const float inv0 = 1.0f / quad_sum(l[u][0]), inv1 = 1.0f / quad_sum(l[u][1]);
-      const int row0 = mp * 32 + u * 16 + g, row1 = row0 + 8;
+      const int row0 = mp * 16 * MT + u * 16 + g, row1 = row0 + 8;
       __nv_bfloat16* orow0 = out + ((size_t)b * T + row0) * (kHeads * kHd) + h * kHd + 2 * t;
       __nv_bfloat16* orow1 = out + ((size_t)b * T + row1) * (kHeads * kHd) + h * kHd + 2 * t;
 #pragma unroll
@@ -506,16 +506,16 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   if (attn_probs == nullptr && attention_online_enabled()) {
     // no probabilities to return: online-softmax kernel, K/V fragments shared by two query tiles per warp
     const int nkb = Tp / kKeyBlock;
+    const bool one = attention_tiles_per_warp() == 1;  // 1: fewer registers, five CTAs per SM; 2: shared K/V fragments
     if (nkb == 5) {
-      HGR_CHECK_CUDA(launch_pdl(attention_kernel_online<5>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T,
-                                scale_log2e, reverse));
+      HGR_CHECK_CUDA(launch_pdl(one ? attention_kernel_online<5, 1> : attention_kernel_online<5, 2>, dim3(grid),
+                                dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
       return 0;
     }
     if (nkb == 9) {
-      HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel_online<9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-      HGR_CHECK_CUDA(launch_pdl(attention_kernel_online<9>, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T,
-                                scale_log2e, reverse));
+      auto kern = one ? attention_kernel_online<9, 1> : attention_kernel_online<9, 2>;
+      HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      HGR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
       return 0;
     }
   }

@@ -47,6 +47,14 @@ bool attention_online_enabled() {
   return on;
 }
 
+int attention_tiles_per_warp() {
+  static const int v = [] {
+    const char* e = getenv("HGR_ATTN_MT");
+    return (e && e[0] == '2') ? 2 : 1;  // measured at batch 1024, T = 145: 0.156 (1) vs 0.166 ms (2) per launch
+  }();
+  return v;
+}
+
 bool vit_fused_enabled() {
   static const bool on = env_flag("HGR_VIT_FUSED", true);
   return on;

@@ -37,6 +37,8 @@ bool zigzag_enabled();
 bool cluster_enabled();
 // HGR_ATTN_ONLINE=0 falls back to the strip-in-registers attention kernels when no probabilities are returned.
 bool attention_online_enabled();
+// HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
+int attention_tiles_per_warp();
 // HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.
 bool halo_pair_enabled();
 // HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
