@@ -333,8 +333,8 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 // halves the ldmatrix traffic that bounds the strip-in-registers kernel above (ncu: l1tex 74 %, tensor 35 %), and
 // only one 32-key block of scores is live at a time, so the rescaled running output (flash-attention recurrence)
 // costs fewer registers than the 16 x T strip did.
-template <int NKB, int MT>
-__global__ void __launch_bounds__(kWarps * 32, (MT == 2 || NKB > 5) ? 3 : 5)
+template <int NKB, int MT, int NW>
+__global__ void __launch_bounds__(NW * 32, NW > 5 ? (MT == 1 ? 3 : 1) : (MT == 2 ? 3 : 5))
 attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
                         float scale_log2e, int reverse) {
   constexpr int Tp = NKB * kKeyBlock;
@@ -354,11 +354,11 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   {
     constexpr int kTotal = 3 * Tp * 4;            // 16-byte chunks of Q, K and V
     constexpr int kBatch = 12;                    // requests in flight per thread
-    for (int i0 = 0; i0 < kTotal; i0 += kBatch * kWarps * 32) {
+    for (int i0 = 0; i0 < kTotal; i0 += kBatch * NW * 32) {
       uint4 v[kBatch];
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
-        const int i = i0 + tid + k * kWarps * 32;
+        const int i = i0 + tid + k * NW * 32;
         const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
         v[k] = make_uint4(0, 0, 0, 0);
         if (i < kTotal && row < T)
@@ -366,7 +366,7 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
       }
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
-        const int i = i0 + tid + k * kWarps * 32;
+        const int i = i0 + tid + k * NW * 32;
         const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
         if (i < kTotal) *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v[k];
       }
@@ -379,7 +379,7 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   const uint32_t k_lane = smem_u32(sk) + ((lane & 7) * kPitch + (lane >> 3) * 8) * 2;
   const uint32_t v_lane = smem_u32(sv) + ((((lane >> 3) & 1) * 8 + (lane & 7)) * kPitch + (lane >> 4) * 8) * 2;
 
-  for (int mp = warp; mp < mgroups; mp += kWarps) {
+  for (int mp = warp; mp < mgroups; mp += NW) {
     uint32_t qa[MT][2][4];
 #pragma unroll
     for (int u = 0; u < MT; ++u) {
@@ -508,14 +508,15 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
     const int nkb = Tp / kKeyBlock;
     const bool one = attention_tiles_per_warp() == 1;  // 1: fewer registers, five CTAs per SM; 2: shared K/V fragments
     if (nkb == 5) {
-      HGR_CHECK_CUDA(launch_pdl(one ? attention_kernel_online<5, 1> : attention_kernel_online<5, 2>, dim3(grid),
-                                dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
+      HGR_CHECK_CUDA(launch_pdl(one ? attention_kernel_online<5, 1, kWarps> : attention_kernel_online<5, 2, kWarps>,
+                                dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
       return 0;
     }
     if (nkb == 9) {
-      auto kern = one ? attention_kernel_online<9, 1> : attention_kernel_online<9, 2>;
+      // 257 tokens = 17 query tiles: nine warps walk them in two rounds (five warps need four)
+      auto kern = one ? attention_kernel_online<9, 1, 9> : attention_kernel_online<9, 2, 9>;
       HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      HGR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
+      HGR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(9 * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
       return 0;
     }
   }
