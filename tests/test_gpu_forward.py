@@ -195,6 +195,22 @@ def test_classifier_session_has_the_onnxruntime_contract():
     assert classifier.run(["heatmap_pred"], inp)[0].shape == (1, 21, 48, 48)
 
 
+def test_classifier_session_graph_replay_equals_plain_launches():
+    """The latency mode (CUDA-graph replay over static buffers) returns the bits of the plain launch sequence, for
+    new inputs on every call and for a second batch size; a too-large batch falls back to the plain path."""
+    from hgr_b200 import ClassifierSession
+    m, _ = build(192, 0)
+    graph, eager = ClassifierSession(m, cuda_graph=True, graph_max_batch=2), ClassifierSession(m, cuda_graph=False)
+    name = graph.get_inputs()[0].name
+    for seed, b in ((1, 1), (2, 1), (3, 2), (4, 1), (5, 3)):
+        x = O.synthetic_images(b, 192, seed).numpy()
+        a, c = graph.run(None, {name: x}), eager.run(None, {name: x})
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]), (seed, b)
+    assert sorted(graph._graphs) == [1, 2]
+    graph.invalidate()
+    assert not graph._graphs
+
+
 @pytest.mark.parametrize("size,batch", [(64, 1), (64, 5), (128, 3), (320, 2), (192, 7)])
 def test_forward_odd_shapes_vs_oracle(size, batch):
     """Ragged tile grids: odd batches and small / large maps leave CTA pairs with an out-of-range second tile,
