@@ -6,6 +6,7 @@
 
 #include <cudaTypedefs.h>
 
+#include "gemm_ops.h"
 #include "hgr_internal.h"
 
 namespace hgr {
@@ -53,6 +54,19 @@ int attention_tiles_per_warp() {
     return (e && e[0] == '2') ? 2 : 1;  // measured at batch 1024, T = 145: 0.156 (1) vs 0.166 ms (2) per launch
   }();
   return v;
+}
+
+bool conv_chain_enabled() {
+  static const bool on = env_flag("HGR_CONV_CHAIN", true);
+  return on && cluster_enabled();
+}
+
+int conv_chain_prefetch() {
+  static const int d = [] {
+    const char* v = getenv("HGR_CHAIN_PREFETCH");
+    return (v && *v) ? atoi(v) : 0;
+  }();
+  return d;
 }
 
 bool vit_fused_enabled() {

@@ -40,4 +40,18 @@ int build_dgrad_s2_op(GemmOp& op, const void* dz, int B, int H, int W, int cout_
 
 int run_op(const GemmOp& op, cudaStream_t stream);
 
+// conv2 -> cspelan1.cv1 as one CTA-pair kernel (conv_chain.cu): a 3x3 conv producing 128 channels followed by the
+// 1x1 128 -> 128 conv that consumes it, the intermediate tensor never leaves the SM.  HGR_CONV_CHAIN=0 disables.
+struct ConvChainOp {
+  CUtensorMap a, w, w2, o;
+  GemmParams p;  // the first layer's walk; out_c_off / out_w_off of the second layer
+  const float* scale2;
+  const float* shift2;
+  double flops, bytes;
+};
+bool conv_chain_enabled();
+int conv_chain_prefetch();  // HGR_CHAIN_PREFETCH=<items ahead>: L2 prefetch of a later item's input patch
+int build_conv_chain_op(ConvChainOp& op, const GemmOp& first, const GemmOp& second, const void* w2);
+int launch_conv_chain(const ConvChainOp& op, int num_sms, cudaStream_t stream);
+
 }  // namespace hgr

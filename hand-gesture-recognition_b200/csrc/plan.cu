@@ -535,6 +535,8 @@ struct hgr_plan {
   std::vector<GemmOp> convs;        // kNumConvs backbone layers
   GemmOp proj;
   GemmOp qkv[kDepth], out[kDepth], ff1[kDepth], ff2[kDepth];
+  ConvChainOp stem_chain;  // conv2 -> cspelan1.cv1 (conv_chain.cu)
+  bool conv_chain = false;
   VitBlockOp blk[kDepth];  // to_out + residual + FeedForward + residual as one chained kernel (vit_block.cu)
   bool vit_fused = false;
   // launch sequence of one forward pass
@@ -711,6 +713,10 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
   gelan("d1", H3, 256, "g2", "t2", "o2", 256, 128);
   conv("o2", H3, 256, 0, nullptr, 0, 0, "d2", 512, 0, ACT_SILU);         // down2
   gelan("d2", H4, 512, "g3", "t3", "o3", 512, 256);
+  if (!rc && conv_chain_enabled() && pl->convs[0].p.cluster == 2) {
+    rc = build_conv_chain_op(pl->stem_chain, pl->convs[0], pl->convs[1], pl->pp<void>(std::string(kConvs[1].name) + ".w"));
+    pl->conv_chain = rc == 0;
+  }
   float* stats = reinterpret_cast<float*>(pl->bp("row_stats"));
   if (!rc)
     rc = build_proj_op(pl->proj, pl->bp("o3"), B, H4 * H4, 512, pl->pp<void>("proj.w"),
@@ -772,7 +778,16 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
         return launch_conv1(io.x, io.x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
                             pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
       });
-  for (int i = 0; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
+  int first_conv = 0;
+  if (pl->conv_chain) {
+    dir = zig ? !dir : 0;
+    ConvChainOp* ch = &pl->stem_chain;
+    ch->p.reverse = dir;
+    add(std::string(kConvs[0].name) + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes,
+        [ch](cudaStream_t st, const Io&) { return launch_conv_chain(*ch, device_sm_count(), st); });
+    first_conv = 2;
+  }
+  for (int i = first_conv; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
   add("decoder.cls_token", 2, 0, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io&) {
     return launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"),
                            pl->pp<float>("decoder.cls_token.stats"), reinterpret_cast<float*>(pl->bp("row_stats")), B,
@@ -957,6 +972,27 @@ int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, int in_c
                              res_ctot, res_coff, d_out, out_ctot, out_coff, cout))
     return rc;
   return run_op(op, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_conv_chain(const void* d_in, int B, int H, int W, const void* d_w1, const float* d_scale1,
+                   const float* d_shift1, const void* d_w2, const float* d_scale2, const float* d_shift2, void* d_out,
+                   int out_ctot, int out_coff, void* stream) {
+  if (!cluster_enabled()) {
+    set_error("hgr_conv_chain: the chained kernel runs on CTA pairs (HGR_CLUSTER=0 disables them)");
+    return -1;
+  }
+  // the intermediate buffer pointer of the two layer descriptors is never dereferenced: only their tile walk,
+  // tensor maps of the outer tensors and epilogue parameters are taken over
+  GemmOp first, second;
+  if (int rc = build_conv_op(first, d_in, B, H, W, 64, 0, 64, d_w1, d_scale1, d_shift1, 3, 2, ACT_SILU, nullptr, 0, 0,
+                             d_out, out_ctot, out_coff, 128))
+    return rc;
+  if (int rc = build_conv_op(second, d_out, B, H / 2, W / 2, out_ctot, out_coff, 128, d_w2, d_scale2, d_shift2, 1, 1,
+                             ACT_SILU, nullptr, 0, 0, d_out, out_ctot, out_coff, 128))
+    return rc;
+  ConvChainOp op;
+  if (int rc = build_conv_chain_op(op, first, second, d_w2)) return rc;
+  return launch_conv_chain(op, device_sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale, const float* d_bias,

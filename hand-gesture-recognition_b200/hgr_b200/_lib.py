@@ -38,6 +38,7 @@ SIGNATURES = {
     "hgr_forward_profile": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, C.POINTER(C.c_float), _i]),
     "hgr_conv_bn_act": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _fp, _fp, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i,
                              _vp]),
+    "hgr_conv_chain": (_i, [_vp, _i, _i, _i, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _i, _i, _vp]),
     "hgr_linear": (_i, [_vp, _ll, _i, _vp, _fp, _fp, _i, _vp, _vp, _i, _fp, _fp, _vp]),
     "hgr_vit_block": (_i, [_vp, _vp, _ll, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _vp]),
     "hgr_vit_block_trace": (_i, [_vp, _vp, _ll, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _vp, _i, _vp]),

@@ -120,6 +120,15 @@ HGR_API int hgr_conv_bn_act(const void* d_in, int B, int H, int W, int in_ctot, 
                     const float* d_scale, const float* d_shift, int k, int s, int act, const void* d_res,
                     int res_ctot, int res_coff, void* d_out, int out_ctot, int out_coff, int cout, void* stream);
 
+/* encoder.conv2 -> encoder.cspelan1.cv1 as one kernel (reference model/gelan.py:156 Conv(64, 128, 3, 2) and :127
+ * GELANBlock.cv1 = Conv(128, 128, 1, 1), each conv + folded BatchNorm + SiLU): the 128-channel tensor between the
+ * two layers stays in shared memory, rounded to bf16 where the separate launches store it.
+ *   d_in   NHWC bf16 (B, H, W, 64), H and W even;  d_w1 bf16 [128][9][64];  d_w2 bf16 [128][128]
+ *   d_out  NHWC bf16 (B, H/2, W/2, out_ctot); channels [out_coff, out_coff + 128) written */
+HGR_API int hgr_conv_chain(const void* d_in, int B, int H, int W, const void* d_w1, const float* d_scale1,
+                           const float* d_shift1, const void* d_w2, const float* d_scale2, const float* d_shift2,
+                           void* d_out, int out_ctot, int out_coff, void* stream);
+
 /* y = act(scale (.) (x W^T) + bias) (+ residual): nn.Linear of the ViT
  * (reference model/transformer.py:34,37,65,75).  x (rows, cin) bf16,
  * W (cout, cin) bf16, y (rows, cout) bf16; d_scale / d_bias / d_res nullable.

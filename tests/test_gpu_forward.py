@@ -73,7 +73,10 @@ def test_forward_per_stage_against_oracle():
         cls, hm, attn = m(x.cuda())
     plan = m.plan_for(batch, torch.device("cuda", torch.cuda.current_device()))
     worst = 0.0
-    for name in ["a1", "a2", "o1", "d1", "o2", "d2", "o3"]:
+    stages = ["a1", "a2", "o1", "d1", "o2", "d2", "o3"]
+    if any("conv2+" in l[0] for l in plan.launch_table()):
+        stages.remove("a2")  # conv2 -> cspelan1.cv1 runs as one kernel: a2 never reaches HBM (test_conv_chain covers it)
+    for name in stages:
         got = plan.buffer(name).float().permute(0, 3, 1, 2)
         r, _ = report("stage " + name, got, taps[name])
         worst = max(worst, r)

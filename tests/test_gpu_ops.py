@@ -189,6 +189,43 @@ def test_linear_with_folded_layernorm(lib, rows, cout, act):
     del packing
 
 
+@pytest.mark.parametrize("b,h", [(2, 96), (3, 96), (1, 32), (5, 64)])
+def test_conv_chain(lib, b, h):
+    """conv2 -> cspelan1.cv1 (reference model/gelan.py:156, :127) as one CTA-pair kernel against the fp32 operators
+    and against the two separate hgr_conv_bn_act launches it replaces (same rounding point for the tensor between)."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(b * 1000 + h)
+    x = bf16_round(torch.randn(b, 64, h, h, generator=g))
+    w1 = torch.randn(128, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    w2 = torch.randn(128, 128, 1, 1, generator=g) * (2.0 / 128) ** 0.5
+    s1, s2 = torch.rand(128, generator=g) + 0.5, torch.rand(128, generator=g) + 0.5
+    t1, t2 = torch.randn(128, generator=g) * 0.3, torch.randn(128, generator=g) * 0.3
+    xin = nhwc_bf16(x, dev)
+    w1d = w1.permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    w2d = w2.reshape(128, 128).contiguous().to(dev, torch.bfloat16)
+    s1d, s2d, t1d, t2d = (t.to(dev).float().contiguous() for t in (s1, s2, t1, t2))
+    out = torch.full((b, h // 2, h // 2, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_conv_chain(xin.data_ptr(), b, h, h, w1d.data_ptr(), s1d.data_ptr(), t1d.data_ptr(), w2d.data_ptr(),
+                            s2d.data_ptr(), t2d.data_ptr(), out.data_ptr(), 256, 64, _stream()), "hgr_conv_chain")
+    torch.cuda.synchronize()
+    got = nchw_f32(out)
+    assert torch.all(got[:, :64] == 7.0) and torch.all(got[:, 192:] == 7.0)
+    # the two separate launches
+    mid = torch.empty(b, h // 2, h // 2, 128, dtype=torch.bfloat16, device=dev)
+    two = torch.empty_like(mid)
+    _chk(lib.hgr_conv_bn_act(xin.data_ptr(), b, h, h, 64, 0, 64, w1d.data_ptr(), s1d.data_ptr(), t1d.data_ptr(), 3, 2, 1,
+                             None, 0, 0, mid.data_ptr(), 128, 0, 128, _stream()), "conv2")
+    _chk(lib.hgr_conv_bn_act(mid.data_ptr(), b, h // 2, h // 2, 128, 0, 128, w2d.data_ptr(), s2d.data_ptr(),
+                             t2d.data_ptr(), 1, 1, 1, None, 0, 0, two.data_ptr(), 128, 0, 128, _stream()), "cv1")
+    torch.cuda.synchronize()
+    a2 = F.silu(F.conv2d(x, bf16_round(w1), None, stride=2, padding=1) * s1.view(1, -1, 1, 1) + t1.view(1, -1, 1, 1))
+    ref = F.silu(F.conv2d(a2, bf16_round(w2)) * s2.view(1, -1, 1, 1) + t2.view(1, -1, 1, 1))
+    r, m = report(f"conv_chain b={b} h={h} vs fp32 operators", got[:, 64:192], ref)
+    assert r <= 6e-3 and m <= 2 * MAX_TOL
+    r2, _ = report(f"conv_chain b={b} h={h} vs two launches", got[:, 64:192], nchw_f32(two))
+    assert r2 <= 1e-3
+
+
 @pytest.mark.parametrize("rows", [1160, 128 * 148 * 2 + 77, 77])
 @pytest.mark.parametrize("inplace", [False, True], ids=["out", "inplace"])
 def test_vit_block(lib, rows, inplace):
