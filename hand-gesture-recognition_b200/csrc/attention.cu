@@ -17,6 +17,7 @@
 // keeps only the running row max / sum, pass 2 recomputes the (bitwise
 // identical) scores, normalises, and feeds P straight back into the P.V MMAs
 // from registers.
+#include "gemm_ops.h"
 #include "hgr_internal.h"
 #include "ptx.cuh"
 
@@ -503,6 +504,8 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
   // softmax(x * d^-0.5) evaluated as exp2((x - max) * d^-0.5 * log2(e))
   const float scale_log2e = 0.17677669529663687f * 1.4426950408889634f;
   const unsigned grid = (unsigned)B * kHeads;
+  if (attn_probs == nullptr && attention_tc_enabled() && attention_tc_supported(T))
+    return launch_attention_tc(qkv, out, B, T, scale_log2e, device_sm_count(), stream, reverse);
   if (attn_probs == nullptr && attention_online_enabled()) {
     // no probabilities to return: online-softmax kernel, K/V fragments shared by two query tiles per warp
     const int nkb = Tp / kKeyBlock;

@@ -37,6 +37,12 @@ bool zigzag_enabled();
 bool cluster_enabled();
 // HGR_ATTN_ONLINE=0 falls back to the strip-in-registers attention kernels when no probabilities are returned.
 bool attention_online_enabled();
+// HGR_ATTN_TC=1: the 145-token attention without probability output runs on the tcgen05 kernel (attention_tc.cu)
+// instead of the mma.sync kernels.  Parity-green but not faster yet (0.17-0.18 vs 0.16 ms per layer), so opt-in.
+bool attention_tc_enabled();
+bool attention_tc_supported(int T);
+int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, float scale_log2e, int num_sms,
+                        cudaStream_t stream, int reverse);
 // HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
 int attention_tiles_per_warp();
 // HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.

@@ -1044,6 +1044,12 @@ int hgr_attention(const void* d_qkv, void* d_out, void* d_probs, int probs_dtype
                           probs_dtype, B, T, static_cast<cudaStream_t>(stream));
 }
 
+int hgr_attention_tc(const void* d_qkv, void* d_out, int B, int T, void* stream) {
+  return launch_attention_tc(static_cast<const __nv_bfloat16*>(d_qkv), static_cast<__nv_bfloat16*>(d_out), B, T,
+                             0.17677669529663687f * 1.4426950408889634f, device_sm_count(),
+                             static_cast<cudaStream_t>(stream), 0);
+}
+
 int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
                  const float* d_bias, void* d_logits, int out_dtype, int B, int T, int num_classes, void* stream) {
   return launch_cls_head(static_cast<const __nv_bfloat16*>(d_tokens), d_gamma, d_beta, d_w, d_bias, d_logits,

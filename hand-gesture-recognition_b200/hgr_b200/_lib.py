@@ -45,6 +45,7 @@ SIGNATURES = {
     "hgr_conv1": (_i, [_vp, _i, _i, _i, _vp, _fp, _vp, _vp]),
     "hgr_layernorm": (_i, [_vp, _vp, _fp, _fp, _ll, _vp]),
     "hgr_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hgr_attention_tc": (_i, [_vp, _vp, _i, _i, _vp]),
     "hgr_cls_head": (_i, [_vp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_pose_head": (_i, [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_get_max_preds": (_i, [_vp, _i, _i, _i, _i, _i, _fp, _fp, _vp]),

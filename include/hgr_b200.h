@@ -175,6 +175,11 @@ HGR_API int hgr_layernorm(const void* d_x, void* d_y, const float* d_gamma, cons
  * d_out (B, T, 256) bf16; d_probs (B, 8, T, T) probs_dtype or NULL. */
 HGR_API int hgr_attention(const void* d_qkv, void* d_out, void* d_probs, int probs_dtype, int B, int T, void* stream);
 
+/* The same attention core on tcgen05 tensor cores (csrc/attention_tc.cu): scores and outputs in TMEM, softmax by
+ * one thread per query row, V as an MN-major operand.  129 <= T <= 160, no probability output.  Opt-in inside the
+ * forward plan (HGR_ATTN_TC=1); exported so that the parity suite covers it. */
+HGR_API int hgr_attention_tc(const void* d_qkv, void* d_out, int B, int T, void* stream);
+
 /* mlp_head: Linear(256, C)(LayerNorm(tokens[:, 0])). */
 HGR_API int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
                  const float* d_bias, void* d_logits, int out_dtype, int B, int T, int num_classes, void* stream);

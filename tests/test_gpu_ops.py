@@ -348,6 +348,24 @@ def test_attention(lib, tokens, probs):
         assert r2 <= (REL_TOL if probs == torch.bfloat16 else 1e-4) and m2 <= MAX_TOL
 
 
+@pytest.mark.parametrize("tokens,b", [(145, 3), (145, 40), (160, 2), (129, 5)])
+def test_attention_tc(lib, tokens, b):
+    """The tcgen05 attention kernel (csrc/attention_tc.cu, opt-in through HGR_ATTN_TC=1) against the fp32 operators."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(tokens * 7 + b)
+    qkv = bf16_round(torch.randn(b, tokens, 768, generator=g) * 1.5)
+    qd = qkv.to(dev, torch.bfloat16)
+    out = torch.full((b, tokens, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_attention_tc(qd.data_ptr(), out.data_ptr(), b, tokens, _stream()), "hgr_attention_tc")
+    torch.cuda.synchronize()
+    q, k, v = qkv.chunk(3, dim=-1)
+    sp = lambda t: t.reshape(b, tokens, 8, 32).permute(0, 2, 1, 3)
+    attn = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) * 32 ** -0.5, dim=-1)
+    ref = (attn @ sp(v)).permute(0, 2, 1, 3).reshape(b, tokens, 256)
+    r, m = report(f"attention_tc T={tokens} B={b}", out, ref)
+    assert r <= 6e-3 and m <= 2 * MAX_TOL
+
+
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_cls_head(lib, out_dtype):
     from hgr_b200 import _lib
