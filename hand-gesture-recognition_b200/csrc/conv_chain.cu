@@ -153,8 +153,8 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 128 * 2);
-      mbar_init(&inter_ready_bar[i], 128 * 2);
+      mbar_init(&acc_empty_bar[i], 4 * 2);    // one arrival per epilogue warp of the group, both CTAs
+      mbar_init(&inter_ready_bar[i], 4 * 2);
       mbar_init(&acc2_full_bar[i], 1);
     }
     mbar_init(w2_bar, 1);
@@ -316,16 +316,23 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_wait();
         if (j == 1) {
           // the G1 stage goes back to the leader's MMA warp before the arithmetic
+          // (one release-arrive per WARP: 128 cluster-scope arrives per tile showed up as membar stalls in ncu)
           tc_fence_before();
-          if (cta_rank == 0) mbar_arrive(&acc_empty_bar[group]);
-          else mbar_arrive_cluster(&acc_empty_bar[group], 0);
+          __syncwarp();
+          if (lane == 0) {
+            if (cta_rank == 0) mbar_arrive(&acc_empty_bar[group]);
+            else mbar_arrive_cluster(&acc_empty_bar[group], 0);
+          }
         }
         activate_store_chunk(acc, s_aff + j * 64, s_aff + kC + j * 64, inter + j * kChunkBytes, row, sw);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      if (cta_rank == 0) mbar_arrive(&inter_ready_bar[group]);
-      else mbar_arrive_cluster(&inter_ready_bar[group], 0);
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank == 0) mbar_arrive(&inter_ready_bar[group]);
+        else mbar_arrive_cluster(&inter_ready_bar[group], 0);
+      }
 
       // ---------------- E2: g tile -> the same buffer, in place -> TMA store ----------------
       mbar_wait(&acc2_full_bar[group], ph);
