@@ -74,6 +74,11 @@ bool attention_tc_enabled() {
   return on;
 }
 
+bool warp_arrive_enabled() {
+  static const bool on = env_flag("HGR_WARP_ARRIVE", true);
+  return on;
+}
+
 bool vit_fused_enabled() {
   static const bool on = env_flag("HGR_VIT_FUSED", true);
   return on;

@@ -158,9 +158,14 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       tmem_ld_wait();
       if (j == BN / 64 - 1) {
         tc_fence_before();
-        // pair mode: the accumulator stage belongs to the leader's MMA thread, which waits for BOTH CTAs' readers
-        if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);
-        else mbar_arrive_cluster(&acc_empty_bar[group], 0);
+        // pair mode: the accumulator stage belongs to the leader's MMA thread, which waits for BOTH CTAs' readers.
+        // One arrival per warp (HGR_WARP_ARRIVE, default): 128 cluster-scope release-arrives per tile show up as
+        // membar stalls in the epilogue.
+        if (p.warp_arrive) __syncwarp();
+        if (!p.warp_arrive || lane == 0) {
+          if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);
+          else mbar_arrive_cluster(&acc_empty_bar[group], 0);
+        }
       }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -281,7 +286,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 128 * CL);  // pair mode: the readers of both CTAs release the leader's stage
+      // pair mode: the readers of both CTAs release the leader's stage; one arrival per warp or per thread
+      mbar_init(&acc_empty_bar[i], (p.warp_arrive ? 4 : 128) * CL);
     }
     fence_barrier_init();
   }
@@ -495,7 +501,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full_bar[i], 1);
-      mbar_init(&acc_empty_bar[i], 128 * CL);
+      mbar_init(&acc_empty_bar[i], (p.warp_arrive ? 4 : 128) * CL);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();

@@ -45,6 +45,8 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int
                         cudaStream_t stream, int reverse);
 // HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
 int attention_tiles_per_warp();
+// HGR_WARP_ARRIVE=0: every epilogue thread arrives on the accumulator-release barrier (the original protocol).
+bool warp_arrive_enabled();
 // HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.
 bool halo_pair_enabled();
 // HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
@@ -92,6 +94,7 @@ struct GemmParams {
   int act;
   int reverse;           // walk the tile grid back to front (see plan.cu: zig-zag order for L2 reuse)
   int prefetch_dist;     // > 0: L2-prefetch the A tile needed that many tiles ahead (HGR_PREFETCH, default 2)
+  int warp_arrive;       // accumulator stages are released by one arrival per epilogue warp instead of per thread
   int cluster;           // 1, or 2 = CTA-pair mode, cta_group::2 MMAs (the W map's box then holds BN / 2 rows)
   const float* scale;  // nullable: 1
   const float* shift;  // nullable: 0

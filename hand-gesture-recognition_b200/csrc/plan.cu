@@ -91,6 +91,7 @@ int build_conv_op(GemmOp& op, const void* in, int B, int H, int W, int in_ctot, 
     bi = 1;
   }
   GemmParams& p = op.p;
+  p.warp_arrive = warp_arrive_enabled() ? 1 : 0;
   p.num_taps = k * k;
   p.chunks_per_tap = cin / 64;
   p.a_c_off = in_coff;
@@ -185,6 +186,7 @@ int build_linear_op(GemmOp& op, const void* x, long long rows, int cin, const vo
   memset(&op, 0, sizeof(op));
   op.bn = pick_bn(cout);
   GemmParams& p = op.p;
+  p.warp_arrive = warp_arrive_enabled() ? 1 : 0;
   p.num_taps = 1;
   p.chunks_per_tap = cin / 64;
   {
@@ -248,6 +250,7 @@ int build_proj_op(GemmOp& op, const void* feat, int B, int P, int cin, const voi
   memset(&op, 0, sizeof(op));
   op.bn = 256;
   GemmParams& p = op.p;
+  p.warp_arrive = warp_arrive_enabled() ? 1 : 0;
   p.num_taps = 1;
   p.chunks_per_tap = cin / 64;
   {
@@ -313,6 +316,7 @@ int build_dgrad_s2_op(GemmOp& op, const void* dz, int B, int H, int W, int cout_
   memset(&op, 0, sizeof(op));
   op.bn = pick_bn(cin_fwd);
   GemmParams& p = op.p;
+  p.warp_arrive = warp_arrive_enabled() ? 1 : 0;
   const int nh = ph ? 2 : 1, nw = pw ? 2 : 1;
   p.num_taps = nh * nw;
   p.chunks_per_tap = cout_fwd / 64;
