@@ -156,8 +156,10 @@ HGR_API int hgr_vit_block(const void* d_attn_out, const void* d_x0, long long ro
                           const float* d_b2, void* d_x2, float* d_row_stats_out, void* stream);
 
 /* Profiling twin of hgr_vit_block: CTA 0 also writes clock64 marks of its first `trace_tiles` tiles into
- * d_trace[trace_tiles][16] (int64): 0 G0 done, 1 E0 done, 2 G1 done, 3 E1 done, 4 G2 done, 5 E2 done / store
- * issued, 8..10 the MMA warp's view of "operand of G0/G1/G2 ready" (tools/vit_block_trace.py). */
+ * d_trace[trace_tiles][16] (int64): 0 G0 done, 1 E0 done, 2 G1 done, 3 E1 done, 4 G2 done (all as seen by the
+ * first epilogue thread), 5 last output chunk's store issued, 6 epilogue back at the top of the chain, 7 first x0
+ * chunk landed, 8..10 the MMA warp starts G0/G1/G2, 11..14 weights of G0's four k-blocks are in shared memory
+ * (tools/vit_block_trace.py prints them as cycle deltas). */
 HGR_API int hgr_vit_block_trace(const void* d_attn_out, const void* d_x0, long long rows, const void* d_w_out,
                                 const void* d_w1, const float* d_c1, const float* d_d1, const void* d_w2,
                                 const float* d_b2, void* d_x2, float* d_row_stats_out, long long* d_trace,
