@@ -337,7 +337,7 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 template <int NKB, int MT, int NW>
 __global__ void __launch_bounds__(NW * 32, NW > 5 ? (MT == 1 ? 3 : 1) : (MT == 2 ? 3 : 5))
 attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
-                        float scale_log2e, int reverse) {
+                        float scale_log2e, int reverse, int attn_cp_async) {
   constexpr int Tp = NKB * kKeyBlock;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -353,23 +353,36 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 
   const __nv_bfloat16* base = qkv + (size_t)b * T * (3 * kHeads * kHd) + h * kHd;
   {
-    constexpr int kTotal = 3 * Tp * 4;            // 16-byte chunks of Q, K and V
-    constexpr int kBatch = 12;                    // requests in flight per thread
-    for (int i0 = 0; i0 < kTotal; i0 += kBatch * NW * 32) {
-      uint4 v[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const int i = i0 + tid + k * NW * 32;
+    // 16-byte chunks of Q, K and V go straight from global to shared memory (cp.async, zero-fill for the padding
+    // rows): no register staging, no second pass of shared-memory stores
+    constexpr int kTotal = 3 * Tp * 4;
+    if (attn_cp_async) {
+      for (int i = tid; i < kTotal; i += NW * 32) {
         const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
-        v[k] = make_uint4(0, 0, 0, 0);
-        if (i < kTotal && row < T)
-          v[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * kHeads * kHd) + part * kHeads * kHd) + c);
+        const int srow = row < T ? row : 0;
+        cp_async_16(sq + (part * Tp + row) * kPitch + c * 8,
+                    base + (size_t)srow * (3 * kHeads * kHd) + part * kHeads * kHd + c * 8, row < T ? 16u : 0u);
       }
+      cp_async_commit();
+      cp_async_wait<0>();
+    } else {
+      constexpr int kBatch = 12;                    // requests in flight per thread
+      for (int i0 = 0; i0 < kTotal; i0 += kBatch * NW * 32) {
+        uint4 v[kBatch];
 #pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const int i = i0 + tid + k * NW * 32;
-        const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
-        if (i < kTotal) *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v[k];
+        for (int k = 0; k < kBatch; ++k) {
+          const int i = i0 + tid + k * NW * 32;
+          const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+          v[k] = make_uint4(0, 0, 0, 0);
+          if (i < kTotal && row < T)
+            v[k] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * kHeads * kHd) + part * kHeads * kHd) + c);
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+          const int i = i0 + tid + k * NW * 32;
+          const int c = i & 3, row = (i >> 2) % Tp, part = (i >> 2) / Tp;
+          if (i < kTotal) *reinterpret_cast<uint4*>(sq + (part * Tp + row) * kPitch + c * 8) = v[k];
+        }
       }
     }
   }
@@ -512,14 +525,16 @@ int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_pr
     const bool one = attention_tiles_per_warp() == 1;  // 1: fewer registers, five CTAs per SM; 2: shared K/V fragments
     if (nkb == 5) {
       HGR_CHECK_CUDA(launch_pdl(one ? attention_kernel_online<5, 1, kWarps> : attention_kernel_online<5, 2, kWarps>,
-                                dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
+                                dim3(grid), dim3(kWarps * 32), smem, stream, qkv, out, T, scale_log2e, reverse,
+                                attention_cp_async_enabled() ? 1 : 0));
       return 0;
     }
     if (nkb == 9) {
       // 257 tokens = 17 query tiles: nine warps walk them in two rounds (five warps need four)
       auto kern = one ? attention_kernel_online<9, 1, 9> : attention_kernel_online<9, 2, 9>;
       HGR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      HGR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(9 * 32), smem, stream, qkv, out, T, scale_log2e, reverse));
+      HGR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(9 * 32), smem, stream, qkv, out, T, scale_log2e, reverse,
+                                attention_cp_async_enabled() ? 1 : 0));
       return 0;
     }
   }

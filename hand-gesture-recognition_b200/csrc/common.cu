@@ -79,6 +79,11 @@ bool warp_arrive_enabled() {
   return on;
 }
 
+bool attention_cp_async_enabled() {
+  static const bool on = env_flag("HGR_ATTN_CPASYNC", true);
+  return on;
+}
+
 bool vit_fused_enabled() {
   static const bool on = env_flag("HGR_VIT_FUSED", true);
   return on;

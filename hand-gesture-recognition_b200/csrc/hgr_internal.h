@@ -43,6 +43,8 @@ bool attention_tc_enabled();
 bool attention_tc_supported(int T);
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, float scale_log2e, int num_sms,
                         cudaStream_t stream, int reverse);
+// HGR_ATTN_CPASYNC=0: the online-softmax attention kernel stages Q, K, V through registers instead of cp.async.
+bool attention_cp_async_enabled();
 // HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
 int attention_tiles_per_warp();
 // HGR_WARP_ARRIVE=0: every epilogue thread arrives on the accumulator-release barrier (the original protocol).
