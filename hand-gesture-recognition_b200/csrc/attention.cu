@@ -329,11 +329,14 @@ attention_kernel_1pass(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __r
 }
 
 // Online-softmax variant for launches that do not return the probabilities (every layer but the last, and the
-// last one too when the attention map is switched off).  A warp owns 32 query rows (two m16 tiles) and walks the
-// key blocks once: the K and V fragments of a block are fetched from shared memory ONCE for both tiles, which
-// halves the ldmatrix traffic that bounds the strip-in-registers kernel above (ncu: l1tex 74 %, tensor 35 %), and
-// only one 32-key block of scores is live at a time, so the rescaled running output (flash-attention recurrence)
-// costs fewer registers than the 16 x T strip did.
+// last one too when the attention map is switched off).  A warp owns MT m16 query tiles and walks the key blocks
+// once: only one 32-key block of scores is live at a time, so the rescaled running output (flash-attention
+// recurrence) costs far fewer registers than the 16 x T strip of the kernel above.
+//   MT = 1 (default): 72 registers, five CTAs per SM at 145 tokens - 0.156 ms per layer at batch 1024;
+//   MT = 2: the K and V fragments of a block are fetched from shared memory once for two tiles (half the
+//           ldmatrix traffic), but 128 registers leave three CTAs per SM - 0.166 ms, like the strip kernel.
+// NW = warps per CTA: 5 at 145 tokens (10 tiles), 9 at 257 tokens (17 tiles in two rounds, 0.593 -> 0.505 ms).
+// Q, K and V are staged by cp.async (0.163 -> 0.154 ms against staging through registers).
 template <int NKB, int MT, int NW>
 __global__ void __launch_bounds__(NW * 32, NW > 5 ? (MT == 1 ? 3 : 1) : (MT == 2 ? 3 : 5))
 attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
