@@ -154,3 +154,24 @@ def test_two_rank_sharding_over_gloo():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 51), (51, 101)]
     assert all(r[3] == 11.0 and r[4] == 101.0 for r in res)
+
+
+def test_committed_ncu_capture_feeds_the_roofline_traffic():
+    """bench.py takes roofline.traffic from the newest profiles/*_step_ncu_full.csv: the committed capture must parse,
+    cover every tcgen05 launch of a forward (implicit-GEMM, halo, chained stem and chained ViT kernels) and give a
+    DRAM figure per launch of the order of the algorithmic bytes (hundreds of MB at batch 1024)."""
+    import csv
+    import importlib.util
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("bench_for_test", root / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per_launch, name = bench.ncu_traffic_per_launch()
+    assert name is not None and (root / "profiles" / name).exists()
+    assert 1e8 < per_launch < 2e9, per_launch
+    rows = list(csv.DictReader((root / "profiles" / name).open()))
+    kernels = " ".join(r["Kernel Name"] for r in rows)
+    for needle in ("gemm_kernel", "halo", "conv1_kernel", "attention_kernel", "pose_head_kernel"):
+        assert needle in kernels, needle
+    shares = [float(r["share_of_step_ncu"]) for r in rows]
+    assert abs(sum(shares) - 1.0) < 1e-2
