@@ -508,6 +508,10 @@ attention_kernel_online(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 
 }  // namespace
 
+// Q, K and V of one (image, head) live in shared memory as three [Tp][kPitch] bf16 arrays.
+int attention_max_tokens() { return (227 * 1024 / (3 * kPitch * 2)) / kKeyBlock * kKeyBlock; }
+bool attention_tokens_supported(int T) { return T >= 1 && T <= attention_max_tokens(); }
+
 int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* attn_probs, int probs_dtype, int B, int T,
                      cudaStream_t stream, int reverse, int probs_pitch) {
   const int pp = probs_pitch > 0 ? probs_pitch : T;

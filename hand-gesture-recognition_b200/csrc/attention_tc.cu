@@ -1,28 +1,45 @@
 // Attention core on the 5th-gen tensor cores for the 145-token case (192 x 192 inputs)
 // (reference model/transformer.py:66-74: softmax(q k^T * d^-0.5) v per head, heads of width 32).
 //
-// The mma.sync kernels of attention.cu spend their time feeding the legacy tensor path (ldmatrix traffic, one CTA
-// per (image, head), ~4 700 SM cycles per head).  Here a persistent CTA walks (image, head pair) items:
-//   * TMA brings the Q, K and V columns of TWO heads (64 columns = one 128-byte swizzle row) as three
-//     [160 tokens x 64] boxes; rows beyond the image's 145 tokens are zero-filled by the tensor map;
-//   * S = Q K^T is one M = 128, N = 160, K = 32 tcgen05.mma per (head, 128-query tile) with the fp32 scores in TMEM;
-//   * softmax warps (one thread per query row) read the scores twice out of TMEM - row maximum, then
-//     exp2 / row sum / bf16 - and write P into shared memory as the K-major SWIZZLE_128B A operand of the next MMA;
-//   * O = P V is M = 128, N = 32, K = 160 with V as the MN-major B operand (the [tokens x 64] box as it was loaded:
-//     no transpose), accumulated in TMEM; the softmax warps scale by 1 / sum and store 'b n (h d)'.
+// A persistent CTA walks (image, head pair) items.  Per item:
+//   * TMA brings the Q, K and V columns of TWO heads (64 columns = one 128-byte swizzle row): Q rows 0-127, K and V as
+//     [160 tokens x 64] boxes whose rows beyond the image's 145 tokens are zero-filled by the tensor map;
+//   * S = Q K^T is an M = 128, N = 160, K = 32 tcgen05.mma per unit with the fp32 scores in TMEM;
+//   * a softmax group (4 warps, ONE THREAD PER QUERY ROW, no cross-thread exchange) reads the scores twice out of
+//     TMEM - row maximum, then exp2 / row sum - and writes the bf16 probabilities back INTO TENSOR MEMORY over the
+//     scores it has consumed (tcgen05.st, two keys per 32-bit column);
+//   * O = P V has P as the TMEM A operand and V as the MN-major shared-memory B operand (the [tokens x 64] box as it
+//     was loaded: no transpose); the group scales by 1 / sum and stores 'b n (h d)'.
+// The probabilities never touch shared memory, so a unit costs exactly 160 TMEM columns (scores, then P in columns
+// 0-79 and O behind them) and THREE units are in flight (3 x 160 of the 512 columns), one per softmax group.
+//
+// The 145 query rows of a head are a full tile (rows 0-127) and a 17-row tile.  A warp can only read its own quarter
+// of the TMEM lanes and lives on the scheduler of the same index, so a unit made of ONE short tile would keep one
+// warp of its group busy and three idle (and that warp's MUFU pipe - one ex2 per score, the bound of this kernel -
+// would carry the whole unit).  The two short tiles of an item therefore share ONE unit: a fourth box holds the
+// rows 128.. of both heads at a NEGATIVE row coordinate of a tensor map that starts at row 128, so that everything
+// around the 17 real rows is zero-filled by TMA; head 0's MMA starts its A operand 32 rows into that box, head 1's at
+// its first row, both ACCUMULATE into the same 160 columns: lane quarter j0 receives head 0's rows, quarter j0 + 1
+// head 1's, every other lane adds zeros.  Their P V is one N = 64 MMA chain against the whole V box (both heads'
+// columns); each quarter reads its own head's 32 output columns.  An item is three units (full head 0, full head 1, the two
+// short tiles), rotated over the three groups, and j0 alternates between 0 and 2, so that the four schedulers carry
+// the same load.
+//
 // The probabilities are not returned by this kernel: launches that need them (the last layer with
-// return_attention=True) use attention.cu.
+// return_attention=True) use attention.cu, and so do token counts outside 129..160.
 //
-// Status (round 1): parity-green (tests/test_gpu_ops.py::test_attention_tc, 1.9e-3 rel-L2 like the mma.sync kernels),
-// 0.223 ms per layer with one softmax warp per lane quarter, 0.170-0.184 ms with two (this version) against 0.156-0.171
-// ms for the mma.sync online-softmax kernel on the same boxes - so it is OPT-IN (HGR_ATTN_TC=1).  What bounds it: a
-// unit's chain S -> max -> exp -> P -> P V -> O is ~4 500 cycles of mostly latency, only two units fit TMEM
-// (2 x 160 score columns + outputs), and the 17-row second query tile keeps one lane quarter busy while three idle.
-// Keeping a row's 80 scores in registers across the two passes spilled (0.233 ms).
-//
-// Units (head hh of the pair, query tile mt) are issued in the order mt-major, so softmax group g (8 warps, two per TMEM
-// lane quarter) always owns head hh = g and both groups see the same mix of full (rows 0-127) and short
-// (rows 128-144) tiles.  TMEM: two score buffers of 160 columns and two output buffers of 32 columns.
+// Measured on B200 (tools/tmem_probe.cu, tools/mufu_probe.cu): tcgen05.ld.32x32b.x32 sustains 173 B/clk per warp and
+// ~800 B/clk per SM, so reading the scores twice costs ~200 cycles per unit; MUFU.EX2 issues one warp instruction per
+// 8 cycles per scheduler (9.3 inside the softmax instruction mix), a lone warp reaches 11.2; the TMEM-A MMA reproduces
+// P V exactly.  Round 1's two-unit variant with P in shared memory ran at 0.17-0.18 ms per layer, the first three-unit
+// version (short tiles as units of their own, one thread per row) at 0.138 ms, with the combined short unit (this
+// version) at 0.108 ms, mma.sync at 0.150 ms.  A variant with two warps per lane quarter splitting a row's keys (24
+// softmax warps, maximum / sum exchanged through shared memory) was SLOWER (0.122-0.133 ms): the cycle timeline
+// (hgr_attention_tc_trace, tools/attention_trace.py) shows the MUFU pipe saturated only while two or three groups are
+// in their exponential pass at the same time (40 % of a unit's life); the maximum pass, the MMA hand-over and the
+// output pass of a unit are stretched by the other groups' queued MUFU work, and more warps add queueing, not
+// throughput.  Next step: two softmax groups over three buffers with the output drained by separate
+// warps, so that a group never waits for its own hand-over.
 #include <cstdio>
 #include <cstring>
 
@@ -33,24 +50,28 @@ namespace hgr {
 
 namespace {
 
-constexpr int kThreads = 640;  // 4 service warps + 2 softmax groups of 8 warps
-constexpr int kTp = 160;                          // padded tokens (keys per MMA, rows per box)
+constexpr int kGroups = 3;                        // softmax groups = units in flight = units per item
+constexpr int kThreads = (4 + 4 * kGroups) * 32;  // 4 service warps + 4 warps per group
+constexpr int kTp = 160;                          // padded tokens (keys per MMA, rows per K / V box)
 constexpr int kHeads = 8;
-constexpr int kBoxBytes = kTp * 128;              // [160 rows][64 cols] bf16
-constexpr int kStageBytes = 3 * kBoxBytes;        // Q | K | V of one head pair
-constexpr int kPChunkBytes = 128 * 128;           // [128 queries][64 keys] bf16
-constexpr int kPBytes = 3 * kPChunkBytes;         // keys 0-63 | 64-127 | 128-159 (+ unused tail)
-constexpr int kOffQkv = 0;
-constexpr int kOffP = 2 * kStageBytes;
-constexpr int kOffExch = kOffP + 2 * kPBytes;    // per group: row maxima and row sums of the two key halves, 2 KiB
-constexpr int kOffBars = kOffExch + 2 * 2048;
-constexpr int kNumBars = 10;
+constexpr int kStages = 2;
+constexpr int kQBytes = 128 * 128;                // Q rows 0-127:  [128 rows][64 cols] bf16
+constexpr int kBoxBytes = kTp * 128;              // K, V, short-row box: [160 rows][64 cols] bf16
+constexpr int kOffK = kQBytes;
+constexpr int kOffV = kOffK + kBoxBytes;
+constexpr int kOffQs = kOffV + kBoxBytes;         // rows 128.. of both heads inside a zero-filled box
+constexpr int kStageBytes = kOffQs + kBoxBytes;
+constexpr int kOffBars = kStages * kStageBytes;
+constexpr int kNumBars = 2 * kStages + 4 * kGroups;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
-constexpr int kSCols = 160;                       // TMEM columns of one score buffer
-constexpr int kOBase = 2 * kSCols;                // output buffers start here, 32 columns each
-static_assert(kBoxBytes % 1024 == 0 && kOffP % 1024 == 0, "operand tiles need 1024-byte alignment");
+constexpr int kUnitCols = 160;  // TMEM columns of one unit: S [0,160), then P [0,80) and O behind it
+constexpr int kOColFull = 128;  // full tile: O (N = 32) in columns [128,160)
+constexpr int kOColShort = 80;  // short tiles: O (N = 64) in columns [80,144)
+constexpr int kGroupThreads = 128;
+static_assert(kQBytes % 1024 == 0 && kBoxBytes % 1024 == 0, "operand tiles need 1024-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "attention_tc shared-memory plan exceeds one CTA");
+static_assert(kGroups * kUnitCols <= 512, "units in flight exceed tensor memory");
 
 // MN-major, 128-byte-swizzled operand: rows of the K dimension are 128 B apart, 8-row groups `sbo_bytes` apart; the
 // 64 MN elements of a row are contiguous (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>:
@@ -71,39 +92,71 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
 struct AttnTcParams {
   __nv_bfloat16* out;  // (B, T, 256)
   int B, T;
   float scale_log2e;
   int reverse;
+  // optional timeline of CTA 0 (hgr_attention_tc_trace): clock64 at the hand-over points, [item][warp][8 marks];
+  // softmax warps: 0 scores ready, 1 maximum done, 2 probabilities written, 3 output ready, 4 output stored;
+  // MMA warp (row 1): 0 S issued, 1 probabilities seen, 2 P V issued (per unit position r: marks 3 r + ..)
+  long long* trace;
+  int trace_items;
 };
 
+// Unit `r` (0..2, == its TMEM buffer == its softmax group) of the CTA's i-th item: the types rotate with the item so
+// that every group sees full and short units alike.  type 0 / 1: rows 0-127 of head 0 / 1; type 2: both short tiles.
+__device__ __forceinline__ int unit_type(int i, int r) {
+  const int t = r + i % 3;
+  return t >= 3 ? t - 3 : t;
+}
+// lane quarter of head 0's short rows in the i-th item (head 1's are in the next quarter)
+__device__ __forceinline__ int short_quarter(int i) { return (i & 1) * 2; }
+
+// kTokens > 0: token count known at compile time (the padded keys cost neither masks nor exponentials); 0: p.T
+template <int kTokens>
 __global__ void __launch_bounds__(kThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmQs, const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int T = kTokens > 0 ? kTokens : p.T;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
-  uint64_t* qkv_full = bars;       // [2]
-  uint64_t* qkv_empty = bars + 2;  // [2]
-  uint64_t* s_full = bars + 4;     // [2] scores of a unit are in TMEM
-  uint64_t* p_ready = bars + 6;    // [2] probabilities of a unit are in shared memory (128 arrivals)
-  uint64_t* o_full = bars + 8;     // [2] P V of a unit is in TMEM
+  uint64_t* qkv_full = bars;              // [kStages]
+  uint64_t* qkv_empty = bars + kStages;   // [kStages]
+  uint64_t* s_full = bars + 2 * kStages;  // [kGroups] scores of a unit are in TMEM
+  uint64_t* p_ready = s_full + kGroups;   // [kGroups] probabilities are in TMEM (128 arrivals)
+  uint64_t* o_full = p_ready + kGroups;   // [kGroups] P V of a unit is in TMEM
+  uint64_t* buf_free = o_full + kGroups;  // [kGroups] the unit's output has been read (128 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("hgr: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  if (warp == 0 && lane == 0) prefetch_tensormap(&tmQkv);
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmKV);
+    prefetch_tensormap(&tmQs);
+  }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&qkv_full[i], 1);
       mbar_init(&qkv_empty[i], 1);
+    }
+    for (int i = 0; i < kGroups; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 256);
+      mbar_init(&p_ready[i], kGroupThreads);
       mbar_init(&o_full[i], 1);
+      mbar_init(&buf_free[i], kGroupThreads);
     }
     fence_barrier_init();
   }
@@ -124,175 +177,227 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const AttnTcParam
   const int step = p.reverse ? -(int)gridDim.x : (int)gridDim.x;
 
   if (warp == 0) {
-    // ================= TMA producer: Q | K | V boxes of one head pair per item =================
+    // ================= TMA producer: Q | K | V | short-row boxes of one head pair per item =================
     if (elect_one_sync()) {
       int item = first;
+      int s = 0, k = 0;  // stage, use count of the stage
       for (int i = 0; i < my_items; ++i, item += step) {
-        const int s = i & 1;
         const int b = item >> 2, pair = item & 3;
-        mbar_wait(&qkv_empty[s], ((i >> 1) & 1) ^ 1);
+        uint8_t* stage = smem + s * kStageBytes;
+        mbar_wait(&qkv_empty[s], (k & 1) ^ 1);
         mbar_expect_tx(&qkv_full[s], kStageBytes);
-#pragma unroll
-        for (int part = 0; part < 3; ++part)
-          tma_load_5d(smem + kOffQkv + s * kStageBytes + part * kBoxBytes, &tmQkv, &qkv_full[s], part * 256 + pair * 64,
-                      0, b, 0, 0);
+        tma_load_5d(stage, &tmQ, &qkv_full[s], pair * 64, 0, b, 0, 0);
+        tma_load_5d(stage + kOffK, &tmKV, &qkv_full[s], 256 + pair * 64, 0, b, 0, 0);
+        tma_load_5d(stage + kOffV, &tmKV, &qkv_full[s], 512 + pair * 64, 0, b, 0, 0);
+        // box row r holds token 128 + r - 32 (j0 + 1); everything outside [128, T) is zero-filled
+        tma_load_5d(stage + kOffQs, &tmQs, &qkv_full[s], pair * 64, -32 * (short_quarter(i) + 1), b, 0, 0);
+        if (++s == kStages) {
+          s = 0;
+          ++k;
+        }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    // unit u = 4 i + 2 mt + hh:  S(u) = Q[mt] K^T into score buffer u & 1, then P V of unit u - 1
+    // ================= MMA issuer: S of unit (i, r), then P V of the unit two positions earlier =================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, kTp);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);  // B is MN-major
-    auto issue_pv = [&](int v) {
-      const int g = v & 1;            // = hh
-      const int s = (v >> 2) & 1;     // shared-memory stage of the unit's item
-      mbar_wait(&p_ready[g], (v >> 1) & 1);
-      tc_fence_after();
-      const uint32_t pbuf = smem_u32(smem + kOffP + g * kPBytes);
-      const uint32_t vbuf = smem_u32(smem + kOffQkv + s * kStageBytes + 2 * kBoxBytes) + g * 64;
-      const uint32_t tmem_d = tmem_base + kOBase + g * 32;
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < kTp / 16; ++k) {
-          const uint64_t a = umma_desc_sw128(pbuf + (k >> 2) * kPChunkBytes, 1024) + 2 * (k & 3);
-          const uint64_t bdesc = umma_desc_mn_sw128(vbuf + k * 2048, 1024);
-          umma_bf16_ss(tmem_d, a, bdesc, idesc_o, k != 0 ? 1u : 0u);
+    constexpr uint32_t idesc_o32 = umma_idesc_bf16(128, 32) | (1u << 16);  // B is MN-major
+    constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64) | (1u << 16);
+    const int num_units = kGroups * my_items;
+    int i_s = 0, r_s = 0;  // item / position of the unit whose scores are issued next
+    int i_o = 0, r_o = 0;  // the same for the unit whose P V is issued next
+    for (int u = 0; u < num_units + 2; ++u) {
+      if (u < num_units) {
+        const int st = i_s % kStages;
+        if (r_s == 0) {
+          mbar_wait(&qkv_full[st], (i_s / kStages) & 1);
+          tc_fence_after();
         }
-        umma_commit(&o_full[g]);
-        if ((v & 3) == 3) umma_commit(&qkv_empty[s]);  // last unit of the item: Q, K, V may be overwritten
-      }
-      __syncwarp();
-    };
-    int u = 0;
-    for (int i = 0; i < my_items; ++i) {
-      const int s = i & 1;
-      mbar_wait(&qkv_full[s], (i >> 1) & 1);
-      tc_fence_after();
-      const uint32_t qbuf = smem_u32(smem + kOffQkv + s * kStageBytes);
-      const uint32_t kbuf = qbuf + kBoxBytes;
-#pragma unroll
-      for (int r = 0; r < 4; ++r, ++u) {
-        const int mt = r >> 1, hh = r & 1;
-        // the score buffer u & 1 is free: P V of unit u - 2 was issued after its probabilities were complete
-        const uint32_t tmem_d = tmem_base + (u & 1) * kSCols;
+        if (i_s >= 1) {
+          // the previous unit of this buffer has been drained (its O has been read, which implies its P V has retired)
+          mbar_wait(&buf_free[r_s], (i_s - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t stage = smem_u32(smem + st * kStageBytes);
+        const uint32_t tmem_d = tmem_base + r_s * kUnitCols;
+        const int ty = unit_type(i_s, r_s);
         if (elect_one_sync()) {
+          if (ty < 2) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint64_t a = umma_desc_sw128(qbuf + mt * 128 * 128 + hh * 64, 1024) + 2 * k;
-            const uint64_t bdesc = umma_desc_sw128(kbuf + hh * 64, 1024) + 2 * k;
-            umma_bf16_ss(tmem_d, a, bdesc, idesc_s, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t a = umma_desc_sw128(stage + ty * 64, 1024) + 2 * k;
+              const uint64_t bdesc = umma_desc_sw128(stage + kOffK + ty * 64, 1024) + 2 * k;
+              umma_bf16_ss(tmem_d, a, bdesc, idesc_s, k != 0 ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              // head 0: its rows are 32 (j0 + 1) rows into the box and belong in quarter j0 -> start 32 rows in;
+              // head 1: quarter j0 + 1 -> start at the box's first row
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t a = umma_desc_sw128(stage + kOffQs + (hh == 0 ? 32 * 128 : 0) + hh * 64, 1024) + 2 * k;
+                const uint64_t bdesc = umma_desc_sw128(stage + kOffK + hh * 64, 1024) + 2 * k;
+                umma_bf16_ss(tmem_d, a, bdesc, idesc_s, (hh | k) != 0 ? 1u : 0u);
+              }
+            }
           }
-          umma_commit(&s_full[u & 1]);
+          umma_commit(&s_full[r_s]);
+          if (p.trace != nullptr && blockIdx.x == 0 && i_s < p.trace_items && r_s < 2)
+            p.trace[((size_t)i_s * (kThreads / 32) + 1) * 8 + 4 * r_s] = clock64();
         }
         __syncwarp();
-        if (u >= 1) issue_pv(u - 1);
+        if (++r_s == kGroups) {
+          r_s = 0;
+          ++i_s;
+        }
+      }
+      if (u >= 2) {
+        const int st = i_o % kStages;
+        mbar_wait(&p_ready[r_o], i_o & 1);
+        tc_fence_after();
+        if (p.trace != nullptr && blockIdx.x == 0 && i_o < p.trace_items && r_o < 2 && lane == 0)
+          p.trace[((size_t)i_o * (kThreads / 32) + 1) * 8 + 4 * r_o + 1] = clock64();
+        const uint32_t vbuf = smem_u32(smem + st * kStageBytes + kOffV);
+        const uint32_t tmem_u = tmem_base + r_o * kUnitCols;
+        const int ty = unit_type(i_o, r_o);
+        if (elect_one_sync()) {
+          if (ty < 2) {
+#pragma unroll
+            for (int k = 0; k < kTp / 16; ++k)
+              umma_bf16_ts(tmem_u + kOColFull, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + ty * 64 + k * 2048, 1024),
+                           idesc_o32, k != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kTp / 16; ++k)
+              umma_bf16_ts(tmem_u + kOColShort, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + k * 2048, 1024), idesc_o64,
+                           k != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_full[r_o]);
+          if (p.trace != nullptr && blockIdx.x == 0 && i_o < p.trace_items && r_o < 2)
+            p.trace[((size_t)i_o * (kThreads / 32) + 1) * 8 + 4 * r_o + 2] = clock64();
+          // last unit of the item: its boxes may be overwritten (not signalled when no later item will use the
+          // stage, so that no arrive is in flight when the CTA exits)
+          if (r_o == kGroups - 1 && i_o + kStages < my_items) umma_commit(&qkv_empty[st]);
+        }
+        __syncwarp();
+        if (++r_o == kGroups) {
+          r_o = 0;
+          ++i_o;
+        }
       }
     }
-    if (u >= 1) issue_pv(u - 1);
   } else if (warp >= 4) {
-    // ================= softmax groups: group g (8 warps) owns head hh = g of every pair; the two warps of a TMEM
-    // lane quarter split the 160 keys of a row (80 each) and exchange row maximum and row sum through shared memory,
-    // so four softmax warps per scheduler keep the MUFU pipe (one ex2 per score) busy =================
+    // ================= softmax groups: group g owns TMEM buffer g, i.e. unit g of every item =================
     const int e4 = warp - 4;
-    const int q = e4 & 3;
-    const int half = (e4 >> 2) & 1;
-    const int g = e4 >> 3;
-    const int lrow = q * 32 + lane;  // row inside the 128-query tile == TMEM lane
-    const uint32_t sw = static_cast<uint32_t>(lrow & 7);
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* pbuf = smem + kOffP + g * kPBytes + lrow * 128;
-    float* xmax = reinterpret_cast<float*>(smem + kOffExch) + g * 512;  // [2 halves][128 rows]
-    float* xsum = xmax + 256;
-    const uint32_t bar_id = 1 + g;
+    const int q = e4 & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int g = e4 >> 2;
+    const uint32_t t_unit = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kUnitCols;
     const float c = p.scale_log2e;
-    const int col_base = half * 80;
+    const int nlast = T - 128;  // valid keys of the last 32-key chunk
     int item = first;
-    int n = 0;  // units this group has processed
     for (int i = 0; i < my_items; ++i, item += step) {
       const int b = item >> 2, pair = item & 3;
-      const int h = pair * 2 + g;
-#pragma unroll 1
-      for (int mt = 0; mt < 2; ++mt, ++n) {
-        const uint32_t ph = n & 1;
-        const int row = mt * 128 + lrow;
-        const bool active = mt == 0 || q == 0;  // rows 128-159 live in lane quarter 0 of the second tile
-        mbar_wait(&s_full[g], ph);
-        tc_fence_after();
-        const uint32_t s_addr = t_lane + g * kSCols + col_base;
-        float m = -INFINITY, l = 0.f;
-        if (active) {
-          // ---- pass 1: maximum over this warp's 80 keys; all five TMEM loads in flight, one wait ----
-          {
-            uint32_t acc[80];
+      const int ty = unit_type(i, g);
+      const int j0 = short_quarter(i);
+      const bool active = ty < 2 || q == j0 || q == j0 + 1;
+      const int hh = ty < 2 ? ty : q - j0;
+      const int h = pair * 2 + hh;
+      const int row = ty < 2 ? q * 32 + lane : 128 + lane;
+      const uint32_t ocol = ty < 2 ? kOColFull : kOColShort + 32 * hh;
+      const uint32_t ph = i & 1;
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      long long* tr = (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < p.trace_items)
+                          ? p.trace + ((size_t)i * (kThreads / 32) + warp) * 8 : nullptr;
+      if (tr) tr[0] = clock64();
+      float l = 0.f;
+      if (active) {
+        // ---- pass 1: row maximum over the valid keys; chunk c + 1 is on its way while chunk c is reduced ----
+        uint32_t sb[2][32];
+        float m0 = -INFINITY, m1 = -INFINITY;
+        tmem_ld_32x32b_x32(t_unit, sb[0]);
 #pragma unroll
-            for (int cb = 0; cb < 5; ++cb) tmem_ld_32x32b_x16(s_addr + cb * 16, acc + cb * 16);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 80; ++e) {
-              const float v = __uint_as_float(acc[e]);
-              if (half == 0 || col_base + e < p.T) m = fmaxf(m, v);  // T > 128: keys 0-79 are always valid
-            }
-          }
-          xmax[half * 128 + lrow] = m;
-        }
-        bar_sync(bar_id, 256);
-        if (active) {
-          m = fmaxf(m, xmax[(half ^ 1) * 128 + lrow]) * c;
-          // ---- pass 2: exponentials, partial row sum, bf16 probabilities into the A-operand layout; the next
-          // block's scores are on their way out of TMEM while this block is computed ----
-          uint32_t accb[2][16];
-          tmem_ld_32x32b_x16(s_addr, accb[0]);
-#pragma unroll
-          for (int cb = 0; cb < 5; ++cb) {
-            const uint32_t(&acc)[16] = accb[cb & 1];
-            tmem_ld_wait();
-            if (cb < 4) tmem_ld_32x32b_x16(s_addr + (cb + 1) * 16, accb[(cb + 1) & 1]);
-            uint32_t packed[8];
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              float p0 = ex2f(fmaf(__uint_as_float(acc[e]), c, -m));
-              float p1 = ex2f(fmaf(__uint_as_float(acc[e + 1]), c, -m));
-              if (half == 1) {
-                if (col_base + cb * 16 + e >= p.T) p0 = 0.f;
-                if (col_base + cb * 16 + e + 1 >= p.T) p1 = 0.f;
-              }
-              l += p0 + p1;
-              packed[e >> 1] = pack_bf16x2(p0, p1);
-            }
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              const int col0 = col_base + cb * 16 + v * 8;
-              const uint32_t piece = static_cast<uint32_t>((col0 & 63) >> 3) ^ sw;
-              *reinterpret_cast<uint4*>(pbuf + (col0 >> 6) * kPChunkBytes + piece * 16) =
-                  make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-            }
-          }
-          xsum[half * 128 + lrow] = l;
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(&p_ready[g]);
-        // ---- output: O / l -> 'b n (h d)', 16 of the 32 columns per warp ----
-        mbar_wait(&o_full[g], ph);
-        tc_fence_after();
-        bar_sync(bar_id, 256);  // both halves' partial sums are visible
-        if (active) {
-          const float inv = 1.0f / (xsum[lrow] + xsum[128 + lrow]);
-          uint32_t o[16];
-          tmem_ld_32x32b_x16(t_lane + kOBase + g * 32 + half * 16, o);
+        for (int cb = 0; cb < 5; ++cb) {
+          const uint32_t(&s)[32] = sb[cb & 1];
           tmem_ld_wait();
-          if (row < p.T) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * p.T + row) * (kHeads * 32) + h * 32 + half * 16);
+          if (cb < 4) tmem_ld_32x32b_x32(t_unit + (cb + 1) * 32, sb[(cb + 1) & 1]);
+          if (cb < 4) {
 #pragma unroll
-            for (int v = 0; v < 2; ++v)
-              dst[v] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * v]) * inv, __uint_as_float(o[8 * v + 1]) * inv),
-                                  pack_bf16x2(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv),
-                                  pack_bf16x2(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv),
-                                  pack_bf16x2(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv));
+            for (int e = 0; e < 32; e += 4) {
+              m0 = max3f(m0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+              m1 = max3f(m1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < nlast) m0 = fmaxf(m0, __uint_as_float(s[e]));
           }
         }
-        tc_fence_before();
+        const float mc = fmaxf(m0, m1) * c;
+        if (tr) tr[1] = clock64();
+        // ---- pass 2: exponentials, row sum, bf16 probabilities over the consumed score columns ----
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        tmem_ld_32x32b_x32(t_unit, sb[0]);
+#pragma unroll
+        for (int cb = 0; cb < 5; ++cb) {
+          const uint32_t(&s)[32] = sb[cb & 1];
+          tmem_ld_wait();
+          if (cb < 4) tmem_ld_32x32b_x32(t_unit + (cb + 1) * 32, sb[(cb + 1) & 1]);
+          uint32_t packed[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float pe[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              if (cb < 4 || (kTokens > 0 && e + x < kTokens - 128)) {
+                pe[x] = ex2f(fmaf(__uint_as_float(s[e + x]), c, -mc));
+              } else if (kTokens > 0) {
+                pe[x] = 0.f;  // padded key: V's row is zero and so is the probability
+              } else {
+                pe[x] = e + x < nlast ? ex2f(fmaf(__uint_as_float(s[e + x]), c, -mc)) : 0.f;
+              }
+            }
+            l0 += pe[0];
+            l1 += pe[1];
+            l2 += pe[2];
+            l3 += pe[3];
+            packed[e >> 1] = pack_bf16x2(pe[0], pe[1]);
+            packed[(e >> 1) + 1] = pack_bf16x2(pe[2], pe[3]);
+          }
+          // keys 32 cb .. 32 cb + 31 -> columns 16 cb .. 16 cb + 15: inside the score columns already consumed
+          tmem_st_32x32b_x16(t_unit + cb * 16, packed);
+        }
+        l = (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
       }
+      tc_fence_before();
+      mbar_arrive(&p_ready[g]);
+      if (tr) tr[2] = clock64();
+      // ---- output: O / l -> 'b n (h d)' ----
+      mbar_wait(&o_full[g], ph);
+      tc_fence_after();
+      if (tr) tr[3] = clock64();
+      if (active) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_unit + ocol, o);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&buf_free[g]);  // the registers hold the output: the MMA warp may reuse the buffer
+        if (row < T) {
+          const float inv = 1.0f / l;
+          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * T + row) * (kHeads * 32) + h * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            dst[v] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * v]) * inv, __uint_as_float(o[8 * v + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv));
+        }
+      } else {
+        tc_fence_before();
+        mbar_arrive(&buf_free[g]);
+      }
+      if (tr) tr[4] = clock64();
     }
   }
 
@@ -305,24 +410,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQkv, const AttnTcParam
 
 bool attention_tc_supported(int T) { return T > 128 && T <= kTp; }
 
+int attention_tc_warps() { return kThreads / 32; }
+
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, float scale_log2e, int num_sms,
-                        cudaStream_t stream, int reverse) {
+                        cudaStream_t stream, int reverse, long long* trace, int trace_items) {
   if (!attention_tc_supported(T)) {
     set_error("attention_tc: built for 129..160 tokens, got %d", T);
     return -1;
   }
   static bool configured = false;
   if (!configured) {
-    HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    HGR_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_tc_kernel<145>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  CUtensorMap tm;
+  CUtensorMap tmQ, tmKV, tmQs;
   {
-    const uint64_t dims[5] = {768, (uint64_t)T, (uint64_t)B, 1, 1};
     const uint64_t row = 768 * 2;
+    const uint64_t dims[5] = {768, (uint64_t)T, (uint64_t)B, 1, 1};
     const uint64_t strides[4] = {row, row * T, row * T * B, row * T * B};
-    const uint32_t box[5] = {64, (uint32_t)kTp, 1, 1, 1};
-    if (int r = make_tensor_map_bf16(&tm, qkv, 5, dims, strides, box)) return r;
+    const uint32_t box_q[5] = {64, 128, 1, 1, 1};
+    const uint32_t box_kv[5] = {64, (uint32_t)kTp, 1, 1, 1};
+    if (int r = make_tensor_map_bf16(&tmQ, qkv, 5, dims, strides, box_q)) return r;
+    if (int r = make_tensor_map_bf16(&tmKV, qkv, 5, dims, strides, box_kv)) return r;
+    // the same tensor seen from token 128 on: T - 128 rows per image, everything else is out of bounds (= zero)
+    const uint64_t dims_s[5] = {768, (uint64_t)(T - 128), (uint64_t)B, 1, 1};
+    if (int r = make_tensor_map_bf16(&tmQs, qkv + (size_t)128 * 768, 5, dims_s, strides, box_kv)) return r;
   }
   AttnTcParams p;
   p.out = out;
@@ -330,10 +444,15 @@ int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int
   p.T = T;
   p.scale_log2e = scale_log2e;
   p.reverse = reverse;
+  p.trace = trace;
+  p.trace_items = trace_items;
   const int items = B * (kHeads / 2);
   const int grid = items < num_sms ? items : num_sms;
   if (grid <= 0) return 0;
-  HGR_CHECK_CUDA(launch_pdl(attention_tc_kernel, dim3(grid), dim3(kThreads), kSmemBytes, stream, tm, p));
+  if (T == 145)
+    HGR_CHECK_CUDA(launch_pdl(attention_tc_kernel<145>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, tmQs, p));
+  else
+    HGR_CHECK_CUDA(launch_pdl(attention_tc_kernel<0>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmQ, tmKV, tmQs, p));
   return 0;
 }
 

@@ -70,7 +70,12 @@ int conv_chain_prefetch() {
 }
 
 bool attention_tc_enabled() {
-  static const bool on = env_flag("HGR_ATTN_TC", false);  // measured 0.17-0.18 ms per layer against 0.16 ms (mma.sync)
+  static const bool on = env_flag("HGR_ATTN_TC", true);
+  return on;
+}
+
+bool pose_head_tc_enabled() {
+  static const bool on = env_flag("HGR_POSE_TC", true);
   return on;
 }
 

@@ -37,12 +37,16 @@ bool zigzag_enabled();
 bool cluster_enabled();
 // HGR_ATTN_ONLINE=0 falls back to the strip-in-registers attention kernels when no probabilities are returned.
 bool attention_online_enabled();
-// HGR_ATTN_TC=1: the 145-token attention without probability output runs on the tcgen05 kernel (attention_tc.cu)
-// instead of the mma.sync kernels.  Parity-green but not faster yet (0.17-0.18 vs 0.16 ms per layer), so opt-in.
+// HGR_ATTN_TC=0: the 129..160-token attention without probability output falls back from the tcgen05 kernel
+// (attention_tc.cu, the default) to the mma.sync kernels of attention.cu.
 bool attention_tc_enabled();
+// token counts the attention kernels can hold in one CTA's shared memory (checked when a plan is created)
+int attention_max_tokens();
+bool attention_tokens_supported(int T);
 bool attention_tc_supported(int T);
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, float scale_log2e, int num_sms,
-                        cudaStream_t stream, int reverse);
+                        cudaStream_t stream, int reverse, long long* trace = nullptr, int trace_items = 0);
+int attention_tc_warps();
 // HGR_ATTN_CPASYNC=0: the online-softmax attention kernel stages Q, K, V through registers instead of cp.async.
 bool attention_cp_async_enabled();
 // HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
@@ -176,8 +180,17 @@ int launch_cls_head(const __nv_bfloat16* tokens, const float* gamma, const float
                     const float* bias, void* logits, int out_dtype, int B, int T, int num_classes,
                     cudaStream_t stream);
 
+// Pose head.  heatmaps may be NULL when preds / maxvals are given (keypoints only: the heatmaps never reach HBM);
+// preds / maxvals may be NULL (heatmaps only).  The tcgen05 kernel (pose_head_tc.cu) serves F <= 20 unless
+// HGR_POSE_TC=0; otherwise pose_head.cu writes the heatmaps and, if asked, tail.cu decodes them.
 int launch_pose_head(const __nv_bfloat16* tokens, const __nv_bfloat16* w /*[Jpad][256]*/, const float* bias,
-                     void* heatmaps, int out_dtype, int B, int F, int J, cudaStream_t stream);
+                     void* heatmaps, int out_dtype, int B, int F, int J, cudaStream_t stream, float* preds = nullptr,
+                     float* maxvals = nullptr);
+bool pose_head_tc_enabled();
+bool pose_head_tc_supported(int F, int J);
+int launch_pose_head_tc(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const float* bias, void* heatmaps,
+                        int out_dtype, float* preds, float* maxvals, int B, int F, int J, int num_sms,
+                        cudaStream_t stream);
 
 int launch_get_max_preds(const void* heatmaps, int dtype, long long rows, int hw, int width, float* preds,
                          float* maxvals, cudaStream_t stream);

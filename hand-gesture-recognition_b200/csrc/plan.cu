@@ -551,6 +551,8 @@ struct hgr_plan {
     void* heat;
     void* attn;
     int out_dtype;
+    float* preds = nullptr;    // hgr_forward_keypoints: decoded keypoints instead of / beside the heatmaps
+    float* maxvals = nullptr;
   };
   struct Step {
     std::string name;
@@ -598,6 +600,14 @@ int check_config(int S, int J, int C) {
   }
   if (J < 1 || J > 24 || C < 1 || C > 4096) {
     set_error("num_joints %d / num_classes %d unsupported", J, C);
+    return -1;
+  }
+  // the attention kernels keep Q, K and V of one (image, head) in shared memory: refuse a token count they cannot
+  // hold HERE, not in the middle of a forward whose backbone has already been launched
+  const int T = (S / 16) * (S / 16) + 1;
+  if (!attention_tokens_supported(T)) {
+    set_error("image_size %d unsupported: %d tokens exceed the attention kernel's shared-memory limit (max %d)", S, T,
+              attention_max_tokens());
     return -1;
   }
   return 0;
@@ -831,7 +841,7 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
       (double)rows * kDim * 2 + dB * J * (dS / 4) * (dS / 4) * 2, [pl, B](cudaStream_t st, const Io& io) {
         return launch_pose_head(pl->bp("tokens"), pl->pp<__nv_bfloat16>("decoder.simple_decoder.1.w"),
                                 pl->pp<float>("decoder.simple_decoder.1.bias"), io.heat, io.out_dtype, B, pl->F, pl->J,
-                                st);
+                                st, io.preds, io.maxvals);
       });
   *out = pl;
   return 0;
@@ -894,6 +904,29 @@ int hgr_forward(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d
   return 0;
 }
 
+int hgr_keypoints_fused(int S, int J) {
+  if (check_config(S, J, 1)) return -1;
+  return pose_head_tc_enabled() && pose_head_tc_supported(S / 16, J) ? 1 : 0;
+}
+
+int hgr_forward_keypoints(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
+                          float* d_preds, float* d_maxvals, int out_dtype, void* stream_v) {
+  if (!d_preds || !d_maxvals) {
+    set_error("hgr_forward_keypoints: null keypoint outputs");
+    return -1;
+  }
+  // d_heatmaps may be NULL here; the argument check only needs a non-null placeholder
+  if (int rc = check_forward_args(pl, d_x, x_dtype, batch, d_logits, d_heatmaps ? d_heatmaps : d_preds, out_dtype))
+    return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  hgr_plan::Io io{d_x, x_dtype, d_logits, d_heatmaps, nullptr, out_dtype};
+  io.preds = d_preds;
+  io.maxvals = d_maxvals;
+  for (const auto& step : pl->steps)
+    if (int rc = step.run(st, io)) return rc;
+  return 0;
+}
+
 int hgr_forward_profile(hgr_plan_t* pl, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
                         void* d_attn, int out_dtype, void* stream_v, float* h_ms, int capacity) {
   if (int rc = check_forward_args(pl, d_x, x_dtype, batch, d_logits, d_heatmaps, out_dtype)) return rc;
@@ -923,6 +956,15 @@ int hgr_forward_host(hgr_plan_t* pl, const void* h_x, int x_dtype, int batch, vo
                      int out_dtype, void* stream_v) {
   if (!pl || !h_x || !h_logits || !h_heatmaps) {
     set_error("hgr_forward_host: null argument");
+    return -1;
+  }
+  // validate BEFORE sizing any copy from the arguments: a smaller batch than the plan's would over-read h_x
+  if (batch != pl->B) {
+    set_error("hgr_forward_host: batch %d does not match the plan's batch %d", batch, pl->B);
+    return -1;
+  }
+  if ((x_dtype != DT_F32 && x_dtype != DT_BF16) || (out_dtype != DT_F32 && out_dtype != DT_BF16)) {
+    set_error("hgr_forward_host: dtype must be HGR_F32 or HGR_BF16");
     return -1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
@@ -1054,10 +1096,29 @@ int hgr_attention_tc(const void* d_qkv, void* d_out, int B, int T, void* stream)
                              static_cast<cudaStream_t>(stream), 0);
 }
 
+int hgr_attention_tc_trace(const void* d_qkv, void* d_out, int B, int T, long long* d_trace, int trace_items,
+                           int* warps, void* stream) {
+  if (warps) *warps = attention_tc_warps();
+  if (!d_trace) return 0;  // size query
+  return launch_attention_tc(static_cast<const __nv_bfloat16*>(d_qkv), static_cast<__nv_bfloat16*>(d_out), B, T,
+                             0.17677669529663687f * 1.4426950408889634f, device_sm_count(),
+                             static_cast<cudaStream_t>(stream), 0, d_trace, trace_items);
+}
+
 int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
                  const float* d_bias, void* d_logits, int out_dtype, int B, int T, int num_classes, void* stream) {
   return launch_cls_head(static_cast<const __nv_bfloat16*>(d_tokens), d_gamma, d_beta, d_w, d_bias, d_logits,
                          out_dtype, B, T, num_classes, static_cast<cudaStream_t>(stream));
+}
+
+int hgr_pose_head_decode(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps, int out_dtype,
+                         float* d_preds, float* d_maxvals, int B, int F, int J, void* stream) {
+  if (!d_preds || !d_maxvals) {
+    set_error("hgr_pose_head_decode: null keypoint outputs");
+    return -1;
+  }
+  return launch_pose_head(static_cast<const __nv_bfloat16*>(d_tokens), static_cast<const __nv_bfloat16*>(d_w), d_bias,
+                          d_heatmaps, out_dtype, B, F, J, static_cast<cudaStream_t>(stream), d_preds, d_maxvals);
 }
 
 int hgr_pose_head(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps, int out_dtype, int B,

@@ -20,6 +20,7 @@
 // contiguous and every fragment is one conflict-free vector load.
 // Heatmaps are written NCHW, the layout get_max_preds and the reference's
 // callers expect.
+#include "gemm_ops.h"
 #include "hgr_internal.h"
 #include "ptx.cuh"
 
@@ -236,13 +237,26 @@ int launch_pose_f(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const flo
 }  // namespace
 
 int launch_pose_head(const __nv_bfloat16* tokens, const __nv_bfloat16* w, const float* bias, void* heatmaps,
-                     int out_dtype, int B, int F, int J, cudaStream_t stream) {
+                     int out_dtype, int B, int F, int J, cudaStream_t stream, float* preds, float* maxvals) {
   if (J > kJPad || J < 1) {
     set_error("pose_head: unsupported J=%d", J);
     return -1;
   }
-  if (out_dtype == DT_F32) return launch_pose_f<float>(tokens, w, bias, static_cast<float*>(heatmaps), B, F, J, stream);
-  return launch_pose_f<__nv_bfloat16>(tokens, w, bias, static_cast<__nv_bfloat16*>(heatmaps), B, F, J, stream);
+  if (pose_head_tc_enabled() && pose_head_tc_supported(F, J))
+    return launch_pose_head_tc(tokens, w, bias, heatmaps, out_dtype, preds, maxvals, B, F, J, device_sm_count(), stream);
+  // mma.sync kernel: it always writes the heatmaps; the decode, if asked for, is a second launch over them
+  if (heatmaps == nullptr) {
+    set_error("pose_head: the keypoints-only mode needs the tcgen05 kernel (F <= 20, HGR_POSE_TC not 0)");
+    return -1;
+  }
+  int rc;
+  if (out_dtype == DT_F32)
+    rc = launch_pose_f<float>(tokens, w, bias, static_cast<float*>(heatmaps), B, F, J, stream);
+  else
+    rc = launch_pose_f<__nv_bfloat16>(tokens, w, bias, static_cast<__nv_bfloat16*>(heatmaps), B, F, J, stream);
+  if (rc == 0 && preds != nullptr)
+    rc = launch_get_max_preds(heatmaps, out_dtype, (long long)B * J, 16 * F * F, 4 * F, preds, maxvals, stream);
+  return rc;
 }
 
 }  // namespace hgr

@@ -204,6 +204,12 @@ int check_train_config(int S, int J, int C, int B) {
     set_error("training: num_joints %d (1..24) / num_classes %d (1..128) / batch %d (>= 2) unsupported", J, C, B);
     return -1;
   }
+  const int T = (S / 16) * (S / 16) + 1;
+  if (!attention_tokens_supported(T)) {
+    set_error("image_size %d unsupported: %d tokens exceed the attention kernel's shared-memory limit (max %d)", S, T,
+              attention_max_tokens());
+    return -1;
+  }
   return 0;
 }
 
@@ -527,6 +533,13 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
   pl->d_jobs = reinterpret_cast<PackJob*>(pl->bp("packjobs"));
   if (cudaMemcpy(pl->d_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error("train plan: copying the pack job table failed");
+    delete pl;
+    return -2;
+  }
+  // the memsets and the copy above ran on the legacy default stream, the first forward runs on the caller's
+  // (possibly non-blocking) stream: make them complete before anyone can launch against this plan
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("train plan: device synchronisation after initialisation failed");
     delete pl;
     return -2;
   }

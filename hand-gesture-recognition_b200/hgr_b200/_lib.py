@@ -30,6 +30,8 @@ SIGNATURES = {
     "hgr_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _vp, _vp, _sz]),
     "hgr_plan_destroy": (None, [_vp]),
     "hgr_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "hgr_keypoints_fused": (_i, [_i, _i]),
+    "hgr_forward_keypoints": (_i, [_vp, _vp, _i, _i, _vp, _vp, _fp, _fp, _i, _vp]),
     "hgr_forward_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "hgr_plan_buffer": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "hgr_plan_launches": (_i, [_vp, _i]),
@@ -46,8 +48,10 @@ SIGNATURES = {
     "hgr_layernorm": (_i, [_vp, _vp, _fp, _fp, _ll, _vp]),
     "hgr_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "hgr_attention_tc": (_i, [_vp, _vp, _i, _i, _vp]),
+    "hgr_attention_tc_trace": (_i, [_vp, _vp, _i, _i, _vp, _i, C.POINTER(_i), _vp]),
     "hgr_cls_head": (_i, [_vp, _fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_pose_head": (_i, [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp]),
+    "hgr_pose_head_decode": (_i, [_vp, _vp, _fp, _vp, _i, _fp, _fp, _i, _i, _i, _vp]),
     "hgr_get_max_preds": (_i, [_vp, _i, _i, _i, _i, _i, _fp, _fp, _vp]),
     "hgr_crop_normalize": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hgr_pose_accuracy": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_double, _vp, _vp, _vp, _vp]),

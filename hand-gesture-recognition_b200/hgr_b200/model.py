@@ -52,6 +52,22 @@ class ResBasicBlock(_Container):
         self.cv2 = Conv(c2, c2, 3, 1, act=False)
 
 
+class ResBottleneck(_Container):
+    """The reference's 1x1 -> 3x3 -> 1x1 bottleneck (model/gelan.py:90-121): same constructor and the same
+    `cv1` / `cv2` / `cv3` parameter tree, so that code which builds or loads one keeps working.  `gelan_spec`
+    (gelan.py:148-151) never instantiates it and `MultiTaskNet` hard-codes 'small' (multitasknet.py:12), so no
+    kernel path exists for it: like every container here it holds parameters and raises when called."""
+
+    def __init__(self, c1, c2, shortcut=True, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)  # hidden channels
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c_, 3, 1)
+        self.cv3 = Conv(c_, c2, 1, 1, act=False)
+        self.add = bool(shortcut and c1 == c2)
+        self.downsample = None  # the reference only creates one when add and c1 != c2, which cannot both hold
+
+
 class GELANBlock(_Container):
     def __init__(self, c_in, c_out, c_hid1, c_hid2, nblocks=1):
         super().__init__()
@@ -203,7 +219,15 @@ class MultiTaskNet(nn.Module):
 
     # ---- weight packing ---------------------------------------------------
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """(storage address, version counter) of every parameter and buffer: changes when a tensor is written in
+        place (load_state_dict, optimiser step), re-homed (.to()) or replaced (load_state_dict(assign=True)).
+        The module tree is fixed, so the per-module `_parameters` / `_buffers` dicts are collected once and only
+        their current values are read here (~50 us instead of ~500 us for a state_dict walk per forward)."""
+        dicts = self.__dict__.get("_sig_dicts")
+        if dicts is None:
+            dicts = [d for m in self.modules() for d in (m._parameters, m._buffers) if d]
+            self.__dict__["_sig_dicts"] = dicts
+        return tuple((t.data_ptr(), t._version) for d in dicts for t in d.values() if t is not None)
 
     def _packed_params(self, device) -> torch.Tensor:
         sig = (device, self._signature())

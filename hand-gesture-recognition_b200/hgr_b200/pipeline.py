@@ -4,9 +4,11 @@ reference detect.py:92-117,140-155 does, per frame and per hand:
     uint8 BGR crop -> /255, mean/std, CHW -> classifier -> argmax(label), get_max_preds(heatmap)
 This class does the same for a whole batch of crops that live in HOST memory:
 pinned uint8 crops are copied to the device, normalised (crop_normalize
-kernel), run through the MultiTaskNet plan, decoded on the device
-(get_max_preds kernel) and only the logits, keypoints and their confidences
-travel back - 19*4 + 21*3*4 bytes per hand instead of a 194 KB heatmap.
+kernel), run through the MultiTaskNet plan with the keypoint decode fused into
+the pose head's epilogue (hgr_forward_keypoints: the fp32 heatmaps - 198 MB per
+1024 crops - are never written, the decode is bit-identical to get_max_preds on
+them) and only the logits, keypoints and their confidences travel back -
+19*4 + 21*3*4 bytes per hand instead of a 194 KB heatmap.
 
 Two lanes (copy stream + buffers + plan each) are used alternately so that the
 host->device copy of batch i+1 and the device->host copy of batch i-1 overlap
@@ -33,7 +35,10 @@ class _Lane:
         self.d_crops = torch.empty(batch, s, s, 3, dtype=torch.uint8, device=device)
         self.d_x = torch.empty(batch, 3, s, s, dtype=dtype, device=device)
         self.d_logits = torch.empty(batch, model.num_classes, dtype=torch.float32, device=device)
-        self.d_heat = torch.empty(batch, model.num_joints, s // 4, s // 4, dtype=torch.float32, device=device)
+        # only when the fused decode is unavailable (image_size > 320 or HGR_POSE_TC=0) do heatmaps reach memory
+        fused = _lib.load().hgr_keypoints_fused(s, model.num_joints) == 1
+        self.d_heat = None if fused else torch.empty(batch, model.num_joints, s // 4, s // 4, dtype=torch.float32,
+                                                     device=device)
         self.d_preds = torch.empty(batch, model.num_joints, 2, dtype=torch.float32, device=device)
         self.d_maxvals = torch.empty(batch, model.num_joints, 1, dtype=torch.float32, device=device)
         self.h_logits = torch.empty(batch, model.num_classes, dtype=torch.float32).pin_memory()
@@ -57,20 +62,36 @@ class HandPipeline:
             self.lanes = [_Lane(model, batch, self.device, compute_dtype) for _ in range(lanes)]
             self.compute = torch.cuda.Stream(self.device)
         self._next = 0
+        self._params = self.lanes[0].plan.params
         self.h2d_bytes = self.lanes[0].h_crops.numel()
         self.d2h_bytes = 4 * (self.lanes[0].h_logits.numel() + self.lanes[0].h_preds.numel()
                               + self.lanes[0].h_maxvals.numel())
-        # crop_normalize + the plan's launches + get_max_preds
-        self.launches_per_batch = self.lanes[0].plan.launches() + 2
+        # crop_normalize + the plan's launches (the keypoint decode is part of the last one)
+        self.launches_per_batch = self.lanes[0].plan.launches() + 1
+
+    def _refresh_plans(self):
+        """The lanes' plans point into the weights packed when they were built.  After load_state_dict / an optimiser
+        step / .to() the model re-packs: rebuild the plans against the new block (the old block stays alive until then,
+        each plan holds a reference to it)."""
+        params = self.model._packed_params(self.device)
+        if params is not self._params:
+            if any(ln.busy for ln in self.lanes):
+                raise RuntimeError("the model's parameters changed while a batch is in flight; collect() it first")
+            m = self.model
+            with torch.cuda.device(self.device):
+                torch.cuda.current_stream(self.device).synchronize()
+                self.compute.synchronize()
+                for ln in self.lanes:
+                    ln.plan = _Plan(m.image_size[0], m.num_joints, m.num_classes, self.batch, params)
+            self._params = params
 
     def _forward_decode(self, ln, dt, st):
         """forward + keypoint decode of lane `ln` on the compute stream `st`."""
-        lib, m = _lib.load(), self.model
-        s = m.image_size[0]
-        _lib.check(lib.hgr_forward(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
-                                   ln.d_heat.data_ptr(), None, _lib.F32, st), "hgr_forward")
-        _lib.check(lib.hgr_get_max_preds(ln.d_heat.data_ptr(), _lib.F32, self.batch, m.num_joints, s // 4, s // 4,
-                                         ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), st), "hgr_get_max_preds")
+        lib = _lib.load()
+        _lib.check(lib.hgr_forward_keypoints(ln.plan.handle, ln.d_x.data_ptr(), dt, self.batch, ln.d_logits.data_ptr(),
+                                             ln.d_heat.data_ptr() if ln.d_heat is not None else None,
+                                             ln.d_preds.data_ptr(), ln.d_maxvals.data_ptr(), _lib.F32, st),
+                   "hgr_forward_keypoints")
 
     def _copy_back(self, ln):
         """results device -> pinned host on the lane's copy stream, after the compute stream is done with them."""
@@ -84,6 +105,7 @@ class HandPipeline:
     def submit(self, crops_u8: torch.Tensor, after: torch.cuda.Event | None = None) -> int:
         """Queue one batch of (B, S, S, 3) uint8 host crops; returns the lane to collect from."""
         lib = _lib.load()
+        self._refresh_plans()
         i = self._next
         self._next = (self._next + 1) % len(self.lanes)
         ln = self.lanes[i]
@@ -119,6 +141,7 @@ class HandPipeline:
         from .ops import box_to_affine, invert_affine
         import numpy as np
         lib = _lib.load()
+        self._refresh_plans()
         i = self._next
         self._next = (self._next + 1) % len(self.lanes)
         ln = self.lanes[i]
@@ -131,6 +154,10 @@ class HandPipeline:
         m = self.model
         s = m.image_size[0]
         idx = np.zeros(self.batch, dtype=np.int32) if frame_index is None else np.asarray(frame_index, dtype=np.int32)
+        # the kernel indexes the frames buffer with these: a bad index would read past its end (ops.crop_warp_normalize
+        # checks the same)
+        if idx.shape != (self.batch,) or (idx < 0).any() or (idx >= frames_u8.shape[0]).any():
+            raise ValueError(f"frame_index must hold {self.batch} indices in [0, {frames_u8.shape[0]})")
         inv = np.stack([invert_affine(box_to_affine(b, s)) for b in boxes])
         dt = _lib.F32 if self.dtype == torch.float32 else _lib.BF16
         with torch.cuda.device(self.device):

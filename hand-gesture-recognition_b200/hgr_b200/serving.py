@@ -14,8 +14,10 @@
 Latency mode: `detect.py` classifies one or two hand crops per camera frame, where the forward is bound by its 38
 kernel launches and the Python in front of them, not by the GPU.  Batches up to `graph_max_batch` are therefore
 captured once into a CUDA graph over static device buffers and replayed (`cuda_graph=True`, the default): a `run()` is
-then one H2D copy, one graph launch and two D2H copies (tools/serving_latency.py measures both modes).  The graph
-holds the packed weights of the moment it was captured - call `invalidate()` after changing the model's parameters.
+then one H2D copy, one graph launch and two D2H copies (tools/serving_latency.py measures both modes).  A captured
+graph holds raw pointers into the plan's workspace and the packed weights of the moment it was captured; the session
+keeps both alive next to the graph and re-captures by itself when the model's parameters have changed since
+(`load_state_dict`, an optimiser step, `.to()`), so a replay can neither read freed memory nor stale weights.
 """
 from __future__ import annotations
 
@@ -38,7 +40,9 @@ class ClassifierSession:
         self.model = model.eval()
         self.device = p.device
         self.cuda_graph, self.graph_max_batch = bool(cuda_graph), int(graph_max_batch)
-        self._graphs = {}  # batch -> (graph, static input, static logits, static heatmaps, pinned host copies)
+        # batch -> (graph, static input, static logits, static heatmaps, pinned host copies, plan, packed weights):
+        # the last two are what the graph's kernels point into, kept here so that they outlive the model's own cache
+        self._graphs = {}
         s = model.image_size[0]
         self._inputs = [_Arg(input_name, ["batch", 3, s, s], "tensor(float)")]
         self._outputs = [_Arg(output_names[0], ["batch", model.num_classes], "tensor(float)"),
@@ -68,7 +72,7 @@ class ClassifierSession:
         return [outs[n] for n in wanted]
 
     def invalidate(self):
-        """Drop the captured graphs (they replay the weights packed at capture time)."""
+        """Drop the captured graphs (done automatically when the model's parameters change)."""
         self._graphs.clear()
 
     def _forward(self, x):
@@ -97,13 +101,20 @@ class ClassifierSession:
             h_x = torch.empty(xs.shape, dtype=torch.float32).pin_memory()
             h_cls = torch.empty(cls.shape, dtype=torch.float32).pin_memory()
             h_hm = torch.empty(hm.shape, dtype=torch.float32).pin_memory()
-        return graph, xs, cls, hm, h_x, h_cls, h_hm
+            plan = self.model.plan_for(b, self.device)
+        return graph, xs, cls, hm, h_x, h_cls, h_hm, plan, plan.params
 
     def _run_graph(self, x):
         b = x.shape[0]
-        if b not in self._graphs:
-            self._graphs[b] = self._capture(b)
-        graph, xs, cls, hm, h_x, h_cls, h_hm = self._graphs[b]
+        # the model re-packs (and drops its plans) when a parameter's storage or version changed: a graph captured
+        # against the previous pack is stale then, whatever batch size it was captured for
+        params = self.model._packed_params(self.device)
+        entry = self._graphs.get(b)
+        if entry is None or entry[-1] is not params:
+            if entry is not None:
+                self._graphs.clear()
+            entry = self._graphs[b] = self._capture(b)
+        graph, xs, cls, hm, h_x, h_cls, h_hm = entry[:7]
         with torch.cuda.device(self.device):
             h_x.copy_(torch.from_numpy(x))
             xs.copy_(h_x, non_blocking=True)

@@ -49,6 +49,7 @@ class TrainPlan:
                                              state.pos_embedding.data_ptr(), self.workspace.data_ptr(), nbytes),
                    "hgr_train_plan_create")
         self.handle = handle
+        self.generation = 0  # bumped by every train-mode forward: the activations of the previous one are gone
 
     def buffer(self, name: str) -> torch.Tensor:
         """bf16 view of a named workspace buffer (activations, gradients, probabilities) for tests / attnmap."""
@@ -152,6 +153,7 @@ def forward_train(state: TrainState, x: torch.Tensor, update_running: bool = Tru
         _lib.check(_lib.load().hgr_train_forward(plan.handle, x.data_ptr(), _dt(x), logits.data_ptr(), heat.data_ptr(),
                                                  BN_MOMENTUM if update_running else -1.0, _stream(x.device)),
                    "hgr_train_forward")
+        plan.generation += 1
         if update_running:
             state.num_batches_tracked += 1
     return logits, heat, plan
@@ -170,13 +172,18 @@ class _TrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, *params):
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("the B200 MultiTaskNet does not compute a gradient for its input "
+                               "(x.requires_grad is set); detach the input")
         state = train_state(model, x.device)
         logits, heat, plan = forward_train(state, x)
-        ctx.state, ctx.plan, ctx.x = state, plan, x
+        ctx.state, ctx.plan, ctx.x, ctx.generation = state, plan, x, plan.generation
         attn = None
         if model.return_attention:
             t = model.image_size[0] // 16 * (model.image_size[0] // 16) + 1
-            attn = plan.buffer(f"l{3}.probs")[..., :t].to(x.dtype)  # rows are stored with a padded pitch
+            # rows are stored with a padded pitch; ALWAYS a copy (a bf16 `.to(bf16)` would be a live view of the
+            # workspace that the next forward overwrites)
+            attn = plan.buffer(f"l{3}.probs")[..., :t].to(x.dtype, copy=True)
             ctx.mark_non_differentiable(attn)
         if x.dtype != torch.float32:
             logits, heat = logits.to(x.dtype), heat.to(x.dtype)
@@ -185,6 +192,10 @@ class _TrainFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, dheat, _dattn):
         state, plan, x = ctx.state, ctx.plan, ctx.x
+        if plan.generation != ctx.generation:
+            raise RuntimeError("backward of a train-mode forward whose activations are gone: another train-mode forward "
+                               "of the same batch size ran in between (the activations live in one workspace per batch "
+                               "size); run backward before the next forward, or use .eval() for the extra call")
         m = state.model
         if dlogits is None:
             dlogits = torch.zeros(x.shape[0], m.num_classes, device=x.device)
@@ -225,6 +236,33 @@ def loss_and_grads(logits, heat, labels, target, target_weight, cls_weight=0.001
     return loss3, dlogits, dheat
 
 
+def broadcast_from_rank0_(tensors, group=None) -> int:
+    """Make every rank start from rank 0's values (parameters, BatchNorm statistics, optimiser moments), like
+    DistributedDataParallel does at construction: identical updates only keep replicas identical if they START
+    identical, and a rank-dependent seed or a checkpoint loaded on rank 0 only would otherwise diverge silently.
+    Returns the world size."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+    return world
+
+
+def replicas_in_sync(flat: torch.Tensor, group=None) -> bool:
+    """True when every rank holds the same values in `flat` (checked with MIN / MAX all-reduces of a checksum)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return True
+    v = flat.double()
+    chk = torch.stack([v.sum(), (v * v).sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool(torch.equal(lo, hi))
+
+
 def allreduce_sum_(flat: torch.Tensor, group=None) -> int:
     """SUM all-reduce of the flat gradient block over the data-parallel group; returns the world size.
     (One call, one bucket: 7.4 M fp32 values = 29.6 MB cross NVSwitch in tens of microseconds, so the cost is
@@ -258,6 +296,9 @@ class DataParallelTrainer:
         self.exp_avg = torch.zeros_like(self.state.params)
         self.exp_avg_sq = torch.zeros_like(self.state.params)
         self.steps = 0
+        # rank 0's weights, running statistics and moments are the replica every rank starts from
+        broadcast_from_rank0_([self.state.params, self.state.bnstats, self.state.num_batches_tracked,
+                               self.exp_avg, self.exp_avg_sq], group)
 
     def step(self, x, labels, target, target_weight):
         st = self.state

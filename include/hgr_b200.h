@@ -80,6 +80,16 @@ HGR_API void hgr_plan_destroy(hgr_plan_t* plan);
 HGR_API int hgr_forward(hgr_plan_t* plan, const void* d_x, int x_dtype, int batch, void* d_logits, void* d_heatmaps,
                 void* d_attn, int out_dtype, void* stream);
 
+/* The forward with the keypoint decode of libs/utils.py:4-32 fused into the pose head (reference detect.py:143-150
+ * runs the classifier and then get_max_preds on its heatmaps): d_preds (B, J, 2) fp32 [x, y] and d_maxvals (B, J, 1)
+ * fp32 are bit-identical to hgr_get_max_preds applied to the heatmaps this call would write.  d_heatmaps may be
+ * NULL: the heatmaps then never reach HBM (only with the tcgen05 pose head, i.e. image_size <= 320). */
+/* 1 when hgr_forward_keypoints can run with d_heatmaps == NULL for this image size (0 otherwise, -1 on a bad size). */
+HGR_API int hgr_keypoints_fused(int image_size, int num_joints);
+
+HGR_API int hgr_forward_keypoints(hgr_plan_t* plan, const void* d_x, int x_dtype, int batch, void* d_logits,
+                                  void* d_heatmaps, float* d_preds, float* d_maxvals, int out_dtype, void* stream);
+
 /* Same call with HOST buffers: pinned or pageable input is copied to the
  * device, the forward runs, logits and heatmaps are copied back; returns after
  * the results are in host memory.  This is the end-to-end path bench.py times. */
@@ -177,10 +187,17 @@ HGR_API int hgr_layernorm(const void* d_x, void* d_y, const float* d_gamma, cons
  * d_out (B, T, 256) bf16; d_probs (B, 8, T, T) probs_dtype or NULL. */
 HGR_API int hgr_attention(const void* d_qkv, void* d_out, void* d_probs, int probs_dtype, int B, int T, void* stream);
 
-/* The same attention core on tcgen05 tensor cores (csrc/attention_tc.cu): scores and outputs in TMEM, softmax by
- * one thread per query row, V as an MN-major operand.  129 <= T <= 160, no probability output.  Opt-in inside the
- * forward plan (HGR_ATTN_TC=1); exported so that the parity suite covers it. */
+/* The same attention core on tcgen05 tensor cores (csrc/attention_tc.cu): scores, probabilities and outputs in
+ * TMEM, P as the TMEM A operand of P V, V as an MN-major operand.  129 <= T <= 160, no probability output.  The
+ * forward plan uses it for every attention launch that returns no probabilities (HGR_ATTN_TC=0 falls back to
+ * hgr_attention's mma.sync kernels); exported so that the parity suite covers it directly. */
 HGR_API int hgr_attention_tc(const void* d_qkv, void* d_out, int B, int T, void* stream);
+
+/* Development aid: the same launch with a cycle timeline of CTA 0.  d_trace receives clock64 marks as
+ * [trace_items][*warps][8] long long (see AttnTcParams in csrc/attention_tc.cu for the marks);
+ * d_trace == NULL only reports *warps. */
+HGR_API int hgr_attention_tc_trace(const void* d_qkv, void* d_out, int B, int T, long long* d_trace, int trace_items,
+                                   int* warps, void* stream);
 
 /* mlp_head: Linear(256, C)(LayerNorm(tokens[:, 0])). */
 HGR_API int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float* d_beta, const float* d_w,
@@ -190,6 +207,10 @@ HGR_API int hgr_cls_head(const void* d_tokens, const float* d_gamma, const float
  * d_tokens (B, F*F+1, 256) bf16, d_w bf16 [J][256] -> (B, J, 4F, 4F). */
 HGR_API int hgr_pose_head(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps, int out_dtype, int B,
                   int F, int J, void* stream);
+
+/* The pose head with the keypoint decode fused into its epilogue (see hgr_forward_keypoints); d_heatmaps may be NULL. */
+HGR_API int hgr_pose_head_decode(const void* d_tokens, const void* d_w, const float* d_bias, void* d_heatmaps,
+                                 int out_dtype, float* d_preds, float* d_maxvals, int B, int F, int J, void* stream);
 
 /* libs.utils.get_max_preds (reference libs/utils.py:4-32):
  * heatmaps (B, J, H, W) -> preds (B, J, 2) fp32 [x, y], maxvals (B, J, 1) fp32. */

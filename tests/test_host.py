@@ -97,6 +97,45 @@ def test_module_tree_and_contract():
     assert MultiTaskNet(21, 19, [256, 256]).decoder.pos_embedding.shape == (256, 256)
 
 
+def test_res_bottleneck_container_and_large_refusal():
+    """model/gelan.py:90-121 is defined but never instantiated by gelan_spec ('small' only): the drop-in keeps the
+    class with the reference's constructor and parameter tree, and refuses the 'large' backbone explicitly."""
+    from hgr_b200.model import GELANNet, ResBottleneck
+    blk = ResBottleneck(64, 64)
+    keys = list(blk.state_dict().keys())
+    want = [f"cv{i}.{leaf}" for i in (1, 2, 3)
+            for leaf in ("conv.weight", "bn.weight", "bn.bias", "bn.running_mean", "bn.running_var",
+                         "bn.num_batches_tracked")]
+    assert keys == want
+    assert tuple(blk.cv1.conv.weight.shape) == (32, 64, 1, 1) and tuple(blk.cv2.conv.weight.shape) == (32, 32, 3, 3)
+    assert tuple(blk.cv3.conv.weight.shape) == (64, 32, 1, 1) and blk.add and blk.downsample is None
+    assert not ResBottleneck(64, 128).add and not ResBottleneck(64, 64, shortcut=False).add
+    with pytest.raises(RuntimeError, match="parameter container"):
+        blk(torch.zeros(1, 64, 8, 8))
+    with pytest.raises(ValueError, match="small"):
+        GELANNet("large")
+
+
+def test_signature_sees_every_kind_of_parameter_change():
+    """The weight pack (and every CUDA graph / pipeline plan built on it) is keyed on this signature."""
+    from hgr_b200 import MultiTaskNet
+    m = MultiTaskNet(21, 19, [192, 192])
+    a = m._signature()
+    assert len(a) == 180 and m._signature() == a
+    with torch.no_grad():
+        m.encoder.cspelan2.cv4.bn.running_var.add_(1.0)          # buffer written in place
+    b = m._signature()
+    assert b != a
+    m.load_state_dict(O.synthetic_state_dict(3), strict=True)    # parameters copied in place
+    c = m._signature()
+    assert c != b
+    m.proj.weight = torch.nn.Parameter(torch.zeros_like(m.proj.weight))  # parameter object replaced
+    d = m._signature()
+    assert d != c
+    m.decoder.cls_token.data = m.decoder.cls_token.data.clone()  # storage re-homed (what .to() does)
+    assert m._signature() != d
+
+
 def test_ops_refuse_cpu_inputs():
     from hgr_b200 import crop_normalize, get_max_preds
     with pytest.raises(RuntimeError):

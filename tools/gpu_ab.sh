@@ -8,7 +8,7 @@ echo "pytest exit $?" | tee $out/summary.txt
 tail -3 $out/pytest.log
 for cfg in "0 0" "1 0" "0 1" "1 1"; do
   set -- $cfg
-  HGR_PDL=$1 HGR_ZIGZAG=$2 timeout 600 python bench.py --no-e2e --no-cpu-baseline --steps 40 > $out/bench_pdl$1_zz$2.json 2>> $out/bench.err
+  HGR_PDL=$1 HGR_ZIGZAG=$2 timeout 600 python bench.py --no-e2e --no-cpu-baseline --no-extras --steps 40 > $out/bench_pdl$1_zz$2.json 2>> $out/bench.err
   python - <<PY
 import json
 d=json.load(open("$out/bench_pdl$1_zz$2.json"))

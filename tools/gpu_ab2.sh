@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_forward.py -q 
 echo "pytest exit $?" | tee $out/summary.txt
 tail -3 $out/pytest.log
 for v in ${3:-0 1 0 1}; do
-  env $var=$v timeout 600 python bench.py --no-e2e --no-cpu-baseline --steps 40 --profile-out $out/table_$v.json > $out/bench_$v.json 2>> $out/bench.err
+  env $var=$v timeout 600 python bench.py --no-e2e --no-cpu-baseline --no-extras --steps 40 --profile-out $out/table_$v.json > $out/bench_$v.json 2>> $out/bench.err
   python - <<PY
 import json
 d=json.load(open("$out/bench_$v.json"))

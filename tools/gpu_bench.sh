@@ -10,7 +10,7 @@ tail -3 $out/pytest.log
 timeout 900 python bench.py --profile-out $out/launch_table.json > $out/bench.json 2> $out/bench.err
 echo "bench exit $?" | tee -a $out/summary.txt
 cat $out/bench.json
-SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extras"
 timeout 600 $SHORT > $out/plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 130 --csv --log-file $out/launches.csv $SHORT > $out/ncu_list.log 2>&1
 echo "ncu list exit $?" | tee -a $out/summary.txt

@@ -14,7 +14,7 @@ echo "bench exit $?" | tee -a $out/summary.txt
 cat $out/bench.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err
 echo "reference arm exit $?" | tee -a $out/summary.txt
-SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extras"
 OURS="regex:gemm_kernel|halo_kernel|vit_block_kernel|conv_chain_kernel|conv1_kernel|attention_kernel|pose_head_kernel|cls_head_kernel|fill_cls_kernel"
 NL=${2:-37}  # launches per forward (46 with HGR_VIT_FUSED=0 HGR_CONV_CHAIN=0)
 timeout 600 $SHORT > $out/plain.log 2>&1 &&

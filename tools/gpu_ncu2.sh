@@ -4,7 +4,7 @@
 tag=$1; shift
 out=gpurun_out/$tag
 mkdir -p $out
-SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extras"
 timeout 600 $SHORT > $out/plain.log 2>&1 || exit 1
 i=0
 for spec in "$@"; do

@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Runs ONE operator of the C ABI a few times at the headline batch (development tool: the command ncu wraps when a
+single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head> [B] [reps]"""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hand-gesture-recognition_b200"))
+import torch
+from hgr_b200 import _lib
+
+op = sys.argv[1] if len(sys.argv) > 1 else "attention_tc"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+lib = _lib.load()
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+st = torch.cuda.current_stream().cuda_stream
+T, F, J = 145, 12, 21
+if op in ("attention_tc", "attention"):
+    qkv = (torch.randn(B, T, 768, generator=g, device=dev) * 1.5).bfloat16()
+    out = torch.empty(B, T, 256, dtype=torch.bfloat16, device=dev)
+    if op == "attention_tc":
+        run = lambda: _lib.check(lib.hgr_attention_tc(qkv.data_ptr(), out.data_ptr(), B, T, st), op)
+    else:
+        run = lambda: _lib.check(lib.hgr_attention(qkv.data_ptr(), out.data_ptr(), None, _lib.F32, B, T, st), op)
+elif op == "pose_head":
+    tok = torch.randn(B, T, 256, generator=g, device=dev).bfloat16()
+    w = (torch.randn(J, 256, generator=g, device=dev) * 0.06).bfloat16()
+    bias = torch.randn(J, generator=g, device=dev)
+    heat = torch.empty(B, J, 4 * F, 4 * F, dtype=torch.bfloat16, device=dev)
+    run = lambda: _lib.check(lib.hgr_pose_head(tok.data_ptr(), w.data_ptr(), bias.data_ptr(), heat.data_ptr(), _lib.BF16,
+                                               B, F, J, st), op)
+else:
+    raise SystemExit(f"unknown op {op}")
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    run()
+e1.record()
+torch.cuda.synchronize()
+print(f"{op} B={B}: {e0.elapsed_time(e1) / reps:.4f} ms per launch")
