@@ -50,28 +50,32 @@ namespace hgr {
 
 namespace {
 
-constexpr int kGroups = 3;                        // softmax groups = units in flight = units per item
-constexpr int kThreads = (4 + 4 * kGroups) * 32;  // 4 service warps + 4 warps per group
+constexpr int kBufs = 3;                          // TMEM buffers = units in flight = units per item
+constexpr int kSoftGroups = 2;                    // softmax groups of four warps (one thread per query row)
+constexpr int kThreads = (8 + 4 * kSoftGroups) * 32;  // 4 service warps + 4 drain warps + the softmax groups
 constexpr int kTp = 160;                          // padded tokens (keys per MMA, rows per K / V box)
 constexpr int kHeads = 8;
-constexpr int kStages = 2;
+// Q, K and the short-row box are dead once the three score MMAs of their item have retired, V lives until the item's
+// last P V: two rings, so that the (long) loads of item i + 2 start while item i's probabilities are still computed
+constexpr int kStages = 2;                        // Q | K | short-row boxes
+constexpr int kVStages = 4;                       // V boxes
 constexpr int kQBytes = 128 * 128;                // Q rows 0-127:  [128 rows][64 cols] bf16
 constexpr int kBoxBytes = kTp * 128;              // K, V, short-row box: [160 rows][64 cols] bf16
 constexpr int kOffK = kQBytes;
-constexpr int kOffV = kOffK + kBoxBytes;
-constexpr int kOffQs = kOffV + kBoxBytes;         // rows 128.. of both heads inside a zero-filled box
+constexpr int kOffQs = kOffK + kBoxBytes;         // rows 128.. of both heads inside a zero-filled box
 constexpr int kStageBytes = kOffQs + kBoxBytes;
-constexpr int kOffBars = kStages * kStageBytes;
-constexpr int kNumBars = 2 * kStages + 4 * kGroups;
+constexpr int kOffVRing = kStages * kStageBytes;
+constexpr int kOffSum = kOffVRing + kVStages * kBoxBytes;  // row sums of the units in flight: [kBufs][128] fp32
+constexpr int kOffBars = kOffSum + kBufs * 128 * 4;
+constexpr int kNumBars = 2 * kStages + 2 * kVStages + 4 * kBufs;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 constexpr int kUnitCols = 160;  // TMEM columns of one unit: S [0,160), then P [0,80) and O behind it
 constexpr int kOColFull = 128;  // full tile: O (N = 32) in columns [128,160)
 constexpr int kOColShort = 80;  // short tiles: O (N = 64) in columns [80,144)
-constexpr int kGroupThreads = 128;
 static_assert(kQBytes % 1024 == 0 && kBoxBytes % 1024 == 0, "operand tiles need 1024-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "attention_tc shared-memory plan exceeds one CTA");
-static_assert(kGroups * kUnitCols <= 512, "units in flight exceed tensor memory");
+static_assert(kBufs * kUnitCols <= 512, "units in flight exceed tensor memory");
 
 // MN-major, 128-byte-swizzled operand: rows of the K dimension are 128 B apart, 8-row groups `sbo_bytes` apart; the
 // 64 MN elements of a row are contiguous (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>:
@@ -104,8 +108,9 @@ struct AttnTcParams {
   float scale_log2e;
   int reverse;
   // optional timeline of CTA 0 (hgr_attention_tc_trace): clock64 at the hand-over points, [item][warp][8 marks];
-  // softmax warps: 0 scores ready, 1 maximum done, 2 probabilities written, 3 output ready, 4 output stored;
-  // MMA warp (row 1): 0 S issued, 1 probabilities seen, 2 P V issued (per unit position r: marks 3 r + ..)
+  // softmax warps (8..): scores ready, maximum done, probabilities written at marks 0-2 (marks 4-6 for a group's
+  // second unit of the same item); drain warps (4-7): output ready / stored at marks 2 r, 2 r + 1 of position r;
+  // MMA warp (1): scores issued at marks 0-2 (position r), P V issued at marks 3-5
   long long* trace;
   int trace_items;
 };
@@ -132,11 +137,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* qkv_full = bars;              // [kStages]
   uint64_t* qkv_empty = bars + kStages;   // [kStages]
-  uint64_t* s_full = bars + 2 * kStages;  // [kGroups] scores of a unit are in TMEM
-  uint64_t* p_ready = s_full + kGroups;   // [kGroups] probabilities are in TMEM (128 arrivals)
-  uint64_t* o_full = p_ready + kGroups;   // [kGroups] P V of a unit is in TMEM
-  uint64_t* buf_free = o_full + kGroups;  // [kGroups] the unit's output has been read (128 arrivals)
+  uint64_t* v_full = bars + 2 * kStages;              // [kVStages]
+  uint64_t* v_empty = v_full + kVStages;              // [kVStages]
+  uint64_t* s_full = v_empty + kVStages;  // [kBufs] scores of a unit are in TMEM
+  uint64_t* p_ready = s_full + kBufs;     // [kBufs] probabilities are in TMEM, row sums in shared memory (128 arrivals)
+  uint64_t* o_full = p_ready + kBufs;     // [kBufs] P V of a unit is in TMEM
+  uint64_t* buf_free = o_full + kBufs;    // [kBufs] the unit's output has been read (128 arrivals)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+  float* lsum = reinterpret_cast<float*>(smem + kOffSum);  // [kBufs][128] row sums, softmax -> drain
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("hgr: dynamic smem base not 1024-byte aligned\n");
@@ -152,11 +160,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&qkv_full[i], 1);
       mbar_init(&qkv_empty[i], 1);
     }
-    for (int i = 0; i < kGroups; ++i) {
+    for (int i = 0; i < kVStages; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < kBufs; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], kGroupThreads);
+      mbar_init(&p_ready[i], 128);
       mbar_init(&o_full[i], 1);
-      mbar_init(&buf_free[i], kGroupThreads);
+      mbar_init(&buf_free[i], 128);
     }
     fence_barrier_init();
   }
@@ -175,142 +187,184 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int my_items = (int)blockIdx.x < total_items ? (total_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int first = p.reverse ? total_items - 1 - (int)blockIdx.x : (int)blockIdx.x;
   const int step = p.reverse ? -(int)gridDim.x : (int)gridDim.x;
+  const int num_units = kBufs * my_items;  // unit u = (item u / 3, position / TMEM buffer u % 3)
 
   if (warp == 0) {
     // ================= TMA producer: Q | K | V | short-row boxes of one head pair per item =================
     if (elect_one_sync()) {
       int item = first;
-      int s = 0, k = 0;  // stage, use count of the stage
       for (int i = 0; i < my_items; ++i, item += step) {
         const int b = item >> 2, pair = item & 3;
+        const int s = i % kStages, sv = i % kVStages;
         uint8_t* stage = smem + s * kStageBytes;
-        mbar_wait(&qkv_empty[s], (k & 1) ^ 1);
+        mbar_wait(&qkv_empty[s], ((i / kStages) & 1) ^ 1);
         mbar_expect_tx(&qkv_full[s], kStageBytes);
         tma_load_5d(stage, &tmQ, &qkv_full[s], pair * 64, 0, b, 0, 0);
         tma_load_5d(stage + kOffK, &tmKV, &qkv_full[s], 256 + pair * 64, 0, b, 0, 0);
-        tma_load_5d(stage + kOffV, &tmKV, &qkv_full[s], 512 + pair * 64, 0, b, 0, 0);
         // box row r holds token 128 + r - 32 (j0 + 1); everything outside [128, T) is zero-filled
         tma_load_5d(stage + kOffQs, &tmQs, &qkv_full[s], pair * 64, -32 * (short_quarter(i) + 1), b, 0, 0);
-        if (++s == kStages) {
-          s = 0;
-          ++k;
-        }
+        mbar_wait(&v_empty[sv], ((i / kVStages) & 1) ^ 1);
+        mbar_expect_tx(&v_full[sv], kBoxBytes);
+        tma_load_5d(smem + kOffVRing + sv * kBoxBytes, &tmKV, &v_full[sv], 512 + pair * 64, 0, b, 0, 0);
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer: S of unit (i, r), then P V of the unit two positions earlier =================
+    // ================= MMA issuer: the scores of the first three units, then P V of unit v and the scores of the
+    // unit that inherits its buffer (v + 3), in the order the softmax groups finish =================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, kTp);
     constexpr uint32_t idesc_o32 = umma_idesc_bf16(128, 32) | (1u << 16);  // B is MN-major
     constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64) | (1u << 16);
-    const int num_units = kGroups * my_items;
     int i_s = 0, r_s = 0;  // item / position of the unit whose scores are issued next
-    int i_o = 0, r_o = 0;  // the same for the unit whose P V is issued next
-    for (int u = 0; u < num_units + 2; ++u) {
-      if (u < num_units) {
-        const int st = i_s % kStages;
-        if (r_s == 0) {
-          mbar_wait(&qkv_full[st], (i_s / kStages) & 1);
-          tc_fence_after();
-        }
-        if (i_s >= 1) {
-          // the previous unit of this buffer has been drained (its O has been read, which implies its P V has retired)
-          mbar_wait(&buf_free[r_s], (i_s - 1) & 1);
-          tc_fence_after();
-        }
-        const uint32_t stage = smem_u32(smem + st * kStageBytes);
-        const uint32_t tmem_d = tmem_base + r_s * kUnitCols;
-        const int ty = unit_type(i_s, r_s);
-        if (elect_one_sync()) {
-          if (ty < 2) {
+    auto issue_scores = [&]() {
+      const int st = i_s % kStages;
+      if (r_s == 0) {
+        mbar_wait(&qkv_full[st], (i_s / kStages) & 1);
+        tc_fence_after();
+      }
+      if (i_s >= 1) {
+        // the previous unit of this buffer has been drained (its O has been read, which implies its P V has retired)
+        mbar_wait(&buf_free[r_s], (i_s - 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t stage = smem_u32(smem + st * kStageBytes);
+      const uint32_t tmem_d = tmem_base + r_s * kUnitCols;
+      const int ty = unit_type(i_s, r_s);
+      if (elect_one_sync()) {
+        if (ty < 2) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t a = umma_desc_sw128(stage + ty * 64, 1024) + 2 * k;
+            const uint64_t bdesc = umma_desc_sw128(stage + kOffK + ty * 64, 1024) + 2 * k;
+            umma_bf16_ss(tmem_d, a, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            // head 0: its rows are 32 (j0 + 1) rows into the box and belong in quarter j0 -> start 32 rows in;
+            // head 1: quarter j0 + 1 -> start at the box's first row
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              const uint64_t a = umma_desc_sw128(stage + ty * 64, 1024) + 2 * k;
-              const uint64_t bdesc = umma_desc_sw128(stage + kOffK + ty * 64, 1024) + 2 * k;
-              umma_bf16_ss(tmem_d, a, bdesc, idesc_s, k != 0 ? 1u : 0u);
-            }
-          } else {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              // head 0: its rows are 32 (j0 + 1) rows into the box and belong in quarter j0 -> start 32 rows in;
-              // head 1: quarter j0 + 1 -> start at the box's first row
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint64_t a = umma_desc_sw128(stage + kOffQs + (hh == 0 ? 32 * 128 : 0) + hh * 64, 1024) + 2 * k;
-                const uint64_t bdesc = umma_desc_sw128(stage + kOffK + hh * 64, 1024) + 2 * k;
-                umma_bf16_ss(tmem_d, a, bdesc, idesc_s, (hh | k) != 0 ? 1u : 0u);
-              }
+              const uint64_t a = umma_desc_sw128(stage + kOffQs + (hh == 0 ? 32 * 128 : 0) + hh * 64, 1024) + 2 * k;
+              const uint64_t bdesc = umma_desc_sw128(stage + kOffK + hh * 64, 1024) + 2 * k;
+              umma_bf16_ss(tmem_d, a, bdesc, idesc_s, (hh | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&s_full[r_s]);
-          if (p.trace != nullptr && blockIdx.x == 0 && i_s < p.trace_items && r_s < 2)
-            p.trace[((size_t)i_s * (kThreads / 32) + 1) * 8 + 4 * r_s] = clock64();
         }
-        __syncwarp();
-        if (++r_s == kGroups) {
-          r_s = 0;
-          ++i_s;
-        }
+        umma_commit(&s_full[r_s]);
+        // the item's last score MMA: its Q, K and short-row boxes may be overwritten (not signalled when no later
+        // item will use the stage, so that no arrive is in flight when the CTA exits)
+        if (r_s == kBufs - 1 && i_s + kStages < my_items) umma_commit(&qkv_empty[st]);
+        if (p.trace != nullptr && blockIdx.x == 0 && i_s < p.trace_items)
+          p.trace[((size_t)i_s * (kThreads / 32) + 1) * 8 + r_s] = clock64();
       }
-      if (u >= 2) {
-        const int st = i_o % kStages;
-        mbar_wait(&p_ready[r_o], i_o & 1);
-        tc_fence_after();
-        if (p.trace != nullptr && blockIdx.x == 0 && i_o < p.trace_items && r_o < 2 && lane == 0)
-          p.trace[((size_t)i_o * (kThreads / 32) + 1) * 8 + 4 * r_o + 1] = clock64();
-        const uint32_t vbuf = smem_u32(smem + st * kStageBytes + kOffV);
-        const uint32_t tmem_u = tmem_base + r_o * kUnitCols;
-        const int ty = unit_type(i_o, r_o);
-        if (elect_one_sync()) {
-          if (ty < 2) {
-#pragma unroll
-            for (int k = 0; k < kTp / 16; ++k)
-              umma_bf16_ts(tmem_u + kOColFull, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + ty * 64 + k * 2048, 1024),
-                           idesc_o32, k != 0 ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < kTp / 16; ++k)
-              umma_bf16_ts(tmem_u + kOColShort, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + k * 2048, 1024), idesc_o64,
-                           k != 0 ? 1u : 0u);
-          }
-          umma_commit(&o_full[r_o]);
-          if (p.trace != nullptr && blockIdx.x == 0 && i_o < p.trace_items && r_o < 2)
-            p.trace[((size_t)i_o * (kThreads / 32) + 1) * 8 + 4 * r_o + 2] = clock64();
-          // last unit of the item: its boxes may be overwritten (not signalled when no later item will use the
-          // stage, so that no arrive is in flight when the CTA exits)
-          if (r_o == kGroups - 1 && i_o + kStages < my_items) umma_commit(&qkv_empty[st]);
-        }
-        __syncwarp();
-        if (++r_o == kGroups) {
-          r_o = 0;
-          ++i_o;
-        }
+      __syncwarp();
+      if (++r_s == kBufs) {
+        r_s = 0;
+        ++i_s;
       }
+    };
+    for (int u = 0; u < kBufs && u < num_units; ++u) issue_scores();
+    int i_o = 0, r_o = 0;
+    for (int v = 0; v < num_units; ++v) {
+      const int sv = i_o % kVStages;
+      if (r_o == 0) mbar_wait(&v_full[sv], (i_o / kVStages) & 1);
+      mbar_wait(&p_ready[r_o], i_o & 1);
+      tc_fence_after();
+      const uint32_t vbuf = smem_u32(smem + kOffVRing + sv * kBoxBytes);
+      const uint32_t tmem_u = tmem_base + r_o * kUnitCols;
+      const int ty = unit_type(i_o, r_o);
+      if (elect_one_sync()) {
+        if (ty < 2) {
+#pragma unroll
+          for (int k = 0; k < kTp / 16; ++k)
+            umma_bf16_ts(tmem_u + kOColFull, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + ty * 64 + k * 2048, 1024),
+                         idesc_o32, k != 0 ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kTp / 16; ++k)
+            umma_bf16_ts(tmem_u + kOColShort, tmem_u + 8 * k, umma_desc_mn_sw128(vbuf + k * 2048, 1024), idesc_o64,
+                         k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[r_o]);
+        // last unit of the item: its V box may be overwritten
+        if (r_o == kBufs - 1 && i_o + kVStages < my_items) umma_commit(&v_empty[sv]);
+        if (p.trace != nullptr && blockIdx.x == 0 && i_o < p.trace_items)
+          p.trace[((size_t)i_o * (kThreads / 32) + 1) * 8 + 3 + r_o] = clock64();
+      }
+      __syncwarp();
+      if (++r_o == kBufs) {
+        r_o = 0;
+        ++i_o;
+      }
+      if (v + kBufs < num_units) issue_scores();
     }
-  } else if (warp >= 4) {
-    // ================= softmax groups: group g owns TMEM buffer g, i.e. unit g of every item =================
-    const int e4 = warp - 4;
-    const int q = e4 & 3;  // == warp % 4: the TMEM lane quarter this warp may access
-    const int g = e4 >> 2;
-    const uint32_t t_unit = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kUnitCols;
-    const float c = p.scale_log2e;
-    const int nlast = T - 128;  // valid keys of the last 32-key chunk
+  } else if (warp >= 4 && warp < 8) {
+    // ================= drain warps (one per lane quarter): O / l -> 'b n (h d)', in unit order =================
+    const int q = warp & 3;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     int item = first;
     for (int i = 0; i < my_items; ++i, item += step) {
       const int b = item >> 2, pair = item & 3;
-      const int ty = unit_type(i, g);
+      const int j0 = short_quarter(i);
+      const uint32_t ph = i & 1;
+#pragma unroll 1
+      for (int r = 0; r < kBufs; ++r) {
+        const int ty = unit_type(i, r);
+        const bool active = ty < 2 || q == j0 || q == j0 + 1;
+        const int hh = ty < 2 ? ty : q - j0;
+        const int h = pair * 2 + hh;
+        const int row = ty < 2 ? q * 32 + lane : 128 + lane;
+        const uint32_t ocol = ty < 2 ? kOColFull : kOColShort + 32 * hh;
+        mbar_wait(&p_ready[r], ph);  // acquires the row sums the softmax threads left in shared memory
+        mbar_wait(&o_full[r], ph);
+        tc_fence_after();
+        long long* tr = (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < p.trace_items)
+                            ? p.trace + ((size_t)i * (kThreads / 32) + warp) * 8 : nullptr;
+        if (tr) tr[2 * r] = clock64();
+        if (active) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(t_lane + r * kUnitCols + ocol, o);
+          const float l = lsum[r * 128 + q * 32 + lane];
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&buf_free[r]);  // the registers hold the output: the MMA warp may reuse the buffer
+          if (row < T) {
+            const float inv = 1.0f / l;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * T + row) * (kHeads * 32) + h * 32);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              dst[v] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * v]) * inv, __uint_as_float(o[8 * v + 1]) * inv),
+                                  pack_bf16x2(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv),
+                                  pack_bf16x2(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv),
+                                  pack_bf16x2(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv));
+          }
+        } else {
+          tc_fence_before();
+          mbar_arrive(&buf_free[r]);
+        }
+        if (tr) tr[2 * r + 1] = clock64();
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= softmax groups: group G takes every second unit (u = G, G + 2, ...), whatever buffer it is
+    // in; it never waits for a P V or an output: as soon as its probabilities are written it moves on =================
+    const int e8 = warp - 8;
+    const int q = e8 & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int grp = e8 >> 2;
+    const float c = p.scale_log2e;
+    const int nlast = T - 128;  // valid keys of the last 32-key chunk
+    int i = 0, r = grp;         // item and position of this group's current unit
+    for (int u = grp; u < num_units; u += kSoftGroups) {
+      const int ty = unit_type(i, r);
       const int j0 = short_quarter(i);
       const bool active = ty < 2 || q == j0 || q == j0 + 1;
-      const int hh = ty < 2 ? ty : q - j0;
-      const int h = pair * 2 + hh;
-      const int row = ty < 2 ? q * 32 + lane : 128 + lane;
-      const uint32_t ocol = ty < 2 ? kOColFull : kOColShort + 32 * hh;
-      const uint32_t ph = i & 1;
-      mbar_wait(&s_full[g], ph);
+      const uint32_t t_unit = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + r * kUnitCols;
+      mbar_wait(&s_full[r], i & 1);
       tc_fence_after();
       long long* tr = (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < p.trace_items)
                           ? p.trace + ((size_t)i * (kThreads / 32) + warp) * 8 : nullptr;
-      if (tr) tr[0] = clock64();
-      float l = 0.f;
+      const int tb = r == 2 ? 4 : 0;  // a group's second unit inside the same item
+      if (tr) tr[tb] = clock64();
       if (active) {
         // ---- pass 1: row maximum over the valid keys; chunk c + 1 is on its way while chunk c is reduced ----
         uint32_t sb[2][32];
@@ -334,7 +388,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         const float mc = fmaxf(m0, m1) * c;
-        if (tr) tr[1] = clock64();
+        if (tr) tr[tb + 1] = clock64();
         // ---- pass 2: exponentials, row sum, bf16 probabilities over the consumed score columns ----
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
         tmem_ld_32x32b_x32(t_unit, sb[0]);
@@ -367,37 +421,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // keys 32 cb .. 32 cb + 31 -> columns 16 cb .. 16 cb + 15: inside the score columns already consumed
           tmem_st_32x32b_x16(t_unit + cb * 16, packed);
         }
-        l = (l0 + l1) + (l2 + l3);
+        lsum[r * 128 + q * 32 + lane] = (l0 + l1) + (l2 + l3);
         tmem_st_wait();
       }
       tc_fence_before();
-      mbar_arrive(&p_ready[g]);
-      if (tr) tr[2] = clock64();
-      // ---- output: O / l -> 'b n (h d)' ----
-      mbar_wait(&o_full[g], ph);
-      tc_fence_after();
-      if (tr) tr[3] = clock64();
-      if (active) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(t_unit + ocol, o);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&buf_free[g]);  // the registers hold the output: the MMA warp may reuse the buffer
-        if (row < T) {
-          const float inv = 1.0f / l;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + ((size_t)b * T + row) * (kHeads * 32) + h * 32);
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            dst[v] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * v]) * inv, __uint_as_float(o[8 * v + 1]) * inv),
-                                pack_bf16x2(__uint_as_float(o[8 * v + 2]) * inv, __uint_as_float(o[8 * v + 3]) * inv),
-                                pack_bf16x2(__uint_as_float(o[8 * v + 4]) * inv, __uint_as_float(o[8 * v + 5]) * inv),
-                                pack_bf16x2(__uint_as_float(o[8 * v + 6]) * inv, __uint_as_float(o[8 * v + 7]) * inv));
-        }
-      } else {
-        tc_fence_before();
-        mbar_arrive(&buf_free[g]);
+      mbar_arrive(&p_ready[r]);
+      if (tr) tr[tb + 2] = clock64();
+      r += kSoftGroups;
+      if (r >= kBufs) {
+        r -= kBufs;
+        ++i;
       }
-      if (tr) tr[4] = clock64();
     }
   }
 

@@ -7,7 +7,7 @@
 //
 //   MMA 1 (interpolation as a GEMM):  D1[128 pixels][256 ch] = U[128 pixels][K] * TOK[K][256 ch]
 //       K = 3 F token positions (the three token rows a 128-pixel tile can touch), padded to a multiple of 16;
-//       U holds the four bilinear weights of each pixel (fp16, K-major SWIZZLE_128B, rebuilt per tile by the aux
+//       U holds the four bilinear weights of each pixel (bf16, K-major SWIZZLE_128B, rebuilt per tile by the aux
 //       warps - it depends on the tile only), TOK is the MN-major B operand exactly as TMA delivers the token rows
 //       ([positions][64 channels] boxes), fp32 accumulation in TMEM;
 //   E1:  ReLU + bf16 (one cvt.rn.relu.bf16x2 per two values) from TMEM back INTO TENSOR MEMORY over the columns
@@ -18,16 +18,15 @@
 // A CTA owns whole images (18 tiles at 192 x 192), so the decode needs no second kernel and the 198 MB of fp32
 // heatmaps that HandPipeline wrote only for max_preds_kernel to read back are never written.
 //
-// Warp roles (640 threads): 0 TMA producer (token boxes, 3 stages), 1 MMA issuer, 2 TMEM allocator, 4-7 aux
+// Warp roles (512 threads): 0 TMA producer (token boxes, 3 stages), 1 MMA issuer, 2 TMEM allocator, 4-7 aux
 // (U tiles, E2), 8-15 E1 (two warps per TMEM lane quarter, 128 channels each).  Two 256-column TMEM buffers:
 // D1 [0,256) -> A2 [0,64) + [128,192) (each E1 warp overwrites columns it has consumed itself) -> D2 [64,96).
 //
-// Numerics: the interpolation weights are fp16 (11 bits; products of two fp32 lambdas rounded once), the tokens bf16,
-// the interpolated value fp32 until the single bf16 rounding in front of the second MMA - one rounding fewer than
-// pose_head.cu's bf16 value + weight * slope form.  Supported: F = 4..20 in steps of 4 (K = 3 F <= 64 fits one
+// Numerics: the interpolation weights are bf16 (products of two fp32 lambdas rounded once; a mixed fp16 x bf16
+// kind::f16 MMA raises an illegal-instruction fault on sm_100a, measured), the tokens bf16, the interpolated value
+// fp32 until the single bf16 rounding in front of the second MMA - the same number of bf16 roundings as
+// pose_head.cu's value + weight * slope form.  Supported: F = 4..20 in steps of 4 (K = 3 F <= 64 fits one
 // swizzle row); larger maps use pose_head.cu.
-#include <cuda_fp16.h>
-
 #include "hgr_internal.h"
 #include "ptx.cuh"
 
@@ -36,10 +35,10 @@ namespace hgr {
 namespace {
 
 constexpr int kDim = 256;
-constexpr int kThreads = 640;
+constexpr int kThreads = 512;
 constexpr int kJPad = 32;
 constexpr int kTokStages = 3;
-constexpr int kUBytes = 128 * 128;       // U tile: [128 pixels][64 k] fp16, one swizzle row per pixel
+constexpr int kUBytes = 128 * 128;       // U tile: [128 pixels][64 k] bf16, one swizzle row per pixel
 constexpr int kWBytes = 4 * kJPad * 128; // W: 4 channel chunks of [32 joints][64 ch] bf16
 constexpr int kBufCols = 256;
 constexpr int kA2Hi = 128;               // A2 columns of channels 128-255
@@ -203,8 +202,8 @@ pose_head_tc_kernel(const __grid_constant__ CUtensorMap tmTok, const PoseTcParam
     }
   } else if (warp == 1) {
     // ================= MMA issuer: MMA 1 of unit u, then MMA 2 of unit u - 1 =================
-    // A = U (fp16, K-major), B = tokens (bf16, MN-major): a_format F16 = 0 [7,10), b_format BF16 = 1 [10,13)
-    constexpr uint32_t idesc1 = (1u << 4) | (0u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    // A = U (bf16, K-major), B = tokens (bf16, MN-major)
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64) | (1u << 16);
     constexpr uint32_t idesc2 = umma_idesc_bf16(128, kJPad);
     const uint32_t ubase = smem_u32(smem + kOffU), wbase = smem_u32(smem + kOffW);
     int s = 0, ks = 0;
@@ -261,6 +260,9 @@ pose_head_tc_kernel(const __grid_constant__ CUtensorMap tmTok, const PoseTcParam
     float best_v[kJPad > 24 ? 24 : kJPad];
     int best_i[kJPad > 24 ? 24 : kJPad];
     const bool decode = p.preds != nullptr;
+    float bias_r[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) bias_r[j] = j < p.J ? __ldg(p.bias + j) : 0.f;
     for (int u = 0; u < num_units + 2; ++u) {
       if (u < num_units) {
         const int ub = u & 1, t = u % kTiles;
@@ -284,11 +286,13 @@ pose_head_tc_kernel(const __grid_constant__ CUtensorMap tmTok, const PoseTcParam
         }
         uint8_t* row = smem + kOffU + ub * kUBytes + r * 128;
         mbar_wait(&u_empty[ub], ((u >> 1) & 1) ^ 1);
+        // rows are 128 B apart: rotate the chunk order with the lane so that the eight lanes of a store phase
+        // cover all 32 banks
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(row + (((c + lane) & 7) << 4)) = make_uint4(0, 0, 0, 0);
         auto put = [&](int k, float wgt) {
           if (wgt != 0.f)
-            *reinterpret_cast<__half*>(row + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2) = __float2half_rn(wgt);
+            *reinterpret_cast<__nv_bfloat16*>(row + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(wgt);
         };
         put((y0 - ty0) * F + x0, w00);
         put((y0 - ty0) * F + x1, w01);
@@ -308,21 +312,29 @@ pose_head_tc_kernel(const __grid_constant__ CUtensorMap tmTok, const PoseTcParam
         tc_fence_before();
         mbar_arrive(&buf_free[vb]);
         const int pix = t * 128 + r;
-        if (t == 0) {
+        float val[24];
 #pragma unroll
-          for (int j = 0; j < 24; ++j) {
-            best_v[j] = 0.f;
-            best_i[j] = 0x7fffffff;
-          }
+        for (int j = 0; j < 24; ++j) val[j] = __uint_as_float(o[j]) + bias_r[j];
+        if (heat != nullptr) {
+          // NCHW: for one joint the 32 lanes of a warp cover 32 consecutive pixels
+          TOut* hp = heat + (size_t)b * p.J * (So * So) + pix;
+#pragma unroll
+          for (int j = 0; j < 24; ++j)
+            if (j < p.J) store_out<TOut>(hp + (size_t)j * (So * So), val[j]);
         }
+        if (decode) {
+          if (t == 0) {
 #pragma unroll
-        for (int j = 0; j < 24; ++j) {
-          if (j < p.J) {
-            const float val = __uint_as_float(o[j]) + __ldg(p.bias + j);
-            if (heat != nullptr) store_out<TOut>(heat + ((size_t)b * p.J + j) * (So * So) + pix, val);
-            if (decode) {
-              const float sv = as_stored<TOut>(val);
-              if (best_i[j] == 0x7fffffff || beats(sv, pix, best_v[j], best_i[j])) {
+            for (int j = 0; j < 24; ++j) {
+              best_v[j] = as_stored<TOut>(val[j]);
+              best_i[j] = pix;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) {
+              const float sv = as_stored<TOut>(val[j]);
+              // pix grows from tile to tile, so on equal values the earlier index stays (numpy's first-occurrence rule)
+              if (beats(sv, pix, best_v[j], best_i[j])) {
                 best_v[j] = sv;
                 best_i[j] = pix;
               }

@@ -223,52 +223,6 @@ def test_conv_chain(lib, b, h):
     r, m = report(f"conv_chain b={b} h={h} vs fp32 operators", got[:, 64:192], ref)
     assert r <= 6e-3 and m <= 2 * MAX_TOL
 
-
-@pytest.mark.parametrize("feat,b", [(12, 3), (12, 310), (16, 5), (8, 4), (4, 2), (20, 2)])
-@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-def test_pose_head_decode(lib, feat, b, out_dtype):
-    """The keypoint decode fused into the pose head's epilogue (libs/utils.py:4-32 after transformer.py:146-150):
-    bit-identical to get_max_preds on the heatmaps the same call writes, and identical again in the keypoints-only
-    mode where the heatmaps never reach memory.  b = 310 gives every CTA several images (arg-max state reset)."""
-    from hgr_b200 import _lib
-    from oracle import multitasknet_oracle as O
-    dev = torch.device("cuda")
-    g = torch.Generator().manual_seed(feat * 31 + b)
-    j = 21
-    tok = bf16_round(torch.randn(b, feat * feat + 1, 256, generator=g) * 2)
-    w = bf16_round(torch.randn(j, 256, generator=g) * 0.1)
-    bias = torch.randn(j, generator=g) * 0.5
-    bias[3] = -1000.0  # an all-negative map: the prediction is masked to (0, 0)
-    td, wd, bd = tok.to(dev, torch.bfloat16), w.to(dev, torch.bfloat16), bias.to(dev)
-    so = 4 * feat
-    dt = _lib.F32 if out_dtype == torch.float32 else _lib.BF16
-    heat = torch.full((b, j, so, so), 7.0, dtype=out_dtype, device=dev)
-    preds = torch.full((b, j, 2), -1.0, device=dev)
-    maxv = torch.full((b, j, 1), -1.0, device=dev)
-    _chk(lib.hgr_pose_head_decode(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), heat.data_ptr(), dt, preds.data_ptr(),
-                                  maxv.data_ptr(), b, feat, j, _stream()), "hgr_pose_head_decode")
-    torch.cuda.synchronize()
-    rp, rv = O.get_max_preds(heat.float().cpu().numpy())
-    assert np.array_equal(preds.cpu().numpy().view(np.uint32), rp.view(np.uint32))
-    assert np.array_equal(maxv.cpu().numpy().view(np.uint32), rv.view(np.uint32))
-    assert float(preds[:, 3].abs().max()) == 0.0
-    # the heatmaps are the ones the plain call writes
-    heat2 = torch.empty_like(heat)
-    _chk(lib.hgr_pose_head(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), heat2.data_ptr(), dt, b, feat, j, _stream()),
-         "hgr_pose_head")
-    assert torch.equal(heat, heat2)
-    # keypoints only
-    p2, v2 = torch.full_like(preds, -1.0), torch.full_like(maxv, -1.0)
-    _chk(lib.hgr_pose_head_decode(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, dt, p2.data_ptr(), v2.data_ptr(),
-                                  b, feat, j, _stream()), "hgr_pose_head_decode (keypoints only)")
-    torch.cuda.synchronize()
-    assert torch.equal(p2, preds) and torch.equal(v2, maxv)
-    # and the values are the operator's (same tolerance as test_pose_head)
-    fmap = tok[:, 1:].reshape(b, feat, feat, 256).permute(0, 3, 1, 2)
-    up = F.relu(F.interpolate(fmap, scale_factor=(4, 4), mode="bilinear", align_corners=True))
-    ref = F.conv2d(bf16_round(up), w.view(j, 256, 1, 1), bias)
-    r, m = report(f"pose_head_decode F={feat} B={b} {out_dtype}", heat, ref)
-    assert r <= 6e-3 and m <= 2 * MAX_TOL
     r2, _ = report(f"conv_chain b={b} h={h} vs two launches", got[:, 64:192], nchw_f32(two))
     assert r2 <= 1e-3
 
@@ -455,4 +409,51 @@ def test_pose_head(lib, feat, out_dtype):
     r, m = report(f"pose_head F={feat} {out_dtype}", out, ref)
     # the interpolated operand is formed in bf16 arithmetic (value + weight * slope): about two bf16 roundings more
     # than the oracle's single rounding of the fp32 up-sampled tensor
+    assert r <= 6e-3 and m <= 2 * MAX_TOL
+
+
+@pytest.mark.parametrize("feat,b", [(12, 3), (12, 310), (16, 5), (8, 4), (4, 2), (20, 2)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_pose_head_decode(lib, feat, b, out_dtype):
+    """The keypoint decode fused into the pose head's epilogue (libs/utils.py:4-32 after transformer.py:146-150):
+    bit-identical to get_max_preds on the heatmaps the same call writes, and identical again in the keypoints-only
+    mode where the heatmaps never reach memory.  b = 310 gives every CTA several images (arg-max state reset)."""
+    from hgr_b200 import _lib
+    from oracle import multitasknet_oracle as O
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(feat * 31 + b)
+    j = 21
+    tok = bf16_round(torch.randn(b, feat * feat + 1, 256, generator=g) * 2)
+    w = bf16_round(torch.randn(j, 256, generator=g) * 0.1)
+    bias = torch.randn(j, generator=g) * 0.5
+    bias[3] = -100.0  # an all-negative map: the prediction is masked to (0, 0)
+    td, wd, bd = tok.to(dev, torch.bfloat16), w.to(dev, torch.bfloat16), bias.to(dev)
+    so = 4 * feat
+    dt = _lib.F32 if out_dtype == torch.float32 else _lib.BF16
+    heat = torch.full((b, j, so, so), 7.0, dtype=out_dtype, device=dev)
+    preds = torch.full((b, j, 2), -1.0, device=dev)
+    maxv = torch.full((b, j, 1), -1.0, device=dev)
+    _chk(lib.hgr_pose_head_decode(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), heat.data_ptr(), dt, preds.data_ptr(),
+                                  maxv.data_ptr(), b, feat, j, _stream()), "hgr_pose_head_decode")
+    torch.cuda.synchronize()
+    rp, rv = O.get_max_preds(heat.float().cpu().numpy())
+    assert np.array_equal(preds.cpu().numpy().view(np.uint32), rp.view(np.uint32))
+    assert np.array_equal(maxv.cpu().numpy().view(np.uint32), rv.view(np.uint32))
+    assert float(preds[:, 3].abs().max()) == 0.0
+    # the heatmaps are the ones the plain call writes
+    heat2 = torch.empty_like(heat)
+    _chk(lib.hgr_pose_head(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), heat2.data_ptr(), dt, b, feat, j, _stream()),
+         "hgr_pose_head")
+    assert torch.equal(heat, heat2)
+    # keypoints only
+    p2, v2 = torch.full_like(preds, -1.0), torch.full_like(maxv, -1.0)
+    _chk(lib.hgr_pose_head_decode(td.data_ptr(), wd.data_ptr(), bd.data_ptr(), None, dt, p2.data_ptr(), v2.data_ptr(),
+                                  b, feat, j, _stream()), "hgr_pose_head_decode (keypoints only)")
+    torch.cuda.synchronize()
+    assert torch.equal(p2, preds) and torch.equal(v2, maxv)
+    # and the values are the operator's (same tolerance as test_pose_head)
+    fmap = tok[:, 1:].reshape(b, feat, feat, 256).permute(0, 3, 1, 2)
+    up = F.relu(F.interpolate(fmap, scale_factor=(4, 4), mode="bilinear", align_corners=True))
+    ref = F.conv2d(bf16_round(up), w.view(j, 256, 1, 1), bias)
+    r, m = report(f"pose_head_decode F={feat} B={b} {out_dtype}", heat, ref)
     assert r <= 6e-3 and m <= 2 * MAX_TOL
