@@ -74,6 +74,16 @@ bool attention_tc_enabled() {
   return on;
 }
 
+bool stem_chain_enabled() {
+  static const bool on = env_flag("HGR_CHAIN_HALO", true);
+  return on && cluster_enabled();
+}
+
+bool conv1_tc_enabled() {
+  static const bool on = env_flag("HGR_CONV1_TC", false);  // measured: 0.320 ms against 0.30 ms (mma.sync), see conv1_tc.cu
+  return on;
+}
+
 bool pose_head_tc_enabled() {
   static const bool on = env_flag("HGR_POSE_TC", true);
   return on;

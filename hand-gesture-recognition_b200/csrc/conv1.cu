@@ -95,6 +95,10 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
   cp_async_commit();
 
   // ---- weights -> B fragments (registers, loaded once) ------------------
+  // SiLU is evaluated on h = x / 2 (x * sigmoid(x) = h + h * tanh(h)).  The halving and the BN shift ride INSIDE the
+  // MMA: every weight is halved (exact in bf16), and two of the five zero-padding slots of K carry shift / 2 as a
+  // bf16 hi + lo pair (k = 27, 28) against A slots forced to 1.0 - the accumulator then IS h and the epilogue is one
+  // MUFU, one FMA and half a pack per output (32 FMAs and 16 registers per tile less than an explicit affine).
   uint32_t bfrag[8][2][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
@@ -103,14 +107,28 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
       const __nv_bfloat16* wr = w + (nt * 8 + g) * 32 + s * 16 + 2 * t;
       bfrag[nt][s][0] = __ldg(reinterpret_cast<const uint32_t*>(wr));
       bfrag[nt][s][1] = __ldg(reinterpret_cast<const uint32_t*>(wr + 8));
-    }
-  // SiLU is evaluated on h = x/2 (x*sigmoid(x) = h + h*tanh(h)): keep shift/2, halve the accumulator with one FMA
-  float sh[8][2];
+      if constexpr (!RAW) {
+        const uint32_t half2 = 0x3F003F00u;  // (0.5, 0.5) bf16
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    sh[nt][0] = RAW ? 0.f : 0.5f * __ldg(shift + nt * 8 + 2 * t);
-    sh[nt][1] = RAW ? 0.f : 0.5f * __ldg(shift + nt * 8 + 2 * t + 1);
+        for (int i = 0; i < 2; ++i)
+          asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(bfrag[nt][s][i]) : "r"(bfrag[nt][s][i]), "r"(half2));
+      }
+    }
+  if constexpr (!RAW) {
+    // k = 16 s + 2 t + {0, 1, 8, 9}: k = 27 is the high half of bfrag[.][1][1] in lanes t == 1, k = 28 the low half
+    // of bfrag[.][1][1] in lanes t == 2
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float hs = 0.5f * __ldg(shift + nt * 8 + g);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(hs);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(hs - __bfloat162float(hi));
+      if (t == 1) bfrag[nt][1][1] = (bfrag[nt][1][1] & 0x0000FFFFu) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+      if (t == 2) bfrag[nt][1][1] = (bfrag[nt][1][1] & 0xFFFF0000u) | (uint32_t)__bfloat16_as_ushort(lo);
+    }
   }
+  // the matching A slots hold 1.0: (value & keep) | one, applied to a[1][2] / a[1][3] (k = 16 + 2 t + 8, + 9)
+  const uint32_t a_keep = RAW ? 0xFFFFFFFFu : (t == 1 ? 0x0000FFFFu : (t == 2 ? 0xFFFF0000u : 0xFFFFFFFFu));
+  const uint32_t a_one = RAW ? 0u : (t == 1 ? 0x3F800000u : (t == 2 ? 0x00003F80u : 0u));
   // per-thread gather offsets of its 8 k values: k = 16*s + 2*t + {0,1,8,9}
   int koff[8];
 #pragma unroll
@@ -166,6 +184,8 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
         a[s][2] = (uint32_t)e[2] | ((uint32_t)e[3] << 16);  // row g,   k 2t+8,2t+9
         a[s][3] = (uint32_t)e[6] | ((uint32_t)e[7] << 16);  // row g+8, k 2t+8,2t+9
       }
+      a[1][2] = (a[1][2] & a_keep) | a_one;  // slots 27 / 28: 1.0 against shift / 2 (hi, lo)
+      a[1][3] = (a[1][3] & a_keep) | a_one;
       __syncwarp();  // previous tile's staging reads are done
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -177,12 +197,9 @@ conv1_kernel(const TIn* __restrict__ x, __nv_bfloat16* __restrict__ out, const _
 #pragma unroll
           for (int i = 0; i < 4; ++i) h[i] = d[i];
         } else {
-          h[0] = fmaf(d[0], 0.5f, sh[nt][0]);
-          h[1] = fmaf(d[1], 0.5f, sh[nt][1]);
-          h[2] = fmaf(d[2], 0.5f, sh[nt][0]);
-          h[3] = fmaf(d[3], 0.5f, sh[nt][1]);
+          // d is (conv + shift) / 2 already
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = fmaf(h[i], tanh_approx(h[i]), h[i]);
+          for (int i = 0; i < 4; ++i) h[i] = fmaf(d[i], tanh_approx(d[i]), d[i]);
         }
         // staging is [16 pixels][64 ch]; XOR the 16-byte chunk with the pixel to spread banks
         *reinterpret_cast<uint32_t*>(st + g * 64 + swz[nt]) = pack_bf16x2(h[0], h[1]);
@@ -230,13 +247,17 @@ static int launch_conv1_impl(const void* x, int x_dtype, __nv_bfloat16* out, con
   return 0;
 }
 
+// The tcgen05 kernel (conv1_tc.cu) serves every image side the plans accept (multiples of 64) unless HGR_CONV1_TC=0;
+// this mma.sync kernel remains for other sides (hgr_conv1 accepts multiples of 32) and as the A/B reference.
 int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
                  int S, cudaStream_t stream) {
+  if (conv1_tc_enabled() && conv1_tc_supported(S)) return launch_conv1_tc(x, x_dtype, out, w, shift, B, S, false, stream);
   return launch_conv1_impl<false>(x, x_dtype, out, w, shift, B, S, stream);
 }
 
 int launch_conv1_raw(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, int B, int S,
                      cudaStream_t stream) {
+  if (conv1_tc_enabled() && conv1_tc_supported(S)) return launch_conv1_tc(x, x_dtype, out, w, nullptr, B, S, true, stream);
   return launch_conv1_impl<true>(x, x_dtype, out, w, nullptr, B, S, stream);
 }
 

@@ -54,4 +54,13 @@ int conv_chain_prefetch();  // HGR_CHAIN_PREFETCH=<items ahead>: L2 prefetch of 
 int build_conv_chain_op(ConvChainOp& op, const GemmOp& first, const GemmOp& second, const void* w2);
 int launch_conv_chain(const ConvChainOp& op, int num_sms, cudaStream_t stream);
 
+// Second version of the chained stem kernel (stem_chain.cu): the stride-2 layer's input patch is staged once per
+// 8 x 16 tile as four parity planes, the intermediate tile lives in tensor memory.  HGR_CHAIN_HALO=0 keeps
+// conv_chain.cu.  Needs an input map that tiles into 32 x 16 blocks and CTA pairs.
+bool stem_chain_enabled();
+bool stem_chain_supported(int H, int W);
+int run_stem_chain(const void* in, int B, int H, int W, const void* w1, const float* scale1, const float* shift1,
+                   const void* w2, const float* scale2, const float* shift2, void* out, int out_ctot, int out_coff,
+                   int reverse, int num_sms, cudaStream_t stream);
+
 }  // namespace hgr

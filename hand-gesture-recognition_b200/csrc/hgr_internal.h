@@ -160,6 +160,11 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 
 // --------------------------------------------------- small kernels ----
 // w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale folded in, k >= 27 zero; shift: [64] fp32.
+// HGR_CONV1_TC=0: the stem convolution falls back from the tcgen05 kernel (conv1_tc.cu) to the mma.sync kernel.
+bool conv1_tc_enabled();
+bool conv1_tc_supported(int S);
+int launch_conv1_tc(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
+                    int S, bool raw, cudaStream_t stream);
 int launch_conv1(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
                  int S, cudaStream_t stream);
 

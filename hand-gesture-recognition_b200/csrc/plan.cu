@@ -797,6 +797,16 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
     dir = zig ? !dir : 0;
     ConvChainOp* ch = &pl->stem_chain;
     ch->p.reverse = dir;
+    if (stem_chain_enabled() && stem_chain_supported(pl->S / 2, pl->S / 2)) {
+      // halo-staged version (stem_chain.cu): same operands, the patch of a tile is loaded once
+      const int rev = dir, H1s = pl->S / 2;
+      const std::string n0 = kConvs[0].name, n1 = kConvs[1].name;
+      add(n0 + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes, [pl, B, H1s, rev, n0, n1](cudaStream_t st, const Io&) {
+        return run_stem_chain(pl->bp("a1"), B, H1s, H1s, pl->pp<void>(n0 + ".w"), pl->pp<float>(n0 + ".scale"),
+                              pl->pp<float>(n0 + ".shift"), pl->pp<void>(n1 + ".w"), pl->pp<float>(n1 + ".scale"),
+                              pl->pp<float>(n1 + ".shift"), pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
+      });
+    } else
     add(std::string(kConvs[0].name) + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes,
         [ch](cudaStream_t st, const Io&) { return launch_conv_chain(*ch, device_sm_count(), st); });
     first_conv = 2;
@@ -1027,6 +1037,9 @@ int hgr_conv_chain(const void* d_in, int B, int H, int W, const void* d_w1, cons
     set_error("hgr_conv_chain: the chained kernel runs on CTA pairs (HGR_CLUSTER=0 disables them)");
     return -1;
   }
+  if (stem_chain_enabled() && stem_chain_supported(H, W))
+    return run_stem_chain(d_in, B, H, W, d_w1, d_scale1, d_shift1, d_w2, d_scale2, d_shift2, d_out, out_ctot, out_coff, 0,
+                          device_sm_count(), static_cast<cudaStream_t>(stream));
   // the intermediate buffer pointer of the two layer descriptors is never dereferenced: only their tile walk,
   // tensor maps of the outer tensors and epilogue parameters are taken over
   GemmOp first, second;

@@ -295,6 +295,18 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// CTA-pair MMA with the A operand in tensor memory: each CTA's 128 rows of A come from its own TMEM.
+__device__ __forceinline__ void umma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive (once every MMA issued so far has retired) on the mbarrier at this offset in every CTA of cta_mask.
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(

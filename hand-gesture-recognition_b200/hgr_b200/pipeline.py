@@ -196,3 +196,41 @@ class HandPipeline:
         """One batch, synchronously: (logits (B, C), keypoints (B, J, 2), confidences (B, J, 1)) on the host."""
         a, b, c = self.collect(self.submit(crops_u8))
         return a.clone(), b.clone(), c.clone()
+
+
+class ShardedHandPipeline:
+    """One process, several GPUs: BASELINE.json configs[2] ("batch 8192 sharded across 1/2/4/8 B200, no collective")
+    as a host-facing call.  A host batch of crops is cut into contiguous shards with `sharding.shard_range`, every
+    device runs its own replica of the model through its own HandPipeline (copy stream + compute stream + plan per
+    device), all shards are submitted before the first one is collected, and the results come back in batch order.
+    There is no cross-device traffic: every crop is independent (reference detect.py:119-155 classifies one crop at a
+    time).  The host buffers are pinned per device pipeline; the process is expected to be bound to the NUMA node of
+    its GPUs by the launcher (numactl) - PyTorch offers no per-allocation NUMA placement."""
+
+    def __init__(self, model: MultiTaskNet, devices, total_batch: int, compute_dtype=torch.bfloat16):
+        import copy
+        from .sharding import shard_range
+        devices = [torch.device(d) for d in devices]
+        if not devices or any(d.type != "cuda" for d in devices):
+            raise RuntimeError("ShardedHandPipeline needs CUDA devices; there is no CPU path")
+        if model.training:
+            raise RuntimeError("ShardedHandPipeline needs model.eval()")
+        self.total_batch = int(total_batch)
+        self.ranges = [shard_range(self.total_batch, r, len(devices)) for r in range(len(devices))]
+        self.pipes = []
+        home = next(model.parameters()).device
+        for d, (lo, hi) in zip(devices, self.ranges):
+            if hi == lo:
+                self.pipes.append(None)
+                continue
+            replica = model if d == home else copy.deepcopy(model).to(d).eval()
+            replica.return_attention = model.return_attention
+            self.pipes.append(HandPipeline(replica, hi - lo, compute_dtype, lanes=1))
+
+    def infer(self, crops_u8: torch.Tensor):
+        """(total_batch, S, S, 3) uint8 host crops -> (logits, keypoints, confidences) on the host, in batch order."""
+        if crops_u8.shape[0] != self.total_batch or crops_u8.is_cuda or crops_u8.dtype != torch.uint8:
+            raise ValueError(f"expected {self.total_batch} host uint8 crops")
+        lanes = [p.submit(crops_u8[lo:hi]) if p is not None else None for p, (lo, hi) in zip(self.pipes, self.ranges)]
+        outs = [p.collect(ln) for p, ln in zip(self.pipes, lanes) if p is not None]
+        return tuple(torch.cat([o[k] for o in outs]) for k in range(3))

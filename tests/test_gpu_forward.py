@@ -178,6 +178,26 @@ def test_hand_pipeline_matches_the_module_and_the_frames_path():
     assert torch.equal(l2, logits) and torch.equal(k2, kps) and torch.equal(c2, conf)
 
 
+def test_sharded_pipeline_equals_the_single_pipeline():
+    """configs[2] as a one-process call: contiguous shards (shard_range), one pipeline per device, results in batch
+    order.  With one GPU in the box both shards run on it; with more they spread over the first two."""
+    from hgr_b200 import HandPipeline, ShardedHandPipeline
+    m, _ = build(192, 0)
+    m.return_attention = False
+    g = torch.Generator().manual_seed(3)
+    crops = torch.randint(0, 256, (7, 192, 192, 3), dtype=torch.uint8, generator=g)
+    ref = HandPipeline(m, 7, torch.bfloat16).infer(crops)
+    n = min(2, torch.cuda.device_count())
+    devs = [f"cuda:{i % n}" for i in range(2)]
+    sh = ShardedHandPipeline(m, devs, 7, torch.bfloat16)
+    assert sh.ranges == [(0, 4), (4, 7)]
+    out = sh.infer(crops)
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        sh.infer(crops[:5])
+
+
 def test_classifier_session_has_the_onnxruntime_contract():
     """detect.py:143-155 verbatim against ClassifierSession: same call sequence, (label_pred, heatmap_pred) out."""
     from hgr_b200 import ClassifierSession

@@ -189,7 +189,7 @@ def test_linear_with_folded_layernorm(lib, rows, cout, act):
     del packing
 
 
-@pytest.mark.parametrize("b,h", [(2, 96), (3, 96), (1, 32), (5, 64)])
+@pytest.mark.parametrize("b,h", [(2, 96), (3, 96), (1, 32), (5, 64), (41, 96), (3, 128)])
 def test_conv_chain(lib, b, h):
     """conv2 -> cspelan1.cv1 (reference model/gelan.py:156, :127) as one CTA-pair kernel against the fp32 operators
     and against the two separate hgr_conv_bn_act launches it replaces (same rounding point for the tensor between)."""
@@ -282,12 +282,13 @@ def test_vit_block(lib, rows, inplace):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-@pytest.mark.parametrize("size", [64, 192])
-def test_conv1(lib, dtype, size):
+@pytest.mark.parametrize("size,b", [(64, 3), (192, 3), (192, 41), (256, 5), (128, 1), (96, 2)])
+def test_conv1(lib, dtype, size, b):
+    """Sides that are multiples of 64 run the tcgen05 kernel (conv1_tc.cu; b = 41 gives every CTA several bands, both
+    patch buffers and both accumulator stages), 96 the mma.sync kernel (conv1.cu)."""
     from hgr_b200 import _lib
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(size)
-    b = 3
     x = torch.randn(b, 3, size, size, generator=g)
     if dtype == torch.bfloat16:
         x = bf16_round(x)
@@ -305,7 +306,7 @@ def test_conv1(lib, dtype, size):
     torch.cuda.synchronize()
     wref = wk.float().cpu()[:, :27].reshape(64, 3, 3, 3).permute(0, 3, 1, 2)  # the bf16-rounded folded weights
     ref = F.silu(F.conv2d(bf16_round(x), wref, None, stride=2, padding=1) + shift.view(1, -1, 1, 1))
-    r, m = report(f"conv1 {size} {dtype}", nchw_f32(out), ref)
+    r, m = report(f"conv1 {size} b={b} {dtype}", nchw_f32(out), ref)
     assert r <= REL_TOL and m <= MAX_TOL
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE operator of the C ABI a few times at the headline batch (development tool: the command ncu wraps when a
-single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head> [B] [reps]"""
+single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head|conv1> [B] [reps]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hand-gesture-recognition_b200"))
 import torch
@@ -28,6 +28,15 @@ elif op == "pose_head":
     heat = torch.empty(B, J, 4 * F, 4 * F, dtype=torch.bfloat16, device=dev)
     run = lambda: _lib.check(lib.hgr_pose_head(tok.data_ptr(), w.data_ptr(), bias.data_ptr(), heat.data_ptr(), _lib.BF16,
                                                B, F, J, st), op)
+elif op == "conv1":
+    S = 192
+    x = torch.randn(B, 3, S, S, generator=g, device=dev).bfloat16()
+    wk = torch.zeros(64, 32, device=dev)
+    wk[:, :27] = torch.randn(64, 27, generator=g, device=dev) * 0.27
+    wk = wk.bfloat16()
+    sh = torch.randn(64, generator=g, device=dev) * 0.3
+    out = torch.empty(B, S // 2, S // 2, 64, dtype=torch.bfloat16, device=dev)
+    run = lambda: _lib.check(lib.hgr_conv1(x.data_ptr(), _lib.BF16, B, S, wk.data_ptr(), sh.data_ptr(), out.data_ptr(), st), op)
 else:
     raise SystemExit(f"unknown op {op}")
 for _ in range(2):
