@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--total-batch", type=int, default=0,
                     help="BASELINE.json configs[2]: one batch of this many crops sharded over the ranks (strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--train-graph", action="store_true",
+                    help="--workload train: replay forward + loss + backward from a CUDA graph")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the memory-tail roofline, the GPU eager baseline, the parity slice and the train record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -92,7 +94,7 @@ def ncu_traffic_per_launch():
     files = sorted((ROOT / "profiles").glob("*_step_ncu_full.csv"))
     if not files:
         return None, None
-    rows = [r for r in csv.DictReader(files[-1].open()) if any(k in r["Kernel Name"] for k in ("gemm_kernel", "halo", "vit_block"))]
+    rows = [r for r in csv.DictReader(files[-1].open()) if any(k in r["Kernel Name"] for k in ("gemm_kernel", "halo", "vit_block", "stem_chain", "conv_chain"))]
     if not rows:
         return None, None
     rd = [k for k in rows[0] if k.startswith("dram__bytes_read.sum")][0]
@@ -435,7 +437,7 @@ def run_train(args, rank, world, local_rank):
     model = MultiTaskNet(21, 19, [S, S])
     synthetic_weights(model)
     model = model.to(dev).train()
-    tr = DataParallelTrainer(model, lr=1e-4)
+    tr = DataParallelTrainer(model, lr=1e-4, cuda_graph=args.train_graph)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(B, 3, S, S, generator=g, device=dev)
     # synthetic supervision of the shape train.py feeds: class labels, Gaussian-blob target heatmaps (sigma 2,
@@ -477,7 +479,7 @@ def run_train(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"MultiTaskNet training step bf16 (fp32 master weights), batch {B} per GPU, 3x{S}x{S}, "
                                    "loss 0.001*CE + JointsMSE, AdamW, NCCL all-reduce of the flat 7.4M-element gradient "
-                                   "block (BASELINE.json configs[4])",
+                                   "block (BASELINE.json configs[4])" + ("; forward + loss + backward replayed from a CUDA graph" if args.train_graph else ""),
                        "batch_per_gpu": B, "image_size": S,
                        "train_gflop_per_image_convention_3x_forward": 3 * gf if gf else None,
                        "tensor_frac_of_sustained": value / world * 3 * gf * 1e9 / (pk["bf16_sustained"] * 1e12) if gf else None},
@@ -599,7 +601,7 @@ def main():
         ms = [statistics.median(r[i] for r in runs) for i in range(len(info))]
         step_ms = sum(ms)
         for (name, kind, fl, by), t in zip(info, ms):
-            table.append({"launch": name, "kind": ["tcgen05_gemm", "mma_sync", "memory"][kind], "ms": t,
+            table.append({"launch": name, "kind": ["tcgen05_gemm", "mma_sync", "memory", "tcgen05_fused"][kind], "ms": t,
                           "share": t / step_ms, "tflops": fl / (t * 1e-3) / 1e12 if t > 0 else None,
                           "gbs": by / (t * 1e-3) / 1e9 if t > 0 else None})
         gem = [(fl, t) for (name, kind, fl, by), t in zip(info, ms) if kind == 0]
@@ -613,7 +615,8 @@ def main():
                                        "launch averaged over the GEMM launches of one step") if traffic else None,
                     "algorithmic_bytes_per_launch_avg": g_by / len(gem),
                     "kernel": f"tcgen05 GEMM kernels: hgr::gemm_kernel<BN> / conv3x3_halo_kernel (implicit GEMM) and the chained "
-                              f"vit_block_kernel, {len(gem)} launches per step",
+                              f"stem_chain_kernel / vit_block_kernel, {len(gem)} launches per step (the fused tcgen05 attention and "
+                              f"pose-head kernels are listed in per_kernel against their own bounds)",
                     "share_of_step": g_ms / step_ms, "launch_ms_avg": g_ms / len(gem),
                     "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "flops_per_launch_avg": g_fl / len(gem)}

@@ -556,7 +556,8 @@ struct hgr_plan {
   };
   struct Step {
     std::string name;
-    int kind;      // 0 = tcgen05 implicit GEMM, 1 = mma.sync kernel, 2 = memory-bound kernel
+    int kind;      // 0 = tcgen05 implicit GEMM, 1 = mma.sync kernel, 2 = memory-bound kernel, 3 = fused tcgen05 kernel
+                   // (attention, pose head: tensor-core contractions inside a kernel bound by something else)
     double flops;  // algorithmic
     double bytes;  // algorithmic
     std::function<int(cudaStream_t, const Io&)> run;
@@ -825,7 +826,10 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
     const bool last = l == kDepth - 1;
     dir = zig ? !dir : 0;
     const int attn_dir = dir;
-    add(a + "attention", 1, 4.0 * dB * kHeads * T * T * 32, (double)rows * kDim * 2 * 4,
+    // the last layer returns probabilities only when the caller asks for them (decided per call): label by the kernel
+    // the benchmark configuration runs
+    add(a + "attention", attention_tc_enabled() && attention_tc_supported(T) ? 3 : 1, 4.0 * dB * kHeads * T * T * 32,
+        (double)rows * kDim * 2 * 4,
         [pl, B, T, last, attn_dir](cudaStream_t st, const Io& io) {
           return launch_attention(pl->bp("qkv"), pl->bp("attn_out"), last ? io.attn : nullptr, io.out_dtype, B, T, st,
                                   attn_dir);
@@ -847,7 +851,8 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
                            pl->pp<float>("decoder.mlp_head.0.bias"), pl->pp<float>("decoder.mlp_head.1.weight"),
                            pl->pp<float>("decoder.mlp_head.1.bias"), io.logits, io.out_dtype, B, T, pl->C, st);
   });
-  add("decoder.simple_decoder", 1, 2.0 * dB * (dS / 4) * (dS / 4) * kDim * J,
+  add("decoder.simple_decoder", pose_head_tc_enabled() && pose_head_tc_supported(pl->F, J) ? 3 : 1,
+      2.0 * dB * (dS / 4) * (dS / 4) * kDim * J,
       (double)rows * kDim * 2 + dB * J * (dS / 4) * (dS / 4) * 2, [pl, B](cudaStream_t st, const Io& io) {
         return launch_pose_head(pl->bp("tokens"), pl->pp<__nv_bfloat16>("decoder.simple_decoder.1.w"),
                                 pl->pp<float>("decoder.simple_decoder.1.bias"), io.heat, io.out_dtype, B, pl->F, pl->J,

@@ -284,7 +284,8 @@ class DataParallelTrainer:
     rank-local, like DDP with broadcast_buffers=False.
     """
 
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, cls_weight=0.001, group=None):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, cls_weight=0.001, group=None,
+                 cuda_graph=False):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("DataParallelTrainer needs the module on a CUDA device (no CPU path)")
@@ -293,6 +294,10 @@ class DataParallelTrainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.cls_weight = cls_weight
         self.group = group
+        # cuda_graph=True: forward + loss + backward (~360 launches of a few microseconds each at batch 32) are
+        # captured once per input shape and replayed; the all-reduce and the AdamW update stay ordinary launches
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         self.exp_avg = torch.zeros_like(self.state.params)
         self.exp_avg_sq = torch.zeros_like(self.state.params)
         self.steps = 0
@@ -300,11 +305,43 @@ class DataParallelTrainer:
         broadcast_from_rank0_([self.state.params, self.state.bnstats, self.state.num_batches_tracked,
                                self.exp_avg, self.exp_avg_sq], group)
 
-    def step(self, x, labels, target, target_weight):
+    def _forward_backward(self, x, labels, target, target_weight, update_running=True):
         st = self.state
-        logits, heat, plan = forward_train(st, x)
+        logits, heat, plan = forward_train(st, x, update_running)
         loss3, dlogits, dheat = loss_and_grads(logits, heat, labels, target, target_weight, self.cls_weight)
         backward_train(st, plan, x, dlogits, dheat)
+        return loss3
+
+    def _forward_backward_graph(self, x, labels, target, target_weight):
+        key = (tuple(x.shape), x.dtype, tuple(target.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = x.device
+            static = [torch.empty_like(t) for t in (x, labels, target, target_weight)]
+            for s_, t in zip(static, (x, labels, target, target_weight)):
+                s_.copy_(t)
+            # plan creation, kernel attributes and the first-touch allocations happen outside the capture; the
+            # warm-up leaves the running statistics alone (the captured forward updates them exactly once per step)
+            self._forward_backward(*static, update_running=False)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss3 = self._forward_backward(*static)
+            entry = self._graphs[key] = (graph, static, loss3)
+            # the capture itself does not execute: replay below performs the step
+        graph, static, loss3 = entry
+        for s_, t in zip(static, (x, labels, target, target_weight)):
+            if s_.data_ptr() != t.data_ptr():
+                s_.copy_(t, non_blocking=True)
+        graph.replay()
+        return loss3
+
+    def step(self, x, labels, target, target_weight):
+        st = self.state
+        if self.cuda_graph:
+            loss3 = self._forward_backward_graph(x, labels, target, target_weight)
+        else:
+            loss3 = self._forward_backward(x, labels, target, target_weight)
         world = allreduce_sum_(st.grads, self.group)
         self.steps += 1
         with torch.cuda.device(x.device):

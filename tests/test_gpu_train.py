@@ -279,3 +279,104 @@ def test_trainer_reduces_the_loss_and_matches_adamw():
         losses.append(float(tr.step(*args)[0]))
     print("[parity] trainer losses", [round(v, 4) for v in losses], flush=True)
     assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0]
+
+
+def test_trainer_cuda_graph_replay_equals_plain_launches():
+    """DataParallelTrainer(cuda_graph=True) replays forward + loss + backward from one captured graph; the step is
+    deterministic, so three graph steps leave exactly the parameters, moments and running statistics of three plain
+    steps - including the first call, whose warm-up must not touch the running statistics."""
+    from hgr_b200 import DataParallelTrainer, MultiTaskNet
+    dev = torch.device("cuda")
+    sd = O.synthetic_state_dict(5)
+    xs = [O.synthetic_images(4, 64, 20 + i).to(dev) for i in range(3)]
+    labels, target, weight = (t.to(dev) for t in O.synthetic_targets(4, 64, seed=7))
+    out = []
+    for graph in (False, True):
+        net = MultiTaskNet(21, 19, [64, 64])
+        net.load_state_dict(sd, strict=True)
+        net = net.to(dev).train()
+        tr = DataParallelTrainer(net, lr=1e-3, cuda_graph=graph)
+        losses = [tr.step(x, labels, target, weight).clone() for x in xs]
+        torch.cuda.synchronize()
+        out.append((tr.state.params.clone(), tr.state.bnstats.clone(), tr.state.num_batches_tracked.clone(),
+                    tr.exp_avg.clone(), torch.stack(losses)))
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    assert int(out[1][2][0]) == 100 + 3  # synthetic_state_dict starts the counters at 100
+
+
+def _dp_gpu_worker(rank, world, port, q):
+    """One rank of the 2-GPU data-parallel check (spawned: own process, own GPU, NCCL)."""
+    import os
+    import torch.distributed as dist
+    from hgr_b200 import DataParallelTrainer, MultiTaskNet, loss_and_grads
+    from hgr_b200.training import allreduce_sum_, backward_train, forward_train, replicas_in_sync
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    size, per = 64, 4
+    # every rank starts from DIFFERENT weights: the trainer must make rank 0's the common replica
+    net = MultiTaskNet(21, 19, [size, size])
+    net.load_state_dict(O.synthetic_state_dict(5 + rank), strict=True)
+    net = net.to(dev).train()
+    tr = DataParallelTrainer(net, lr=1e-3)
+    in_sync = replicas_in_sync(tr.state.params) and replicas_in_sync(tr.state.bnstats)
+    x = O.synthetic_images(world * per, size, 6)
+    labels, target, weight = O.synthetic_targets(world * per, size, seed=7)
+    sl = slice(rank * per, (rank + 1) * per)
+    xs = x[sl].to(dev)
+    logits, heat, plan = forward_train(tr.state, xs, update_running=False)
+    _, dl, dh = loss_and_grads(logits, heat, labels[sl].to(dev), target[sl].to(dev), weight[sl].to(dev))
+    backward_train(tr.state, plan, xs, dl, dh)
+    w = allreduce_sum_(tr.state.grads)
+    mean_grads = (tr.state.grads / w).cpu()
+    loss3 = tr.step(xs, labels[sl].to(dev), target[sl].to(dev), weight[sl].to(dev))
+    after = replicas_in_sync(tr.state.params)
+    q.put((rank, bool(in_sync), bool(after), mean_grads.numpy(), [float(v) for v in loss3.cpu()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_dp_step_on_two_gpus_averages_the_shard_gradients():
+    """SURVEY.md section 4 item 6 / BASELINE.json configs[4]: on 2 ranks that START from different weights the
+    trainer first makes rank 0's parameters, BatchNorm statistics and moments the common replica (broadcast), the
+    all-reduced gradient block equals the MEAN of the per-shard gradients of the reference algorithm (oracle, fp32,
+    local BatchNorm statistics per shard like the reference's plain nn.BatchNorm2d), and the replicas are still
+    bit-identical after the step."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), "parameters not broadcast from rank 0 at construction"
+    assert all(r[2] for r in res), "replicas diverged after one step"
+    assert np.array_equal(res[0][3], res[1][3]), "ranks hold different averaged gradients"
+    # oracle: mean over the two shards of the reference's gradients, on rank 0's weights
+    sd = O.synthetic_state_dict(5)
+    x = O.synthetic_images(8, 64, 6)
+    labels, target, weight = O.synthetic_targets(8, 64, seed=7)
+    from hgr_b200 import _lib
+    layout = _lib.train_param_layout(21, 19)
+    ref = None
+    for r in range(2):
+        sl = slice(4 * r, 4 * r + 4)
+        _, grads, _, _ = O.train_step_grads(sd, x[sl], labels[sl], target[sl], weight[sl])
+        flat = torch.cat([grads[name].flatten().double() for name, _, _ in layout])
+        ref = flat if ref is None else ref + flat
+    ref = ref / 2
+    got = torch.cat([torch.from_numpy(res[0][3])[off: off + n].double() for _, off, n in layout])
+    cos = float((got @ ref) / (got.norm() * ref.norm()))
+    rel = float((got - ref).norm() / ref.norm())
+    print(f"[parity] 2-GPU DP averaged gradient vs mean of per-shard oracle gradients: cosine {cos:.5f} rel-L2 {rel:.3e}",
+          flush=True)
+    assert cos >= 0.99 and rel <= 0.15

@@ -210,7 +210,7 @@ def test_committed_ncu_capture_feeds_the_roofline_traffic():
     assert 1e8 < per_launch < 2e9, per_launch
     rows = list(csv.DictReader((root / "profiles" / name).open()))
     kernels = " ".join(r["Kernel Name"] for r in rows)
-    for needle in ("gemm_kernel", "halo", "conv1_kernel", "attention_kernel", "pose_head_kernel"):
+    for needle in ("gemm_kernel", "halo", "conv1_kernel", "stem_chain_kernel", "attention_tc_kernel", "pose_head_tc_kernel"):
         assert needle in kernels, needle
     shares = [float(r["share_of_step_ncu"]) for r in rows]
     assert abs(sum(shares) - 1.0) < 1e-2
