@@ -74,6 +74,11 @@ bool attention_tc_enabled() {
   return on;
 }
 
+bool stem_fused_enabled() {
+  static const bool on = env_flag("HGR_STEM_FUSED", true);
+  return on;
+}
+
 bool stem_chain_enabled() {
   static const bool on = env_flag("HGR_CHAIN_HALO", true);
   return on && cluster_enabled();
@@ -140,7 +145,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }  // namespace
 
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                         const uint32_t* box) {
+                         const uint32_t* box, int swizzle_bytes) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -157,7 +162,9 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
     if (i > 0) gstride[i - 1] = strides[i - 1];
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstride, bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstride, bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu %llu %llu %llu %llu box %u %u %u %u %u)",

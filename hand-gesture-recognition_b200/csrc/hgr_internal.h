@@ -154,9 +154,11 @@ int build_vit_block_op(VitBlockOp& op, const void* attn_out, const void* x0, lon
 int launch_vit_block(const VitBlockOp& op, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------ tensor maps ----
-// rank <= 5; dims innermost first; strides in bytes for dims 1..rank-1.
+// rank <= 5; dims innermost first; strides in bytes for dims 1..rank-1.  swizzle_bytes: 128 / 64 = SWIZZLE_128B /
+// SWIZZLE_64B (innermost box extent at most that many bytes), 0 = the box lands dense (innermost box extent a multiple
+// of 16 bytes).  The innermost start coordinate of a load must sit on a 16-byte boundary of the tensor row.
 int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                         const uint32_t* box);
+                         const uint32_t* box, int swizzle_bytes = 128);
 
 // --------------------------------------------------- small kernels ----
 // w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale folded in, k >= 27 zero; shift: [64] fp32.

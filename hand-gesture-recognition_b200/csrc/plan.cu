@@ -788,29 +788,57 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
   };
   const int T = pl->T;
   const double dB = B, dS = S;
-  add("encoder.conv1", 1, 2.0 * dB * (dS / 2) * (dS / 2) * 64 * 27,
-      dB * 3 * dS * dS * 2 + dB * (dS / 2) * (dS / 2) * 64 * 2, [pl, B](cudaStream_t st, const Io& io) {
-        return launch_conv1(io.x, io.x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
-                            pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
-      });
+  const double conv1_flops = 2.0 * dB * (dS / 2) * (dS / 2) * 64 * 27;
+  const double conv1_bytes = dB * 3 * dS * dS * 2 + dB * (dS / 2) * (dS / 2) * 64 * 2;
+  auto run_conv1 = [pl, B](cudaStream_t st, const Io& io) {
+    return launch_conv1(io.x, io.x_dtype, pl->bp("a1"), pl->pp<__nv_bfloat16>("encoder.conv1.w"),
+                        pl->pp<float>("encoder.conv1.shift"), B, pl->S, st);
+  };
   int first_conv = 0;
   if (pl->conv_chain) {
-    dir = zig ? !dir : 0;
     ConvChainOp* ch = &pl->stem_chain;
-    ch->p.reverse = dir;
-    if (stem_chain_enabled() && stem_chain_supported(pl->S / 2, pl->S / 2)) {
-      // halo-staged version (stem_chain.cu): same operands, the patch of a tile is loaded once
-      const int rev = dir, H1s = pl->S / 2;
-      const std::string n0 = kConvs[0].name, n1 = kConvs[1].name;
-      add(n0 + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes, [pl, B, H1s, rev, n0, n1](cudaStream_t st, const Io&) {
-        return run_stem_chain(pl->bp("a1"), B, H1s, H1s, pl->pp<void>(n0 + ".w"), pl->pp<float>(n0 + ".scale"),
-                              pl->pp<float>(n0 + ".shift"), pl->pp<void>(n1 + ".w"), pl->pp<float>(n1 + ".scale"),
-                              pl->pp<float>(n1 + ".shift"), pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
-      });
-    } else
-    add(std::string(kConvs[0].name) + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes,
-        [ch](cudaStream_t st, const Io&) { return launch_conv_chain(*ch, device_sm_count(), st); });
+    const std::string n0 = kConvs[0].name, n1 = kConvs[1].name;
+    const int H1s = pl->S / 2;
+    auto run_chain_halo = [pl, B, H1s, n0, n1](cudaStream_t st, int rev) {
+      return run_stem_chain(pl->bp("a1"), B, H1s, H1s, pl->pp<void>(n0 + ".w"), pl->pp<float>(n0 + ".scale"),
+                            pl->pp<float>(n0 + ".shift"), pl->pp<void>(n1 + ".w"), pl->pp<float>(n1 + ".scale"),
+                            pl->pp<float>(n1 + ".shift"), pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
+    };
+    const bool halo = stem_chain_enabled() && stem_chain_supported(H1s, H1s);
+    if (halo && stem_fused_enabled() && stem_fused_supported(pl->S)) {
+      // conv1 -> conv2 -> cspelan1.cv1 in one launch (stem_fused.cu): a1 never reaches HBM.  The kernel reads a bf16
+      // batch through a TMA box; an fp32 batch (decided per call) takes the two launches it replaces.
+      dir = zig ? !dir : 0;
+      const int rev = dir;
+      add("encoder.conv1+" + std::string(kConvs[0].name + 8) + "+" + (kConvs[1].name + 8), 0, conv1_flops + ch->flops,
+          ch->bytes - dB * (dS / 2) * (dS / 2) * 64 * 2 + dB * 3 * dS * dS * 2,
+          [pl, B, rev, n0, n1, run_conv1, run_chain_halo](cudaStream_t st, const Io& io) {
+            if (io.x_dtype != DT_BF16 || (reinterpret_cast<uintptr_t>(io.x) & 15u) != 0) {
+              if (int rc = run_conv1(st, io)) return rc;
+              return run_chain_halo(st, rev);
+            }
+            return run_stem_fused(io.x, B, pl->S, pl->pp<void>("encoder.conv1.w"), pl->pp<float>("encoder.conv1.shift"),
+                                  pl->pp<void>(n0 + ".w"), pl->pp<float>(n0 + ".scale"), pl->pp<float>(n0 + ".shift"),
+                                  pl->pp<void>(n1 + ".w"), pl->pp<float>(n1 + ".scale"), pl->pp<float>(n1 + ".shift"),
+                                  pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
+          });
+    } else {
+      add("encoder.conv1", 1, conv1_flops, conv1_bytes, run_conv1);
+      dir = zig ? !dir : 0;
+      ch->p.reverse = dir;
+      if (halo) {
+        // halo-staged version (stem_chain.cu): same operands, the patch of a tile is loaded once
+        const int rev = dir;
+        add(n0 + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes,
+            [run_chain_halo, rev](cudaStream_t st, const Io&) { return run_chain_halo(st, rev); });
+      } else {
+        add(n0 + "+" + (kConvs[1].name + 8), 0, ch->flops, ch->bytes,
+            [ch](cudaStream_t st, const Io&) { return launch_conv_chain(*ch, device_sm_count(), st); });
+      }
+    }
     first_conv = 2;
+  } else {
+    add("encoder.conv1", 1, conv1_flops, conv1_bytes, run_conv1);
   }
   for (int i = first_conv; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
   add("decoder.cls_token", 2, 0, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io&) {
@@ -1057,6 +1085,17 @@ int hgr_conv_chain(const void* d_in, int B, int H, int W, const void* d_w1, cons
   ConvChainOp op;
   if (int rc = build_conv_chain_op(op, first, second, d_w2)) return rc;
   return launch_conv_chain(op, device_sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+int hgr_stem_fused(const void* d_x, int B, int S, const void* d_w0, const float* d_shift0, const void* d_w1,
+                   const float* d_scale1, const float* d_shift1, const void* d_w2, const float* d_scale2,
+                   const float* d_shift2, void* d_out, int out_ctot, int out_coff, void* stream) {
+  if (!cluster_enabled()) {
+    set_error("hgr_stem_fused: the fused stem kernel runs on CTA pairs (HGR_CLUSTER=0 disables them)");
+    return -1;
+  }
+  return run_stem_fused(d_x, B, S, d_w0, d_shift0, d_w1, d_scale1, d_shift1, d_w2, d_scale2, d_shift2, d_out, out_ctot,
+                        out_coff, 0, device_sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale, const float* d_bias,

@@ -92,7 +92,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 
+// Development aid: when a kernel's host wrapper points this at mapped host memory, a timed-out wait leaves
+// {0xDEAD, block, thread, barrier address, parity} there, readable after the trap has killed the context's printf.
+static __device__ volatile unsigned int* hgr_dbg_ptr = nullptr;
+
 static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  if (hgr_dbg_ptr) {
+    hgr_dbg_ptr[1] = blockIdx.x;
+    hgr_dbg_ptr[2] = threadIdx.x;
+    hgr_dbg_ptr[3] = bar;
+    hgr_dbg_ptr[4] = parity;
+    hgr_dbg_ptr[0] = 0xDEADu;
+    __threadfence_system();
+  }
   printf("hgr: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
   __trap();
 }
@@ -132,6 +144,25 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Register re-allocation between the warpgroups of a warp-specialised CTA (every warp of the warpgroup executes it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // CTA-pair (cta_group::2) loads: the data lands in the EXECUTING CTA's shared memory, the transaction bytes are

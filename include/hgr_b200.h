@@ -139,6 +139,18 @@ HGR_API int hgr_conv_chain(const void* d_in, int B, int H, int W, const void* d_
                            const float* d_shift1, const void* d_w2, const float* d_scale2, const float* d_shift2,
                            void* d_out, int out_ctot, int out_coff, void* stream);
 
+/* encoder.conv1 -> encoder.conv2 -> encoder.cspelan1.cv1 as one kernel (reference model/gelan.py:155 Conv(3, 64, 3, 2),
+ * :156 Conv(64, 128, 3, 2), :127 GELANBlock.cv1 = Conv(128, 128, 1, 1), each conv + folded BatchNorm + SiLU): neither
+ * the 64-channel nor the 128-channel tensor between the layers reaches HBM; both are rounded to bf16 where the
+ * separate launches (hgr_conv1, hgr_conv_chain) store them.
+ *   d_x    NCHW bf16 (B, 3, S, S), S a multiple of 64, 16-byte aligned
+ *   d_w0   bf16 [64][32] as for hgr_conv1 (BN scale folded in), d_shift0 fp32 [64]
+ *   d_w1   bf16 [128][9][64];  d_w2 bf16 [128][128]
+ *   d_out  NHWC bf16 (B, S/4, S/4, out_ctot); channels [out_coff, out_coff + 128) written */
+HGR_API int hgr_stem_fused(const void* d_x, int B, int S, const void* d_w0, const float* d_shift0, const void* d_w1,
+                           const float* d_scale1, const float* d_shift1, const void* d_w2, const float* d_scale2,
+                           const float* d_shift2, void* d_out, int out_ctot, int out_coff, void* stream);
+
 /* y = act(scale (.) (x W^T) + bias) (+ residual): nn.Linear of the ViT
  * (reference model/transformer.py:34,37,65,75).  x (rows, cin) bf16,
  * W (cout, cin) bf16, y (rows, cout) bf16; d_scale / d_bias / d_res nullable.

@@ -74,6 +74,9 @@ def test_headline_batch1024_bf16_io_per_stage():
     assert attn is None and cls.dtype == hm.dtype == torch.bfloat16
     plan = m.plan_for(batch, torch.device("cuda", torch.cuda.current_device()))
     stages = ["a1", "o1", "d1", "o2", "d2", "o3"]
+    if any("conv1+" in l[0] for l in plan.launch_table()):
+        stages.remove("a1")  # conv1 -> conv2 -> cspelan1.cv1 runs as one kernel on a bf16 batch: a1 never reaches HBM
+        # (test_stem_fused compares that kernel with the launches it replaces; HGR_STEM_FUSED=0 below runs them here)
     bufs = {n: plan.buffer(n) for n in stages}
     tok = plan.buffer("tokens").reshape(batch, -1, 256)
     acc = {n: _Acc() for n in stages + ["tokens_l3", "logits", "heatmaps"]}
@@ -171,8 +174,8 @@ np.savez({out!r}, cls=cls.float().cpu().numpy(), hm=hm[:, :, ::3, ::3].float().c
 """
 
 
-@pytest.mark.parametrize("switch", ["HGR_CONV_CHAIN=0", "HGR_VIT_FUSED=0", "HGR_CLUSTER=0", "HGR_ZIGZAG=0",
-                                    "HGR_ATTN_TC=0"])
+@pytest.mark.parametrize("switch", ["HGR_STEM_FUSED=0", "HGR_CONV_CHAIN=0", "HGR_VIT_FUSED=0", "HGR_CLUSTER=0",
+                                    "HGR_ZIGZAG=0", "HGR_ATTN_TC=0"])
 def test_toggled_launch_paths_agree_with_the_default_path(switch, tmp_path):
     """Every run-time switch selects a different kernel or tile order for the same arithmetic; the library reads them
     once per process, so each variant runs in its own interpreter.  Batch 256 gives every persistent kernel several
@@ -190,6 +193,9 @@ def test_toggled_launch_paths_agree_with_the_default_path(switch, tmp_path):
         outs[tag] = np.load(out)
     a, b = outs["default"], outs["variant"]
     print(f"[parity] {switch}: launches {int(a['launches'])} -> {int(b['launches'])}", flush=True)
-    for key, tol in (("o3", 6e-3), ("cls", 6e-3), ("hm", 6e-3)):
+    # two bf16 paths that differ in ONE rounding anywhere upstream decorrelate layer by layer and end up about sqrt(2) x
+    # the rounding share of their own error against fp32 apart (o3: 9.8e-3 against the oracle), so the bar between two
+    # variants is 1e-2 - still below the 1.5e-2 bar against the oracle
+    for key, tol in (("o3", 1e-2), ("cls", 1e-2), ("hm", 1e-2)):
         r, _ = report(f"{switch} {key} vs default path", torch.from_numpy(b[key]), torch.from_numpy(a[key]))
         assert r <= tol

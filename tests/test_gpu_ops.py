@@ -227,6 +227,57 @@ def test_conv_chain(lib, b, h):
     assert r2 <= 1e-3
 
 
+@pytest.mark.parametrize("b,size", [(2, 192), (3, 192), (1, 64), (5, 128), (41, 192), (3, 256)])
+def test_stem_fused(lib, b, size):
+    """conv1 -> conv2 -> cspelan1.cv1 (reference model/gelan.py:155, :156, :127) as one kernel against the fp32
+    operators and against the two launches it replaces (hgr_conv1 + hgr_conv_chain: the same conv1 arithmetic and
+    rounding points, conv2's taps summed in another order).  b = 41 gives every CTA pair several tiles (both input
+    patch buffers, both accumulator stages, the per-plane barriers through several phases); b = 3 an odd image count."""
+    from hgr_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(b * 1000 + size)
+    x = bf16_round(torch.randn(b, 3, size, size, generator=g))
+    w0 = torch.randn(64, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    s0, t0 = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    w1 = torch.randn(128, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    w2 = torch.randn(128, 128, 1, 1, generator=g) * (2.0 / 128) ** 0.5
+    s1, s2 = torch.rand(128, generator=g) + 0.5, torch.rand(128, generator=g) + 0.5
+    t1, t2 = torch.randn(128, generator=g) * 0.3, torch.randn(128, generator=g) * 0.3
+    wk = torch.zeros(64, 32)
+    wk[:, :27] = (w0 * s0.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 27)
+    wk = wk.to(dev, torch.bfloat16)
+    t0d = t0.to(dev)
+    w1d = w1.permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    w2d = w2.reshape(128, 128).contiguous().to(dev, torch.bfloat16)
+    s1d, s2d, t1d, t2d = (t.to(dev).float().contiguous() for t in (s1, s2, t1, t2))
+    xd = x.to(dev, torch.bfloat16).contiguous()
+    q = size // 4
+    out = torch.full((b, q, q, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_stem_fused(xd.data_ptr(), b, size, wk.data_ptr(), t0d.data_ptr(), w1d.data_ptr(), s1d.data_ptr(),
+                            t1d.data_ptr(), w2d.data_ptr(), s2d.data_ptr(), t2d.data_ptr(), out.data_ptr(), 256, 64,
+                            _stream()), "hgr_stem_fused")
+    torch.cuda.synchronize()
+    got = nchw_f32(out)
+    assert torch.all(got[:, :64] == 7.0) and torch.all(got[:, 192:] == 7.0)
+    # the launches it replaces
+    a1 = torch.empty(b, size // 2, size // 2, 64, dtype=torch.bfloat16, device=dev)
+    two = torch.full((b, q, q, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_conv1(xd.data_ptr(), _lib.BF16, b, size, wk.data_ptr(), t0d.data_ptr(), a1.data_ptr(), _stream()),
+         "hgr_conv1")
+    _chk(lib.hgr_conv_chain(a1.data_ptr(), b, size // 2, size // 2, w1d.data_ptr(), s1d.data_ptr(), t1d.data_ptr(),
+                            w2d.data_ptr(), s2d.data_ptr(), t2d.data_ptr(), two.data_ptr(), 256, 64, _stream()),
+         "hgr_conv_chain")
+    torch.cuda.synchronize()
+    w0ref = wk.float().cpu()[:, :27].reshape(64, 3, 3, 3).permute(0, 3, 1, 2)  # the bf16-rounded folded weights
+    a1r = F.silu(F.conv2d(x, w0ref, None, stride=2, padding=1) + t0.view(1, -1, 1, 1))
+    a2r = F.silu(F.conv2d(a1r, bf16_round(w1), None, stride=2, padding=1) * s1.view(1, -1, 1, 1) + t1.view(1, -1, 1, 1))
+    ref = F.silu(F.conv2d(a2r, bf16_round(w2)) * s2.view(1, -1, 1, 1) + t2.view(1, -1, 1, 1))
+    r, m = report(f"stem_fused b={b} size={size} vs fp32 operators", got[:, 64:192], ref)
+    assert r <= 8e-3 and m <= 2 * MAX_TOL
+    r2, _ = report(f"stem_fused b={b} size={size} vs conv1 + conv_chain", got[:, 64:192], nchw_f32(two)[:, 64:192])
+    assert r2 <= 2e-3
+
+
 @pytest.mark.parametrize("rows", [1160, 128 * 148 * 2 + 77, 77])
 @pytest.mark.parametrize("inplace", [False, True], ids=["out", "inplace"])
 def test_vit_block(lib, rows, inplace):

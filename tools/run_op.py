@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE operator of the C ABI a few times at the headline batch (development tool: the command ncu wraps when a
-single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head|conv1> [B] [reps]"""
+single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head|conv1|stem_fused|stem_two> [B] [reps]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hand-gesture-recognition_b200"))
 import torch
@@ -37,6 +37,28 @@ elif op == "conv1":
     sh = torch.randn(64, generator=g, device=dev) * 0.3
     out = torch.empty(B, S // 2, S // 2, 64, dtype=torch.bfloat16, device=dev)
     run = lambda: _lib.check(lib.hgr_conv1(x.data_ptr(), _lib.BF16, B, S, wk.data_ptr(), sh.data_ptr(), out.data_ptr(), st), op)
+elif op in ("stem_fused", "stem_two"):
+    S = 192
+    x = torch.randn(B, 3, S, S, generator=g, device=dev).bfloat16()
+    wk = torch.zeros(64, 32, device=dev)
+    wk[:, :27] = torch.randn(64, 27, generator=g, device=dev) * 0.27
+    wk = wk.bfloat16()
+    sh = torch.randn(64, generator=g, device=dev) * 0.3
+    w1 = (torch.randn(128, 9, 64, generator=g, device=dev) * 0.06).bfloat16()
+    w2 = (torch.randn(128, 128, generator=g, device=dev) * 0.12).bfloat16()
+    s1, s2 = torch.rand(128, generator=g, device=dev) + 0.5, torch.rand(128, generator=g, device=dev) + 0.5
+    t1, t2 = torch.randn(128, generator=g, device=dev) * 0.3, torch.randn(128, generator=g, device=dev) * 0.3
+    a1 = torch.empty(B, S // 2, S // 2, 64, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, S // 4, S // 4, 256, dtype=torch.bfloat16, device=dev)
+    if op == "stem_fused":
+        run = lambda: _lib.check(lib.hgr_stem_fused(x.data_ptr(), B, S, wk.data_ptr(), sh.data_ptr(), w1.data_ptr(),
+                                                    s1.data_ptr(), t1.data_ptr(), w2.data_ptr(), s2.data_ptr(),
+                                                    t2.data_ptr(), out.data_ptr(), 256, 0, st), op)
+    else:
+        def run():
+            _lib.check(lib.hgr_conv1(x.data_ptr(), _lib.BF16, B, S, wk.data_ptr(), sh.data_ptr(), a1.data_ptr(), st), op)
+            _lib.check(lib.hgr_conv_chain(a1.data_ptr(), B, S // 2, S // 2, w1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
+                                          w2.data_ptr(), s2.data_ptr(), t2.data_ptr(), out.data_ptr(), 256, 0, st), op)
 else:
     raise SystemExit(f"unknown op {op}")
 for _ in range(2):
