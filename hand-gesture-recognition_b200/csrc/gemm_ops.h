@@ -63,13 +63,14 @@ int run_stem_chain(const void* in, int B, int H, int W, const void* w1, const fl
                    const void* w2, const float* scale2, const float* shift2, void* out, int out_ctot, int out_coff,
                    int reverse, int num_sms, cudaStream_t stream);
 
-// conv1 -> conv2 -> cspelan1.cv1 as one CTA-pair kernel (stem_fused.cu): conv1 runs in producer warps that write the
-// stride-2 layer's parity planes straight into shared memory, so the 64-channel map between the two layers never
-// reaches HBM.  bf16 NCHW input, image side a multiple of 64, CTA pairs.  HGR_STEM_FUSED=0 keeps conv1 + stem_chain.
+// conv1 -> conv2 -> cspelan1.cv1 as one CTA-pair kernel, all three contractions on tcgen05 (stem_umma.cu): im2col rows
+// built in shared memory, conv1 into tensor memory, SiLU'd pixels stored into the stride-2 layer's parity planes; the
+// 64-channel map between the first two layers never reaches HBM.  bf16 NCHW input, image side a multiple of 64, CTA
+// pairs.  HGR_STEM_FUSED=0 keeps conv1 + stem_chain.
 bool stem_fused_enabled();
-bool stem_fused_supported(int S);
-int run_stem_fused(const void* x, int B, int S, const void* w0, const float* shift0, const void* w1,
-                   const float* scale1, const float* shift1, const void* w2, const float* scale2, const float* shift2,
-                   void* out, int out_ctot, int out_coff, int reverse, int num_sms, cudaStream_t stream);
+bool stem_umma_supported(int S);
+int run_stem_umma(const void* x, int B, int S, const void* w0, const float* shift0, const void* w1, const float* scale1,
+                  const float* shift1, const void* w2, const float* scale2, const float* shift2, void* out,
+                  int out_ctot, int out_coff, int reverse, int num_sms, cudaStream_t stream);
 
 }  // namespace hgr

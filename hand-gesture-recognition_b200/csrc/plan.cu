@@ -805,8 +805,8 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
                             pl->pp<float>(n1 + ".shift"), pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
     };
     const bool halo = stem_chain_enabled() && stem_chain_supported(H1s, H1s);
-    if (halo && stem_fused_enabled() && stem_fused_supported(pl->S)) {
-      // conv1 -> conv2 -> cspelan1.cv1 in one launch (stem_fused.cu): a1 never reaches HBM.  The kernel reads a bf16
+    if (halo && stem_fused_enabled() && stem_umma_supported(pl->S)) {
+      // conv1 -> conv2 -> cspelan1.cv1 in one launch (stem_umma.cu): a1 never reaches HBM.  The kernel reads a bf16
       // batch through a TMA box; an fp32 batch (decided per call) takes the two launches it replaces.
       dir = zig ? !dir : 0;
       const int rev = dir;
@@ -817,7 +817,7 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
               if (int rc = run_conv1(st, io)) return rc;
               return run_chain_halo(st, rev);
             }
-            return run_stem_fused(io.x, B, pl->S, pl->pp<void>("encoder.conv1.w"), pl->pp<float>("encoder.conv1.shift"),
+            return run_stem_umma(io.x, B, pl->S, pl->pp<void>("encoder.conv1.w"), pl->pp<float>("encoder.conv1.shift"),
                                   pl->pp<void>(n0 + ".w"), pl->pp<float>(n0 + ".scale"), pl->pp<float>(n0 + ".shift"),
                                   pl->pp<void>(n1 + ".w"), pl->pp<float>(n1 + ".scale"), pl->pp<float>(n1 + ".shift"),
                                   pl->bp("g1"), 256, 0, rev, device_sm_count(), st);
@@ -1094,8 +1094,8 @@ int hgr_stem_fused(const void* d_x, int B, int S, const void* d_w0, const float*
     set_error("hgr_stem_fused: the fused stem kernel runs on CTA pairs (HGR_CLUSTER=0 disables them)");
     return -1;
   }
-  return run_stem_fused(d_x, B, S, d_w0, d_shift0, d_w1, d_scale1, d_shift1, d_w2, d_scale2, d_shift2, d_out, out_ctot,
-                        out_coff, 0, device_sm_count(), static_cast<cudaStream_t>(stream));
+  return run_stem_umma(d_x, B, S, d_w0, d_shift0, d_w1, d_scale1, d_shift1, d_w2, d_scale2, d_shift2, d_out, out_ctot, out_coff, 0,
+             device_sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale, const float* d_bias,

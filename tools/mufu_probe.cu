@@ -9,6 +9,16 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float tanhf_(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf_(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ unsigned pack2(float lo, float hi) {
   unsigned r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -28,6 +38,12 @@ __global__ void __launch_bounds__(1024, 1) k(long long* cyc, float* sink, int it
     if (MODE == 0) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) v[e] = ex2f(v[e]);
+    } else if (MODE == 2) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = tanhf_(v[e]);
+    } else if (MODE == 3) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = rcpf_(v[e]);
     } else {
 #pragma unroll
       for (int e = 0; e < 32; e += 4) {
@@ -54,17 +70,19 @@ int main() {
   cudaMalloc(&d, 8);
   cudaMalloc(&s, 4);
   const int iters = 2000;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 4; ++mode)
     for (int wps : {1, 2, 3, 4, 6, 8}) {
       long long c = 0;
       for (int rep = 0; rep < 2; ++rep) {
         if (mode == 0) k<0><<<1, wps * 128>>>(d, s, iters, 1.01f, 0.5f);
-        else k<1><<<1, wps * 128>>>(d, s, iters, 1.01f, 0.5f);
+        else if (mode == 1) k<1><<<1, wps * 128>>>(d, s, iters, 1.01f, 0.5f);
+        else if (mode == 2) k<2><<<1, wps * 128>>>(d, s, iters, 1.01f, 0.5f);
+        else k<3><<<1, wps * 128>>>(d, s, iters, 1.01f, 0.5f);
         cudaDeviceSynchronize();
         cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
       }
       printf("%s warps/scheduler %d: %.2f clk per warp-level EX2 per scheduler (%.2f clk per EX2 of one warp)\n",
-             mode ? "softmax mix" : "pure ex2   ", wps, (double)c / (iters * 32.0 * wps), (double)c / (iters * 32.0));
+             mode == 0 ? "pure ex2   " : (mode == 1 ? "softmax mix" : (mode == 2 ? "pure tanh  " : "pure rcp   ")), wps, (double)c / (iters * 32.0 * wps), (double)c / (iters * 32.0));
     }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
