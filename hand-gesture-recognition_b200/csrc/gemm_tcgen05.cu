@@ -164,7 +164,7 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
         if (p.warp_arrive) __syncwarp();
         if (!p.warp_arrive || lane == 0) {
           if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);
-          else mbar_arrive_cluster(&acc_empty_bar[group], 0);
+          else mbar_arrive_remote(&acc_empty_bar[group], 0);
         }
       }
 #pragma unroll

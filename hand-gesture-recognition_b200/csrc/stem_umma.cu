@@ -31,7 +31,9 @@
 // cycles per item each, ~8 k per tile), the builders (~1.5 k per block) and the G0 groups all sit near the tile time,
 // the MUFU pipe (one tanh per a1, a2 and g element) is 60 % busy and shared memory, tensor memory (512 columns) and
 // the thread count leave no room for another stage.  Measured negatives: E2 with direct global stores instead of the
-// staging buffer + TMA store (0.62 ms), one E group + three G0 warps per scheduler (0.72 ms).
+// staging buffer + TMA store (0.62 ms); one E group + three G0 warps per scheduler (0.72 ms); E1 spread over the G0
+// warps with a2 in its own tensor-memory buffer and G2 accumulating into the G1 stage (0.58 ms: E2's reads then sit
+// inside the stage-reuse loop); __nanosleep back-off in the waits (no change).
 //
 // Tensor memory (512 columns): G1 stages at 0 and 128 (a2 over the first 64 columns of its stage), G2's single
 // stage at 256, G0's two 64-column accumulators at 384 and 448.  CTA pairs as in stem_chain.cu; every arrival that
