@@ -308,6 +308,19 @@ def memory_tail_roofline(model, B, S, dev, hbm_gbs, conv1_row):
                     "achieved": nb / (conv1_row["ms"] * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                     "frac": nb / (conv1_row["ms"] * 1e-3) / 1e9 / hbm_gbs,
                     "what": "bf16 NCHW input in, bf16 NHWC 64-channel map out; timed inside the forward"})
+    else:
+        # the default forward runs conv1 inside the fused stem kernel (a1 never reaches HBM); the stand-alone kernel
+        # still serves fp32 input batches, other image sides and the training step
+        del crops, frames
+        wk = torch.zeros(64, 32, device=dev)
+        wk[:, :27] = torch.randn(64, 27, generator=g, device=dev) * 0.27
+        wk = wk.bfloat16()
+        sh = torch.randn(64, generator=g, device=dev) * 0.3
+        a1 = [torch.empty(B, S // 2, S // 2, 64, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        timed("conv1_kernel (model/gelan.py:155, K = 27; stand-alone launch, fused into the stem kernel in the forward)",
+              lambda k: _lib.check(lib.hgr_conv1(xn[k].data_ptr(), _lib.BF16, B, S, wk.data_ptr(), sh.data_ptr(),
+                                                 a1[k].data_ptr(), st), "hgr_conv1"),
+              B * (3 * S * S * 2 + 64 * (S // 2) * (S // 2) * 2), "bf16 NCHW input in, bf16 NHWC 64-channel map out")
     return out
 
 
@@ -345,7 +358,7 @@ def train_record(S, dev, rank, world, local_rank, barrier, steps=10):
     model = MultiTaskNet(21, 19, [S, S])
     synthetic_weights(model)
     model = model.to(dev).train()
-    tr = DataParallelTrainer(model, lr=1e-4)
+    tr = DataParallelTrainer(model, lr=1e-4, cuda_graph=True)  # forward + loss + backward replayed from a CUDA graph
     g = torch.Generator(device=dev).manual_seed(11 + rank)
     x = torch.randn(B, 3, S, S, generator=g, device=dev)
     labels = torch.randint(0, 19, (B,), generator=g, device=dev)
@@ -373,7 +386,8 @@ def train_record(S, dev, rank, world, local_rank, barrier, steps=10):
     ok = bool(torch.isfinite(loss).all())
     return {"metric": "training images/s, MultiTaskNet fwd+bwd+allreduce+AdamW (BASELINE.json configs[4])",
             "value": world * B / (ms * 1e-3), "unit": "images/s", "batch_per_gpu": B, "ms_per_step": ms,
-            "allreduce_ms_exposed": ar, "allreduce_bytes": tr.state.numel * 4, "steps": steps, "finite_loss": ok}
+            "allreduce_ms_exposed": ar, "allreduce_bytes": tr.state.numel * 4, "steps": steps, "finite_loss": ok,
+            "cuda_graph": "forward + loss + backward replayed from one captured graph; all-reduce and AdamW are plain launches"}
 
 
 def workload(B, S):
