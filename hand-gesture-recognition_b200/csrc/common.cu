@@ -79,6 +79,11 @@ bool stem_fused_enabled() {
   return on;
 }
 
+bool gelan_tail_enabled() {
+  static const bool on = env_flag("HGR_GELAN_TAIL", true);
+  return on;
+}
+
 bool stem_chain_enabled() {
   static const bool on = env_flag("HGR_CHAIN_HALO", true);
   return on && cluster_enabled();

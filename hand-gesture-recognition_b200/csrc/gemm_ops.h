@@ -73,4 +73,13 @@ int run_stem_umma(const void* x, int B, int S, const void* w0, const float* shif
                   const float* shift1, const void* w2, const float* scale2, const float* shift2, void* out,
                   int out_ctot, int out_coff, int reverse, int num_sms, cudaStream_t stream);
 
+// cspelan1.cv3.0.cv2 (+ residual, SiLU) -> cspelan1.cv4 as one CTA-pair kernel (gelan_tail.cu): y3 stays in tensor
+// memory as the A operand of cv4's last K block.  64-channel chunks, maps that tile into 16 x 8 blocks, CTA pairs.
+// HGR_GELAN_TAIL=0 keeps the two launches.
+bool gelan_tail_enabled();
+bool gelan_tail_supported(int H, int W);
+int run_gelan_tail(const void* t, const void* g, int B, int H, int W, const void* w_h, const float* scale_h,
+                   const float* shift_h, const void* w4, const float* scale_4, const float* shift_4, void* out,
+                   int reverse, int num_sms, cudaStream_t stream);
+
 }  // namespace hgr

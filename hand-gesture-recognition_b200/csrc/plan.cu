@@ -840,7 +840,26 @@ int hgr_plan_create(hgr_plan_t** out, int S, int J, int C, int batch, void* d_pa
   } else {
     add("encoder.conv1", 1, conv1_flops, conv1_bytes, run_conv1);
   }
-  for (int i = first_conv; i < kNumConvs; ++i) add_gemm(kConvs[i].name, &pl->convs[i]);
+  // cspelan1.cv3.0.cv2 + cspelan1.cv4 (kConvs[5], [6]) as one launch (gelan_tail.cu): y3 never reaches HBM
+  const bool tail = gelan_tail_enabled() && cluster_enabled() && gelan_tail_supported(S / 4, S / 4);
+  for (int i = first_conv; i < kNumConvs; ++i) {
+    if (tail && i == 5) {
+      dir = zig ? !dir : 0;
+      const int rev = dir, H2s = S / 4;
+      const std::string nh = kConvs[5].name, n4 = kConvs[6].name;
+      GemmOp *oh = &pl->convs[5], *o4 = &pl->convs[6];
+      add(nh + "+" + (kConvs[6].name + 8), 0, oh->flops + o4->flops, oh->bytes + o4->bytes - 2.0 * dB * H2s * H2s * 64 * 2,
+          [pl, B, H2s, rev, nh, n4](cudaStream_t st, const Io&) {
+            return run_gelan_tail(pl->bp("t1"), pl->bp("g1"), B, H2s, H2s, pl->pp<void>(nh + ".w"),
+                                  pl->pp<float>(nh + ".scale"), pl->pp<float>(nh + ".shift"), pl->pp<void>(n4 + ".w"),
+                                  pl->pp<float>(n4 + ".scale"), pl->pp<float>(n4 + ".shift"), pl->bp("o1"), rev,
+                                  device_sm_count(), st);
+          });
+      ++i;  // cv4 is part of the launch
+      continue;
+    }
+    add_gemm(kConvs[i].name, &pl->convs[i]);
+  }
   add("decoder.cls_token", 2, 0, dB * kDim * 2, [pl, B, T](cudaStream_t st, const Io&) {
     return launch_fill_cls(pl->bp("tokens"), pl->pp<float>("decoder.cls_token"),
                            pl->pp<float>("decoder.cls_token.stats"), reinterpret_cast<float*>(pl->bp("row_stats")), B,
@@ -1096,6 +1115,17 @@ int hgr_stem_fused(const void* d_x, int B, int S, const void* d_w0, const float*
   }
   return run_stem_umma(d_x, B, S, d_w0, d_shift0, d_w1, d_scale1, d_shift1, d_w2, d_scale2, d_shift2, d_out, out_ctot, out_coff, 0,
              device_sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+int hgr_gelan_tail(const void* d_t, const void* d_g, int B, int H, int W, const void* d_wh, const float* d_scale_h,
+                   const float* d_shift_h, const void* d_w4, const float* d_scale4, const float* d_shift4, void* d_out,
+                   void* stream) {
+  if (!cluster_enabled()) {
+    set_error("hgr_gelan_tail: the fused kernel runs on CTA pairs (HGR_CLUSTER=0 disables them)");
+    return -1;
+  }
+  return run_gelan_tail(d_t, d_g, B, H, W, d_wh, d_scale_h, d_shift_h, d_w4, d_scale4, d_shift4, d_out, 0,
+                        device_sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 int hgr_linear(const void* d_x, long long rows, int cin, const void* d_w, const float* d_scale, const float* d_bias,

@@ -42,6 +42,7 @@ SIGNATURES = {
                              _vp]),
     "hgr_conv_chain": (_i, [_vp, _i, _i, _i, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _i, _i, _vp]),
     "hgr_stem_fused": (_i, [_vp, _i, _i, _vp, _fp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _i, _i, _vp]),
+    "hgr_gelan_tail": (_i, [_vp, _vp, _i, _i, _i, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _vp]),
     "hgr_linear": (_i, [_vp, _ll, _i, _vp, _fp, _fp, _i, _vp, _vp, _i, _fp, _fp, _vp]),
     "hgr_vit_block": (_i, [_vp, _vp, _ll, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _vp]),
     "hgr_vit_block_trace": (_i, [_vp, _vp, _ll, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _fp, _vp, _i, _vp]),

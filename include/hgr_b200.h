@@ -151,6 +151,16 @@ HGR_API int hgr_stem_fused(const void* d_x, int B, int S, const void* d_w0, cons
                            const float* d_scale1, const float* d_shift1, const void* d_w2, const float* d_scale2,
                            const float* d_shift2, void* d_out, int out_ctot, int out_coff, void* stream);
 
+/* The tail of the first GELAN block as one kernel (reference model/gelan.py:73-87 ResBasicBlock.forward, second conv +
+ * residual + SiLU, and :137-142 GELANBlock.forward's cv4 over the concatenation): y3 = SiLU(BN_h(conv3x3(t)) + y2) is
+ * rounded to bf16 where the separate launches store it and stays on the SM as an operand of the 1x1 layer.
+ *   d_t    NHWC bf16 (B, H, W, 64), H % 16 == 0, W % 8 == 0;  d_wh bf16 [64][9][64]
+ *   d_g    NHWC bf16 (B, H, W, 256): y0 | y1 | y2 in channels 0..191 (y2 is also the residual); 192..255 untouched
+ *   d_w4   bf16 [128][256];  d_out NHWC bf16 (B, H, W, 128) */
+HGR_API int hgr_gelan_tail(const void* d_t, const void* d_g, int B, int H, int W, const void* d_wh,
+                           const float* d_scale_h, const float* d_shift_h, const void* d_w4, const float* d_scale4,
+                           const float* d_shift4, void* d_out, void* stream);
+
 /* y = act(scale (.) (x W^T) + bias) (+ residual): nn.Linear of the ViT
  * (reference model/transformer.py:34,37,65,75).  x (rows, cin) bf16,
  * W (cout, cin) bf16, y (rows, cout) bf16; d_scale / d_bias / d_res nullable.

@@ -227,6 +227,47 @@ def test_conv_chain(lib, b, h):
     assert r2 <= 1e-3
 
 
+@pytest.mark.parametrize("b,h", [(2, 48), (3, 48), (1, 16), (41, 48), (5, 64)])
+def test_gelan_tail(lib, b, h):
+    """cspelan1.cv3.0.cv2 (+ residual, SiLU) -> cspelan1.cv4 (reference model/gelan.py:73-87, :137-142) as one CTA-pair
+    kernel against the fp32 operators and against the two hgr_conv_bn_act launches it replaces (same rounding point
+    for y3, same K order in the 1x1 layer)."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(b * 100 + h)
+    t = bf16_round(torch.randn(b, 64, h, h, generator=g))
+    y012 = bf16_round(torch.randn(b, 192, h, h, generator=g))
+    wh = torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5
+    w4 = torch.randn(128, 256, 1, 1, generator=g) * (2.0 / 256) ** 0.5
+    sh_, s4 = torch.rand(64, generator=g) + 0.5, torch.rand(128, generator=g) + 0.5
+    th_, t4 = torch.randn(64, generator=g) * 0.3, torch.randn(128, generator=g) * 0.3
+    td = nhwc_bf16(t, dev)
+    gbuf = torch.full((b, h, h, 256), 7.0, dtype=torch.bfloat16, device=dev)
+    gbuf[..., :192] = nhwc_bf16(y012, dev)
+    whd = wh.permute(0, 2, 3, 1).contiguous().to(dev, torch.bfloat16)
+    w4d = w4.reshape(128, 256).contiguous().to(dev, torch.bfloat16)
+    shd, s4d, thd, t4d = (v.to(dev).float().contiguous() for v in (sh_, s4, th_, t4))
+    out = torch.full((b, h, h, 128), 7.0, dtype=torch.bfloat16, device=dev)
+    _chk(lib.hgr_gelan_tail(td.data_ptr(), gbuf.data_ptr(), b, h, h, whd.data_ptr(), shd.data_ptr(), thd.data_ptr(),
+                            w4d.data_ptr(), s4d.data_ptr(), t4d.data_ptr(), out.data_ptr(), _stream()), "hgr_gelan_tail")
+    torch.cuda.synchronize()
+    assert torch.all(gbuf[..., 192:] == 7.0)  # y3 is not written
+    # the two launches
+    g2 = gbuf.clone()
+    two = torch.empty_like(out)
+    _chk(lib.hgr_conv_bn_act(td.data_ptr(), b, h, h, 64, 0, 64, whd.data_ptr(), shd.data_ptr(), thd.data_ptr(), 3, 1, 1,
+                             g2.data_ptr(), 256, 128, g2.data_ptr(), 256, 192, 64, _stream()), "cv3.0.cv2")
+    _chk(lib.hgr_conv_bn_act(g2.data_ptr(), b, h, h, 256, 0, 256, w4d.data_ptr(), s4d.data_ptr(), t4d.data_ptr(), 1, 1, 1,
+                             None, 0, 0, two.data_ptr(), 128, 0, 128, _stream()), "cv4")
+    torch.cuda.synchronize()
+    y2 = y012[:, 128:192]
+    y3 = F.silu(F.conv2d(t, bf16_round(wh), None, padding=1) * sh_.view(1, -1, 1, 1) + th_.view(1, -1, 1, 1) + y2)
+    ref = F.silu(F.conv2d(torch.cat([y012, y3], 1), bf16_round(w4)) * s4.view(1, -1, 1, 1) + t4.view(1, -1, 1, 1))
+    r, m = report(f"gelan_tail b={b} h={h} vs fp32 operators", nchw_f32(out), ref)
+    assert r <= 6e-3 and m <= 2 * MAX_TOL
+    r2, _ = report(f"gelan_tail b={b} h={h} vs two launches", nchw_f32(out), nchw_f32(two))
+    assert r2 <= 1e-3
+
+
 @pytest.mark.parametrize("b,size", [(2, 192), (3, 192), (1, 64), (5, 128), (41, 192), (3, 256)])
 def test_stem_fused(lib, b, size):
     """conv1 -> conv2 -> cspelan1.cv1 (reference model/gelan.py:155, :156, :127) as one kernel against the fp32

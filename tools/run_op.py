@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE operator of the C ABI a few times at the headline batch (development tool: the command ncu wraps when a
-single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head|conv1|stem_fused|stem_two> [B] [reps]"""
+single kernel is profiled, and a quick CUDA-event timer).  Usage: tools/run_op.py <attention_tc|attention|pose_head|conv1|stem_fused|stem_two|gelan_tail|gelan_tail_two> [B] [reps]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "hand-gesture-recognition_b200"))
 import torch
@@ -59,6 +59,25 @@ elif op in ("stem_fused", "stem_two"):
             _lib.check(lib.hgr_conv1(x.data_ptr(), _lib.BF16, B, S, wk.data_ptr(), sh.data_ptr(), a1.data_ptr(), st), op)
             _lib.check(lib.hgr_conv_chain(a1.data_ptr(), B, S // 2, S // 2, w1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
                                           w2.data_ptr(), s2.data_ptr(), t2.data_ptr(), out.data_ptr(), 256, 0, st), op)
+elif op in ("gelan_tail", "gelan_tail_two"):
+    H = 48
+    t = torch.randn(B, H, H, 64, generator=g, device=dev).bfloat16()
+    gb = torch.randn(B, H, H, 256, generator=g, device=dev).bfloat16()
+    wh = (torch.randn(64, 9, 64, generator=g, device=dev) * 0.06).bfloat16()
+    w4 = (torch.randn(128, 256, generator=g, device=dev) * 0.09).bfloat16()
+    sh_, s4 = torch.rand(64, generator=g, device=dev) + 0.5, torch.rand(128, generator=g, device=dev) + 0.5
+    th_, t4 = torch.randn(64, generator=g, device=dev) * 0.3, torch.randn(128, generator=g, device=dev) * 0.3
+    out = torch.empty(B, H, H, 128, dtype=torch.bfloat16, device=dev)
+    if op == "gelan_tail":
+        run = lambda: _lib.check(lib.hgr_gelan_tail(t.data_ptr(), gb.data_ptr(), B, H, H, wh.data_ptr(), sh_.data_ptr(),
+                                                    th_.data_ptr(), w4.data_ptr(), s4.data_ptr(), t4.data_ptr(),
+                                                    out.data_ptr(), st), op)
+    else:
+        def run():
+            _lib.check(lib.hgr_conv_bn_act(t.data_ptr(), B, H, H, 64, 0, 64, wh.data_ptr(), sh_.data_ptr(), th_.data_ptr(),
+                                           3, 1, 1, gb.data_ptr(), 256, 128, gb.data_ptr(), 256, 192, 64, st), op)
+            _lib.check(lib.hgr_conv_bn_act(gb.data_ptr(), B, H, H, 256, 0, 256, w4.data_ptr(), s4.data_ptr(), t4.data_ptr(),
+                                           1, 1, 1, None, 0, 0, out.data_ptr(), 128, 0, 128, st), op)
 else:
     raise SystemExit(f"unknown op {op}")
 for _ in range(2):
