@@ -245,6 +245,38 @@ def gpu_eager_rate(size, batch, dev, iters=6):
                     f"{iters} iterations, CUDA events"}
 
 
+def forward_other_size(size, batch, dev, pk, steps=8):
+    """BASELINE.json configs[3] in the default line: the same forward at another image side (256 x 256), device
+    resident, bf16 in / out, CUDA events over `steps` forwards after 3 warm-up forwards."""
+    import torch
+    from hgr_b200 import MultiTaskNet
+    torch.manual_seed(0)
+    model = MultiTaskNet(21, 19, [size, size])
+    synthetic_weights(model)
+    model = model.to(dev).eval()
+    model.return_attention = False
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(batch, 3, size, size, generator=g, device=dev).bfloat16()
+    with torch.no_grad():
+        for _ in range(3):
+            out = model(x)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = model(x)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ok = bool(torch.isfinite(out[0].float()).all() and torch.isfinite(out[1].float()).all())
+    gf = GFLOP_PER_IMG.get(size)
+    value = batch / (ms * 1e-3)
+    return {"metric": "hand-crop images/s, MultiTaskNet forward (BASELINE.json configs[3])", "image_size": size,
+            "batch": batch, "value": value, "unit": "images/s", "ms_per_step": ms, "steps": steps, "finite": ok,
+            "net_tensor_frac_of_sustained": value * gf * 1e9 / (pk["bf16_sustained"] * 1e12) if gf else None,
+            "net_tensor_frac_of_burst": value * gf * 1e9 / (pk["bf16_burst"] * 1e12) if gf else None}
+
+
 def memory_tail_roofline(model, B, S, dev, hbm_gbs, conv1_row):
     """Achieved GB/s of the HBM-bound kernels around the forward (north_star: 'achieved HBM GB/s for the memory-bound
     kernels'): algorithmic bytes / CUDA-event time over 20 launches that alternate between two buffer sets larger
@@ -651,11 +683,15 @@ def main():
         conv1_row = next((r for r in table if r["launch"] == "encoder.conv1"), None)
         mem_tail = memory_tail_roofline(model, min(B, 1024), S, dev, pk["hbm_gbs"], conv1_row if B <= 1024 else None)
         eager = gpu_eager_rate(S, min(B, 1024), dev)
-    train = None
+    train = other = None
     if not args.no_extras:
         del out
         torch.cuda.empty_cache()
         train = train_record(S, dev, rank, world, local_rank, barrier)
+    if extras and S == 192 and B <= 1024:
+        del model
+        torch.cuda.empty_cache()
+        other = forward_other_size(256, B, dev, pk)
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------
     cpu = None
@@ -681,7 +717,7 @@ def main():
                        "target_images_per_s_per_gpu": 0.5 * pk["bf16_burst"] * 1e12 / (gf * 1e9) if gf else None},
             "clocks": clocks, "gpu_launches": launches_per_step * K,
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-            "roofline_memory": mem_tail, "gpu_eager_baseline": eager, "train": train,
+            "roofline_memory": mem_tail, "gpu_eager_baseline": eager, "train": train, "forward_256": other,
         }
         if e2e is not None:
             line["gpu_launches_e2e"] = launches_e2e * K

@@ -359,7 +359,6 @@ int launch_conv1_tc(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_b
     return -1;
   }
   const int sms = device_sm_count();
-  if (getenv("HGR_CONV1_EXPERIMENT_RAW")) raw = true;  // timing experiment only: epilogue without the SiLU
   if (x_dtype == DT_F32)
     return raw ? launch_t<float, true>(x, out, w, shift, B, S, sms, stream)
                : launch_t<float, false>(x, out, w, shift, B, S, sms, stream);

@@ -50,7 +50,7 @@ struct ConvChainOp {
   double flops, bytes;
 };
 bool conv_chain_enabled();
-int conv_chain_prefetch();  // HGR_CHAIN_PREFETCH=<items ahead>: L2 prefetch of a later item's input patch
+int conv_chain_prefetch();  // fixed to 0 (common.cu): no L2 prefetch of a later item's input patch
 int build_conv_chain_op(ConvChainOp& op, const GemmOp& first, const GemmOp& second, const void* w2);
 int launch_conv_chain(const ConvChainOp& op, int num_sms, cudaStream_t stream);
 

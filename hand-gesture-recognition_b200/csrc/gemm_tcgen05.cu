@@ -159,8 +159,8 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       if (j == BN / 64 - 1) {
         tc_fence_before();
         // pair mode: the accumulator stage belongs to the leader's MMA thread, which waits for BOTH CTAs' readers.
-        // One arrival per warp (HGR_WARP_ARRIVE, default): 128 cluster-scope release-arrives per tile show up as
-        // membar stalls in the epilogue.
+        // One arrival per warp, and from the peer a plain (CTA-scope release) remote arrive: cluster-scope
+        // release-arrives show up as membar stalls in the epilogue (~800 cycles each).
         if (p.warp_arrive) __syncwarp();
         if (!p.warp_arrive || lane == 0) {
           if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);

@@ -29,7 +29,7 @@ const char* last_error();
 // executes griddepcontrol.wait (ptx.cuh: pdl_wait) before it touches memory another kernel wrote.
 // Measured on B200 (gpurun r1n, batch 1024): 7.06 ms/step with it against 6.88 ms without - the early-scheduled
 // CTAs of the next grid take the SM slots the persistent kernels' stragglers are about to free and gain nothing
-// back - so it is OFF by default; HGR_PDL=1 in the environment turns it on.
+// back - so it is off (fixed in common.cu; the launchers keep the attribute code).
 bool pdl_enabled();
 // HGR_ZIGZAG=0 disables the alternating tile order of plan.cu.
 bool zigzag_enabled();
@@ -47,15 +47,15 @@ bool attention_tc_supported(int T);
 int launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, float scale_log2e, int num_sms,
                         cudaStream_t stream, int reverse, long long* trace = nullptr, int trace_items = 0);
 int attention_tc_warps();
-// HGR_ATTN_CPASYNC=0: the online-softmax attention kernel stages Q, K, V through registers instead of cp.async.
+// fixed to true (common.cu): the online-softmax attention kernel stages Q, K, V by cp.async, not through registers
 bool attention_cp_async_enabled();
-// HGR_ATTN_MT=1|2: query tiles a warp of the online-softmax attention kernel works on at once (default 1).
+// fixed to 1 (common.cu): query tiles a warp of the online-softmax attention kernel works on at once
 int attention_tiles_per_warp();
-// HGR_WARP_ARRIVE=0: every epilogue thread arrives on the accumulator-release barrier (the original protocol).
+// fixed to true (common.cu): one accumulator-release arrive per epilogue warp instead of one per thread
 bool warp_arrive_enabled();
-// HGR_HALO_PAIR=0 keeps the 64-channel halo kernel on single CTAs.
+// fixed to false (common.cu): the 64-channel halo kernel runs on single CTAs
 bool halo_pair_enabled();
-// HGR_PREFETCH=<tiles ahead> (0 disables) for the L2 prefetch of activation tiles.
+// fixed to 0 (common.cu): no L2 prefetch of later activation tiles
 int prefetch_distance();
 
 template <typename... KArgs, typename... Args>
@@ -99,7 +99,7 @@ struct GemmParams {
   int cout;              // channels produced by this layer (length of scale/shift)
   int act;
   int reverse;           // walk the tile grid back to front (see plan.cu: zig-zag order for L2 reuse)
-  int prefetch_dist;     // > 0: L2-prefetch the A tile needed that many tiles ahead (HGR_PREFETCH, default 2)
+  int prefetch_dist;     // > 0: L2-prefetch the A tile needed that many tiles ahead (prefetch_distance(), default 2)
   int warp_arrive;       // accumulator stages are released by one arrival per epilogue warp instead of per thread
   int cluster;           // 1, or 2 = CTA-pair mode, cta_group::2 MMAs (the W map's box then holds BN / 2 rows)
   const float* scale;  // nullable: 1
