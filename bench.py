@@ -94,7 +94,7 @@ def ncu_traffic_per_launch():
     files = sorted((ROOT / "profiles").glob("*_step_ncu_full.csv"))
     if not files:
         return None, None
-    rows = [r for r in csv.DictReader(files[-1].open()) if any(k in r["Kernel Name"] for k in ("gemm_kernel", "halo", "vit_block", "stem_chain", "conv_chain"))]
+    rows = [r for r in csv.DictReader(files[-1].open()) if any(k in r["Kernel Name"] for k in ("gemm_kernel", "halo", "vit_block", "stem_chain", "conv_chain", "stem_umma", "gelan_tail"))]
     if not rows:
         return None, None
     rd = [k for k in rows[0] if k.startswith("dram__bytes_read.sum")][0]
@@ -661,7 +661,7 @@ def main():
                                        "launch averaged over the GEMM launches of one step") if traffic else None,
                     "algorithmic_bytes_per_launch_avg": g_by / len(gem),
                     "kernel": f"tcgen05 GEMM kernels: hgr::gemm_kernel<BN> / conv3x3_halo_kernel (implicit GEMM) and the chained "
-                              f"stem_chain_kernel / vit_block_kernel, {len(gem)} launches per step (the fused tcgen05 attention and "
+                              f"stem_umma_kernel / gelan_tail_kernel / vit_block_kernel, {len(gem)} launches per step (the fused tcgen05 attention and "
                               f"pose-head kernels are listed in per_kernel against their own bounds)",
                     "share_of_step": g_ms / step_ms, "launch_ms_avg": g_ms / len(gem),
                     "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",

@@ -197,7 +197,7 @@ def test_two_rank_sharding_over_gloo():
 
 def test_committed_ncu_capture_feeds_the_roofline_traffic():
     """bench.py takes roofline.traffic from the newest profiles/*_step_ncu_full.csv: the committed capture must parse,
-    cover every tcgen05 launch of a forward (implicit-GEMM, halo, chained stem and chained ViT kernels) and give a
+    cover every tcgen05 launch of a forward (implicit-GEMM, halo, fused stem, fused GELAN tail and chained ViT kernels) and give a
     DRAM figure per launch of the order of the algorithmic bytes (hundreds of MB at batch 1024)."""
     import csv
     import importlib.util
@@ -210,7 +210,7 @@ def test_committed_ncu_capture_feeds_the_roofline_traffic():
     assert 1e8 < per_launch < 2e9, per_launch
     rows = list(csv.DictReader((root / "profiles" / name).open()))
     kernels = " ".join(r["Kernel Name"] for r in rows)
-    for needle in ("gemm_kernel", "halo", "conv1_kernel", "stem_chain_kernel", "attention_tc_kernel", "pose_head_tc_kernel"):
+    for needle in ("gemm_kernel", "halo", "stem_umma_kernel", "gelan_tail_kernel", "attention_tc_kernel", "pose_head_tc_kernel"):
         assert needle in kernels, needle
     shares = [float(r["share_of_step_ncu"]) for r in rows]
     assert abs(sum(shares) - 1.0) < 1e-2

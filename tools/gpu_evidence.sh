@@ -16,8 +16,8 @@ cat $out/bench.json
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_reference.json 2>> $out/bench.err
 echo "reference arm exit $?" | tee -a $out/summary.txt
 SHORT="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extras"
-OURS="regex:gemm_kernel|halo_kernel|vit_block_kernel|conv_chain_kernel|stem_chain_kernel|conv1_kernel|conv1_tc_kernel|attention_kernel|attention_tc_kernel|pose_head_kernel|pose_head_tc_kernel|cls_head_kernel|fill_cls_kernel"
-NL=${2:-37}  # launches per forward (46 with HGR_VIT_FUSED=0 HGR_CONV_CHAIN=0)
+OURS="regex:gemm_kernel|halo_kernel|vit_block_kernel|conv_chain_kernel|stem_chain_kernel|stem_umma_kernel|gelan_tail_kernel|conv1_kernel|conv1_tc_kernel|attention_kernel|attention_tc_kernel|pose_head_kernel|pose_head_tc_kernel|cls_head_kernel|fill_cls_kernel"
+NL=${2:-35}  # launches per forward
 timeout 600 $SHORT > $out/plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$OURS" -s $((3 * NL)) -c $((2 * NL)) --csv \
     --log-file $out/launches.csv $SHORT > $out/ncu_list.log 2>&1
