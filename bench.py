@@ -99,8 +99,9 @@ def ncu_traffic_per_launch():
         return None, None
     rd = [k for k in rows[0] if k.startswith("dram__bytes_read.sum")][0]
     wr = [k for k in rows[0] if k.startswith("dram__bytes_write.sum")][0]
-    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[rd.split("[")[1].rstrip("]")]
-    total = sum(float(r[rd]) + float(r[wr]) for r in rows) * unit
+    units = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    u_rd, u_wr = (units[k.split("[")[1].rstrip("]")] for k in (rd, wr))  # ncu picks the unit per column
+    total = sum(float(r[rd]) * u_rd + float(r[wr]) * u_wr for r in rows)
     return total / len(rows), files[-1].name
 
 
