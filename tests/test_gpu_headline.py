@@ -174,8 +174,8 @@ np.savez({out!r}, cls=cls.float().cpu().numpy(), hm=hm[:, :, ::3, ::3].float().c
 """
 
 
-@pytest.mark.parametrize("switch", ["HGR_STEM_FUSED=0", "HGR_GELAN_TAIL=0", "HGR_CONV_CHAIN=0", "HGR_VIT_FUSED=0", "HGR_CLUSTER=0",
-                                    "HGR_ZIGZAG=0", "HGR_ATTN_TC=0"])
+@pytest.mark.parametrize("switch", ["HGR_STEM_FUSED=0", "HGR_GELAN_TAIL=0", "HGR_CONV_CHAIN=0", "HGR_CHAIN_HALO=0",
+                                    "HGR_VIT_FUSED=0", "HGR_CLUSTER=0", "HGR_ZIGZAG=0", "HGR_ATTN_TC=0", "HGR_POSE_TC=0"])
 def test_toggled_launch_paths_agree_with_the_default_path(switch, tmp_path):
     """Every run-time switch selects a different kernel or tile order for the same arithmetic; the library reads them
     once per process, so each variant runs in its own interpreter.  Batch 256 gives every persistent kernel several
