@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--total-batch", type=int, default=0,
                     help="BASELINE.json configs[2]: one batch of this many crops sharded over the ranks (strong scaling)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="N > 1: do not bind the rank to the CPU socket of its GPU (A/B of the e2e path)")
     ap.add_argument("--train-graph", action="store_true",
                     help="--workload train: replay forward + loss + backward from a CUDA graph")
     ap.add_argument("--no-extras", action="store_true",
@@ -469,6 +471,8 @@ def run_train(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from hgr_b200.sharding import bind_host_to_device_node
+    numa_node = bind_host_to_device_node(local_rank) if world > 1 and not args.no_numa_bind else None  # pinned buffers on the GPU's socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -556,6 +560,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the MultiTaskNet path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from hgr_b200.sharding import bind_host_to_device_node
+    numa_node = bind_host_to_device_node(local_rank) if world > 1 and not args.no_numa_bind else None  # pinned buffers on the GPU's socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -631,7 +637,8 @@ def main():
         e2e = {"value": total_per_step * K / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K,
                "path": "HandPipeline: pinned uint8 crops -> H2D -> crop_normalize -> forward -> get_max_preds -> "
-                       "logits+keypoints D2H, 2 lanes"}
+                       "logits+keypoints D2H, 2 lanes",
+               "host_numa_node": numa_node}
         launches_e2e = pipe.launches_per_batch
         del pipe
 

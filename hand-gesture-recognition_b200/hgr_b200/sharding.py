@@ -8,8 +8,44 @@ region that bench.py needs.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device_node(device_index: int) -> int | None:
+    """One process per GPU: run this process (and, by first touch, the pinned staging buffers it allocates afterwards)
+    on the CPU socket the GPU hangs off, so that the per-step host->device copies of eight ranks do not all cross the
+    socket interconnect.  Reads the GPU's NUMA node from sysfs and narrows the process's CPU affinity to that node's
+    cores (never widens it).  Returns the node, or None when the platform does not say (single-socket boxes report
+    -1) - then nothing is changed."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.6
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # no such attribute / sysfs entry / device: leave the affinity alone
+        return None
 
 
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:

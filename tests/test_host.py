@@ -214,3 +214,16 @@ def test_committed_ncu_capture_feeds_the_roofline_traffic():
         assert needle in kernels, needle
     shares = [float(r["share_of_step_ncu"]) for r in rows]
     assert abs(sum(shares) - 1.0) < 1e-2
+
+
+def test_numa_binding_helper_parses_cpulists_and_never_fails():
+    """sharding.bind_host_to_device_node narrows the process's CPU affinity to the GPU's socket when sysfs says which
+    one that is; without a GPU (here) or without NUMA information it must leave the affinity alone and return None."""
+    import os
+    from hgr_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert sharding._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_host_to_device_node(0) is None or os.sched_getaffinity(0) <= before
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
