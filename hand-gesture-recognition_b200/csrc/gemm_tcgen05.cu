@@ -52,10 +52,16 @@ struct Cfg {
   static constexpr int kOffOut = kOffB + kStages * kBBytes;     // [2 groups][kOutBufs][16 KiB]
   static constexpr int kOffScale = kOffOut + 2 * kOutBufs * kStageBufBytes;  // scale[kMaxCout], shift[kMaxCout]
   static constexpr int kOffBars = kOffScale + 2 * kMaxCout * 4;
-  static constexpr int kNumBars = 2 * kStages + 4;
+  // accumulator stages in tensor memory: with two, a tile's MMAs cannot start before the epilogue of the tile two
+  // back has pulled its last column; with four (BN <= 128: all 512 columns) every epilogue group alternates between
+  // two stages of its own and the MMAs run a tile ahead (+0.4 % on the step, three same-box A/B pairs).  Moving
+  // to_qkv from 256- to 128-wide tiles to get the four stages was slower (0.071 -> 0.079 ms): the extra operand
+  // traffic of the narrower tile costs more than the overlap returns.
+  static constexpr int kAccStages = BN <= 128 ? 4 : 2;
+  static constexpr int kNumBars = 2 * kStages + 2 * kAccStages;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmemPtr + 16;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages: 128 / 256 / 512 columns
+  static constexpr int kTmemCols = kAccStages * BN;  // 256 / 512 / 512 columns
   static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan exceeds one CTA");
 };
 
@@ -85,7 +91,7 @@ struct TileMap {
 // NBUF = staging buffers per group (each one 64-column chunk, 16 KiB).
 enum : int { ROW_NONE = 0, ROW_NORM_IN = 1, ROW_STATS_OUT = 2 };
 
-template <int BN, int ACT, bool RES, int NBUF, int ROW = ROW_NONE>
+template <int BN, int ACT, bool RES, int NBUF, int ROW = ROW_NONE, int NACC = 2>
 __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtensorMap* tmO, const TileMap& tm,
                                                uint8_t* out_bufs, const float* s_scale, const float* s_shift,
                                                uint64_t* acc_full_bar, uint64_t* acc_empty_bar, uint32_t tmem_base,
@@ -104,7 +110,8 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
   int iter = 0;
   for (int tile = first; tile < total_tiles; tile += stride, ++iter) {
     if ((iter & 1) != group) continue;
-    const uint32_t acc_phase = (iter >> 1) & 1;
+    const int acc = iter % NACC;  // the group's tiles alternate between its NACC / 2 accumulator stages
+    const uint32_t acc_phase = (iter / NACC) & 1;
     int w0, h0, n0, noff;
     tm.coords(tile, w0, h0, n0, noff);
     const bool valid = (w0 + wi < p.W) && (h0 + hi < p.H) && (n0 + ni < p.NIMG);
@@ -130,9 +137,9 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
       }
     }
 
-    mbar_wait(&acc_full_bar[group], acc_phase);
+    mbar_wait(&acc_full_bar[acc], acc_phase);
     tc_fence_after();
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + group * BN;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 
 #pragma unroll 1
     for (int j = 0; j < BN / 64; ++j, ++store_count) {
@@ -163,8 +170,8 @@ __device__ __forceinline__ void epilogue_group(const GemmParams& p, const CUtens
         // release-arrives show up as membar stalls in the epilogue (~800 cycles each).
         if (p.warp_arrive) __syncwarp();
         if (!p.warp_arrive || lane == 0) {
-          if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[group]);
-          else mbar_arrive_remote(&acc_empty_bar[group], 0);
+          if (pair_rank <= 0) mbar_arrive(&acc_empty_bar[acc]);
+          else mbar_arrive_remote(&acc_empty_bar[acc], 0);
         }
       }
 #pragma unroll
@@ -263,8 +270,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
   uint64_t* full_bar = bars;                              // [kStages]
   uint64_t* empty_bar = bars + C::kStages;                // [kStages]
-  uint64_t* acc_full_bar = bars + 2 * C::kStages;         // [2]
-  uint64_t* acc_empty_bar = bars + 2 * C::kStages + 2;    // [2]
+  uint64_t* acc_full_bar = bars + 2 * C::kStages;                       // [kAccStages]
+  uint64_t* acc_empty_bar = bars + 2 * C::kStages + C::kAccStages;      // [kAccStages]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::kOffTmemPtr);
   float* s_scale = reinterpret_cast<float*>(smem + C::kOffScale);
   float* s_shift = s_scale + kMaxCout;
@@ -284,7 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < C::kAccStages; ++i) {
       mbar_init(&acc_full_bar[i], 1);
       // pair mode: the readers of both CTAs release the leader's stage; one arrival per warp or per thread
       mbar_init(&acc_empty_bar[i], (p.warp_arrive ? 4 : 128) * CL);
@@ -378,8 +385,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int iter = 0;
     for (int tile = first; tile < total_tiles; tile += stride, ++iter) {
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int acc = iter % C::kAccStages;
+      const uint32_t acc_phase = (iter / C::kAccStages) & 1;
       mbar_wait(&acc_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
@@ -414,7 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ================= epilogue groups =================
     const int group = (warp - 4) >> 2;  // accumulator stage this group drains
-    epilogue_group<BN, ACT, RES, C::kOutBufs, ROW>(p, &tmO, tm, smem + C::kOffOut + group * C::kOutBufs * kStageBufBytes,
+    epilogue_group<BN, ACT, RES, C::kOutBufs, ROW, C::kAccStages>(p, &tmO, tm, smem + C::kOffOut + group * C::kOutBufs * kStageBufBytes,
                                                    s_scale, s_shift, acc_full_bar, acc_empty_bar, tmem_base, group,
                                                    total_tiles, first, stride, CL == 2 ? (int)cta_rank : -1);
   }
