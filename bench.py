@@ -488,7 +488,8 @@ def run_train(args, rank, world, local_rank):
     model = MultiTaskNet(21, 19, [S, S])
     synthetic_weights(model)
     model = model.to(dev).train()
-    tr = DataParallelTrainer(model, lr=1e-4, cuda_graph=args.train_graph)
+    overlap = os.environ.get("HGR_TRAIN_OVERLAP", "0") == "1"  # A/B: 1 = bucketed all-reduce under the backward (measured slower)
+    tr = DataParallelTrainer(model, lr=1e-4, cuda_graph=args.train_graph, overlap_allreduce=overlap)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(B, 3, S, S, generator=g, device=dev)
     # synthetic supervision of the shape train.py feeds: class labels, Gaussian-blob target heatmaps (sigma 2,
@@ -531,7 +532,7 @@ def run_train(args, rank, world, local_rank):
             "config": {"workload": f"MultiTaskNet training step bf16 (fp32 master weights), batch {B} per GPU, 3x{S}x{S}, "
                                    "loss 0.001*CE + JointsMSE, AdamW, NCCL all-reduce of the flat 7.4M-element gradient "
                                    "block (BASELINE.json configs[4])" + ("; forward + loss + backward replayed from a CUDA graph" if args.train_graph else ""),
-                       "batch_per_gpu": B, "image_size": S,
+                       "batch_per_gpu": B, "image_size": S, "allreduce_overlapped_with_backward": tr.overlap,
                        "train_gflop_per_image_convention_3x_forward": 3 * gf if gf else None,
                        "tensor_frac_of_sustained": value / world * 3 * gf * 1e9 / (pk["bf16_sustained"] * 1e12) if gf else None},
             "clocks": clocks, "final_loss": lv}), flush=True)

@@ -621,67 +621,78 @@ int hgr_train_forward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, float*
 
 // Backward of the forward pass last run on this plan: d_dlogits (B, C) fp32 and d_dheatmaps (B, J, S/4, S/4)
 // fp32 are the loss gradients; every entry of the flat gradient block is overwritten.
-int hgr_train_backward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const float* d_dlogits,
-                       const float* d_dheatmaps, void* stream) {
-  if (!pl || !d_x || !d_dlogits || !d_dheatmaps || (x_dtype != DT_F32 && x_dtype != DT_BF16)) {
-    set_error("hgr_train_backward: bad argument");
+// The backward in three parts, in the order the gradients become final (the flat gradient block is in state_dict
+// order, so each part completes one contiguous range of it and the trainer can start that range's all-reduce while
+// the next part runs): 0 = heads, transformer, token assembly, proj (parameters from "proj.weight" on);
+// 1 = cspelan3 and down2 (kDefs[kSplitConv ..]); 2 = the rest of the backbone down to conv1.
+constexpr int kSplitConv = 15;  // "encoder.down2"
+static_assert(kNumDefs == 22, "the split index assumes GELANNet('small')'s 22 convolutions");
+
+int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const float* d_dlogits,
+                            const float* d_dheatmaps, int part, void* stream) {
+  if (!pl || !d_x || !d_dlogits || !d_dheatmaps || (x_dtype != DT_F32 && x_dtype != DT_BF16) || part < 0 || part > 2) {
+    set_error("hgr_train_backward_part: bad argument");
     return -1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = pl->B, S = pl->S, T = pl->T, F = pl->F;
   const long long R = (long long)B * T;
-  // heads
-  if (int rc = launch_pose_head_bwd(pl->x[kDepth], pl->P("decoder.simple_decoder.1.weight"), d_dheatmaps, B, F, pl->J,
-                                    pl->gA, pl->wpartial, pl->G("decoder.simple_decoder.1.weight"),
-                                    pl->G("decoder.simple_decoder.1.bias"), st))
-    return rc;
-  if (int rc = launch_cls_head_bwd(pl->x[kDepth], pl->P("decoder.mlp_head.0.weight"), pl->P("decoder.mlp_head.0.bias"),
-                                   pl->P("decoder.mlp_head.1.weight"), d_dlogits, B, T, pl->C, pl->gA,
-                                   pl->G("decoder.mlp_head.0.weight"), pl->G("decoder.mlp_head.0.bias"),
-                                   pl->G("decoder.mlp_head.1.weight"), pl->G("decoder.mlp_head.1.bias"), st))
-    return rc;
-  // transformer layers, last to first; gA holds d(x[l+1]) on entry and d(x[l]) on exit
-  for (int l = kDepth - 1; l >= 0; --l) {
-    LayerRt& L = pl->layer[l];
-    const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
-    const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
-    // FeedForward: x[l+1] = xmid + W4 gelu(W1 LN2(xmid) + b1) + b4
-    if (int rc = launch_colsum(pl->gA, R, kDim, pl->G(f + "4.bias"), pl->partial, st)) return rc;
-    if (int rc = launch_wgrad(pl->gA, kDim, L.hact, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                              pl->G(f + "4.weight"), st))
+  if (part == 0) {
+    // heads
+    if (int rc = launch_pose_head_bwd(pl->x[kDepth], pl->P("decoder.simple_decoder.1.weight"), d_dheatmaps, B, F, pl->J,
+                                      pl->gA, pl->wpartial, pl->G("decoder.simple_decoder.1.weight"),
+                                      pl->G("decoder.simple_decoder.1.bias"), st))
       return rc;
-    if (int rc = run(L.b_dh, st)) return rc;
-    if (int rc = launch_gelu_bwd(L.hpre, pl->dh, R * kDim, st)) return rc;
-    if (int rc = launch_colsum(pl->dh, R, kDim, pl->G(f + "1.bias"), pl->partial, st)) return rc;
-    if (int rc = launch_wgrad(pl->dh, kDim, L.ln2, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                              pl->G(f + "1.weight"), st))
+    if (int rc = launch_cls_head_bwd(pl->x[kDepth], pl->P("decoder.mlp_head.0.weight"), pl->P("decoder.mlp_head.0.bias"),
+                                     pl->P("decoder.mlp_head.1.weight"), d_dlogits, B, T, pl->C, pl->gA,
+                                     pl->G("decoder.mlp_head.0.weight"), pl->G("decoder.mlp_head.0.bias"),
+                                     pl->G("decoder.mlp_head.1.weight"), pl->G("decoder.mlp_head.1.bias"), st))
       return rc;
-    if (int rc = run(L.b_dln2, st)) return rc;
-    if (int rc = launch_ln_bwd(pl->dln, L.xmid, pl->P(f + "0.weight"), pl->gA, pl->gB, R, pl->G(f + "0.weight"),
-                               pl->G(f + "0.bias"), pl->partial, st))
+    // transformer layers, last to first; gA holds d(x[l+1]) on entry and d(x[l]) on exit
+    for (int l = kDepth - 1; l >= 0; --l) {
+      LayerRt& L = pl->layer[l];
+      const std::string a = "decoder.transformer.layers." + std::to_string(l) + ".0.";
+      const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
+      // FeedForward: x[l+1] = xmid + W4 gelu(W1 LN2(xmid) + b1) + b4
+      if (int rc = launch_colsum(pl->gA, R, kDim, pl->G(f + "4.bias"), pl->partial, st)) return rc;
+      if (int rc = launch_wgrad(pl->gA, kDim, L.hact, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
+                                pl->G(f + "4.weight"), st))
+        return rc;
+      if (int rc = run(L.b_dh, st)) return rc;
+      if (int rc = launch_gelu_bwd(L.hpre, pl->dh, R * kDim, st)) return rc;
+      if (int rc = launch_colsum(pl->dh, R, kDim, pl->G(f + "1.bias"), pl->partial, st)) return rc;
+      if (int rc = launch_wgrad(pl->dh, kDim, L.ln2, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
+                                pl->G(f + "1.weight"), st))
+        return rc;
+      if (int rc = run(L.b_dln2, st)) return rc;
+      if (int rc = launch_ln_bwd(pl->dln, L.xmid, pl->P(f + "0.weight"), pl->gA, pl->gB, R, pl->G(f + "0.weight"),
+                                 pl->G(f + "0.bias"), pl->partial, st))
+        return rc;
+      // Attention: xmid = x[l] + Wo attn(LN1(x[l]))
+      if (int rc = launch_wgrad(pl->gB, kDim, L.attn_out, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
+                                pl->G(a + "to_out.weight"), st))
+        return rc;
+      if (int rc = run(L.b_dattn, st)) return rc;
+      if (int rc = launch_attention_bwd(L.qkv, L.probs, probs_pitch(T), L.attn_out, pl->dattn, pl->dqkv, B, T, st)) return rc;
+      if (int rc = launch_wgrad(pl->dqkv, 3 * kDim, L.ln1, kDim, (int)R, 1, 1, kDim, 3 * kDim, 1, 1, pl->wpartial,
+                                pl->G(a + "to_qkv.weight"), st))
+        return rc;
+      if (int rc = run(L.b_dln1, st)) return rc;
+      if (int rc = launch_ln_bwd(pl->dln, pl->x[l], pl->P(a + "norm.weight"), pl->gB, pl->gA, R,
+                                 pl->G(a + "norm.weight"), pl->G(a + "norm.bias"), pl->partial, st))
+        return rc;
+    }
+    // token assembly and proj
+    if (int rc = launch_token_bwd(pl->gA, pl->dfeat, pl->G("decoder.cls_token"), B, T, st)) return rc;
+    if (int rc = launch_wgrad(pl->dfeat, kDim, pl->bp("o3"), 512, B, F, F, 512, kDim, 1, 1, pl->wpartial,
+                              pl->G("proj.weight"), st))
       return rc;
-    // Attention: xmid = x[l] + Wo attn(LN1(x[l]))
-    if (int rc = launch_wgrad(pl->gB, kDim, L.attn_out, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                              pl->G(a + "to_out.weight"), st))
-      return rc;
-    if (int rc = run(L.b_dattn, st)) return rc;
-    if (int rc = launch_attention_bwd(L.qkv, L.probs, probs_pitch(T), L.attn_out, pl->dattn, pl->dqkv, B, T, st)) return rc;
-    if (int rc = launch_wgrad(pl->dqkv, 3 * kDim, L.ln1, kDim, (int)R, 1, 1, kDim, 3 * kDim, 1, 1, pl->wpartial,
-                              pl->G(a + "to_qkv.weight"), st))
-      return rc;
-    if (int rc = run(L.b_dln1, st)) return rc;
-    if (int rc = launch_ln_bwd(pl->dln, pl->x[l], pl->P(a + "norm.weight"), pl->gB, pl->gA, R,
-                               pl->G(a + "norm.weight"), pl->G(a + "norm.bias"), pl->partial, st))
-      return rc;
+    if (int rc = run(pl->b_do3, st)) return rc;
+    return 0;
   }
-  // token assembly and proj
-  if (int rc = launch_token_bwd(pl->gA, pl->dfeat, pl->G("decoder.cls_token"), B, T, st)) return rc;
-  if (int rc = launch_wgrad(pl->dfeat, kDim, pl->bp("o3"), 512, B, F, F, 512, kDim, 1, 1, pl->wpartial,
-                            pl->G("proj.weight"), st))
-    return rc;
-  if (int rc = run(pl->b_do3, st)) return rc;
   // backbone, last conv to first
-  for (int i = kNumDefs - 1; i >= 0; --i) {
+  const int i_hi = part == 1 ? kNumDefs - 1 : kSplitConv - 1, i_lo = part == 1 ? kSplitConv : 0;
+  for (int i = i_hi; i >= i_lo; --i) {
     const ConvDef& d = kDefs[i];
     ConvRt& r = pl->conv[i];
     const std::string n = d.name;
@@ -704,6 +715,13 @@ int hgr_train_backward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const
     for (int q = 0; q < r.ndg; ++q)
       if (int rc = run(r.dg[q], st)) return rc;
   }
+  return 0;
+}
+
+int hgr_train_backward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const float* d_dlogits,
+                       const float* d_dheatmaps, void* stream) {
+  for (int part = 0; part < 3; ++part)
+    if (int rc = hgr_train_backward_part(pl, d_x, x_dtype, d_dlogits, d_dheatmaps, part, stream)) return rc;
   return 0;
 }
 

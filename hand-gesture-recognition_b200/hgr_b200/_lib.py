@@ -71,6 +71,7 @@ SIGNATURES = {
     "hgr_train_buffer": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(C.c_int64)]),
     "hgr_train_forward": (_i, [_vp, _vp, _i, _vp, _vp, C.c_float, _vp]),
     "hgr_train_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "hgr_train_backward_part": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
     "hgr_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "hgr_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _i,
                             C.c_float, _vp]),

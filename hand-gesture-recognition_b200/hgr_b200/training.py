@@ -159,11 +159,27 @@ def forward_train(state: TrainState, x: torch.Tensor, update_running: bool = Tru
     return logits, heat, plan
 
 
-def backward_train(state: TrainState, plan: TrainPlan, x, dlogits, dheat):
-    """Fills state.grads from the loss gradients (fp32, contiguous)."""
+def backward_train(state: TrainState, plan: TrainPlan, x, dlogits, dheat, part=None):
+    """Fills state.grads from the loss gradients (fp32, contiguous).  part = 0, 1, 2 (in this order) runs one third of
+    the backward: each completes one contiguous range of the gradient block (grad_buckets)."""
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().hgr_train_backward(plan.handle, x.data_ptr(), _dt(x), dlogits.data_ptr(),
-                                                  dheat.data_ptr(), _stream(x.device)), "hgr_train_backward")
+        if part is None:
+            _lib.check(_lib.load().hgr_train_backward(plan.handle, x.data_ptr(), _dt(x), dlogits.data_ptr(),
+                                                      dheat.data_ptr(), _stream(x.device)), "hgr_train_backward")
+        else:
+            _lib.check(_lib.load().hgr_train_backward_part(plan.handle, x.data_ptr(), _dt(x), dlogits.data_ptr(),
+                                                           dheat.data_ptr(), part, _stream(x.device)),
+                       "hgr_train_backward_part")
+
+
+def grad_buckets(num_joints: int, num_classes: int):
+    """[start, stop) of the gradient block's three ranges in the order the backward completes them
+    (hgr_train_backward_part 0, 1, 2): proj + decoder, encoder.down2 + cspelan3, the rest of the backbone."""
+    layout = _lib.train_param_layout(num_joints, num_classes)
+    off = {name: o for name, o, _ in layout}
+    total = layout[-1][1] + layout[-1][2]
+    a, b = off["encoder.down2.conv.weight"], off["proj.weight"]
+    return [(b, total), (a, b), (0, a)]
 
 
 class _TrainFunction(torch.autograd.Function):
@@ -285,7 +301,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, cls_weight=0.001, group=None,
-                 cuda_graph=False):
+                 cuda_graph=False, overlap_allreduce=False):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("DataParallelTrainer needs the module on a CUDA device (no CPU path)")
@@ -298,6 +314,16 @@ class DataParallelTrainer:
         # captured once per input shape and replayed; the all-reduce and the AdamW update stay ordinary launches
         self.cuda_graph = bool(cuda_graph)
         self._graphs = {}
+        # overlap_allreduce (world > 1): the backward runs in three parts and the all-reduce of the range each part
+        # completes (proj + decoder, then down2 + cspelan3 = 58 % of the block) rides on a side stream under the
+        # next part; only the last range (conv1 .. cspelan2, 18 %) is exchanged after the backward.  Bitwise the
+        # same step, but OFF by default: measured on 2 B200s (profiles/r2e_overlap_2gpu.txt) it is slower, 4.88 ms
+        # against 4.75 ms - the whole exchange costs under 0.1 ms of the step, less than the three graph replays,
+        # the two extra collective launches and the SMs NCCL takes from the persistent backward kernels
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = bool(overlap_allreduce) and world > 1
+        self._buckets = grad_buckets(model.num_joints, model.num_classes)
+        self._side = torch.cuda.Stream(dev) if self.overlap else None
         self.exp_avg = torch.zeros_like(self.state.params)
         self.exp_avg_sq = torch.zeros_like(self.state.params)
         self.steps = 0
@@ -305,12 +331,54 @@ class DataParallelTrainer:
         broadcast_from_rank0_([self.state.params, self.state.bnstats, self.state.num_batches_tracked,
                                self.exp_avg, self.exp_avg_sq], group)
 
-    def _forward_backward(self, x, labels, target, target_weight, update_running=True):
+    def _forward_loss(self, x, labels, target, target_weight, update_running=True):
         st = self.state
         logits, heat, plan = forward_train(st, x, update_running)
         loss3, dlogits, dheat = loss_and_grads(logits, heat, labels, target, target_weight, self.cls_weight)
-        backward_train(st, plan, x, dlogits, dheat)
+        return loss3, plan, dlogits, dheat
+
+    def _forward_backward(self, x, labels, target, target_weight, update_running=True):
+        loss3, plan, dlogits, dheat = self._forward_loss(x, labels, target, target_weight, update_running)
+        backward_train(self.state, plan, x, dlogits, dheat)
         return loss3
+
+    def _stages(self, x, labels, target, target_weight):
+        """The step's device work as three callables (forward + loss + backward part 0, part 1, part 2) and the loss
+        tensor: plain launches, or three CUDA graphs captured once per input shape."""
+        if not self.cuda_graph:
+            box = {}
+
+            def s0():
+                box["v"] = self._forward_loss(x, labels, target, target_weight)
+                backward_train(self.state, box["v"][1], x, box["v"][2], box["v"][3], 0)
+
+            def part(k):
+                return lambda: backward_train(self.state, box["v"][1], x, box["v"][2], box["v"][3], k)
+
+            return [s0, part(1), part(2)], lambda: box["v"][0]
+        key = ("parts", tuple(x.shape), x.dtype, tuple(target.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = x.device
+            static = [torch.empty_like(t) for t in (x, labels, target, target_weight)]
+            for s_, t in zip(static, (x, labels, target, target_weight)):
+                s_.copy_(t)
+            self._forward_backward(*static, update_running=False)  # warm-up outside the capture (see below)
+            torch.cuda.synchronize(dev)
+            graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
+            pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(graphs[0], pool=pool):
+                loss3, plan, dlogits, dheat = self._forward_loss(*static)
+                backward_train(self.state, plan, static[0], dlogits, dheat, 0)
+            for k in (1, 2):
+                with torch.cuda.graph(graphs[k], pool=pool):
+                    backward_train(self.state, plan, static[0], dlogits, dheat, k)
+            entry = self._graphs[key] = (graphs, static, loss3)
+        graphs, static, loss3 = entry
+        for s_, t in zip(static, (x, labels, target, target_weight)):
+            if s_.data_ptr() != t.data_ptr():
+                s_.copy_(t, non_blocking=True)
+        return [g.replay for g in graphs], lambda: loss3
 
     def _forward_backward_graph(self, x, labels, target, target_weight):
         key = (tuple(x.shape), x.dtype, tuple(target.shape))
@@ -336,13 +404,33 @@ class DataParallelTrainer:
         graph.replay()
         return loss3
 
+    def _step_overlapped(self, x, labels, target, target_weight):
+        """forward + backward in three parts with the all-reduce of each finished gradient range on a side stream."""
+        st = self.state
+        main = torch.cuda.current_stream(x.device)
+        stages, loss = self._stages(x, labels, target, target_weight)
+        for k, run in enumerate(stages):
+            run()
+            lo, hi = self._buckets[k]
+            if k < 2:
+                self._side.wait_stream(main)  # the range is final once this part has run
+                with torch.cuda.stream(self._side):
+                    dist.all_reduce(st.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            else:
+                dist.all_reduce(st.grads[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        main.wait_stream(self._side)
+        return loss(), dist.get_world_size(self.group)
+
     def step(self, x, labels, target, target_weight):
         st = self.state
-        if self.cuda_graph:
-            loss3 = self._forward_backward_graph(x, labels, target, target_weight)
+        if self.overlap:
+            loss3, world = self._step_overlapped(x, labels, target, target_weight)
         else:
-            loss3 = self._forward_backward(x, labels, target, target_weight)
-        world = allreduce_sum_(st.grads, self.group)
+            if self.cuda_graph:
+                loss3 = self._forward_backward_graph(x, labels, target, target_weight)
+            else:
+                loss3 = self._forward_backward(x, labels, target, target_weight)
+            world = allreduce_sum_(st.grads, self.group)
         self.steps += 1
         with torch.cuda.device(x.device):
             _lib.check(_lib.load().hgr_adamw_step(st.params.data_ptr(), st.grads.data_ptr(), self.exp_avg.data_ptr(),

@@ -293,6 +293,13 @@ HGR_API int hgr_train_forward(hgr_train_plan_t* plan, const void* d_x, int x_dty
 /* Backward of the last hgr_train_forward of this plan (same d_x): overwrites the whole gradient block. */
 HGR_API int hgr_train_backward(hgr_train_plan_t* plan, const void* d_x, int x_dtype, const float* d_dlogits,
                                const float* d_dheatmaps, void* stream);
+/* The same backward in three parts, to be called in order 0, 1, 2 (train.py:58-108 under DistributedDataParallel
+ * overlaps the gradient all-reduce with the backward; the flat gradient block is in state_dict order, so each part
+ * completes one contiguous range of it): 0 = heads, transformer, proj (parameters from "proj.weight" to the end),
+ * 1 = encoder.cspelan3 and encoder.down2 (from "encoder.down2.conv.weight" to "proj.weight"), 2 = the rest of the
+ * backbone (the start of the block). */
+HGR_API int hgr_train_backward_part(hgr_train_plan_t* plan, const void* d_x, int x_dtype, const float* d_dlogits,
+                                    const float* d_dheatmaps, int part, void* stream);
 
 /* train.py:63-64 / libs/loss.py: total = cls_weight * CrossEntropy(logits, labels) + JointsMSELoss(heatmaps, target,
  * target_weight).  d_loss3 = {total, weighted class loss, joints loss}; d_dlogits / d_dheatmaps (nullable) receive

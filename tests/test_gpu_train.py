@@ -305,6 +305,36 @@ def test_trainer_cuda_graph_replay_equals_plain_launches():
     assert int(out[1][2][0]) == 100 + 3  # synthetic_state_dict starts the counters at 100
 
 
+def test_backward_in_three_parts_equals_the_whole_backward():
+    """hgr_train_backward_part 0, 1, 2 (the units the data-parallel step overlaps its all-reduce with) write exactly
+    the gradient block of hgr_train_backward, and each part completes the range grad_buckets names: after part k
+    the ranges of parts 0..k already hold their final values."""
+    from hgr_b200 import MultiTaskNet, loss_and_grads
+    from hgr_b200.training import backward_train, forward_train, grad_buckets, train_state
+    dev = torch.device("cuda")
+    net = MultiTaskNet(21, 19, [64, 64])
+    net.load_state_dict(O.synthetic_state_dict(5), strict=True)
+    net = net.to(dev).train()
+    st = train_state(net, dev)
+    x = O.synthetic_images(4, 64, 6).to(dev)
+    labels, target, weight = (t.to(dev) for t in O.synthetic_targets(4, 64, seed=7))
+    logits, heat, plan = forward_train(st, x, update_running=False)
+    _, dl, dh = loss_and_grads(logits, heat, labels, target, weight)
+    backward_train(st, plan, x, dl, dh)
+    whole = st.grads.clone()
+    buckets = grad_buckets(21, 19)
+    total = st.layout[-1][1] + st.layout[-1][2]  # the block itself is padded to a multiple of 128 floats
+    assert buckets[0][1] == total <= whole.numel() and buckets[2][0] == 0
+    assert [b[0] for b in buckets[:2]] == [b[1] for b in buckets[1:]]
+    st.grads.fill_(float("nan"))
+    for k in range(3):
+        backward_train(st, plan, x, dl, dh, k)
+        torch.cuda.synchronize()
+        for lo, hi in buckets[: k + 1]:
+            assert torch.equal(st.grads[lo:hi], whole[lo:hi]), f"range [{lo},{hi}) not final after part {k}"
+    assert torch.equal(st.grads[:total], whole[:total])
+
+
 def _dp_gpu_worker(rank, world, port, q):
     """One rank of the 2-GPU data-parallel check (spawned: own process, own GPU, NCCL)."""
     import os
@@ -333,7 +363,20 @@ def _dp_gpu_worker(rank, world, port, q):
     mean_grads = (tr.state.grads / w).cpu()
     loss3 = tr.step(xs, labels[sl].to(dev), target[sl].to(dev), weight[sl].to(dev))
     after = replicas_in_sync(tr.state.params)
-    q.put((rank, bool(in_sync), bool(after), mean_grads.numpy(), [float(v) for v in loss3.cpu()]))
+    # the bucketed exchange under the backward (default at world > 1; plain launches and three CUDA graphs) leaves
+    # exactly the parameters of the single all-reduce after the backward
+    finals = []
+    for overlap, graph in ((False, False), (True, False), (True, True)):
+        n2 = MultiTaskNet(21, 19, [size, size])
+        n2.load_state_dict(O.synthetic_state_dict(5), strict=True)
+        t2 = DataParallelTrainer(n2.to(dev).train(), lr=1e-3, cuda_graph=graph, overlap_allreduce=overlap)
+        assert t2.overlap == overlap
+        for _ in range(3):
+            t2.step(xs, labels[sl].to(dev), target[sl].to(dev), weight[sl].to(dev))
+        torch.cuda.synchronize(dev)
+        finals.append((t2.state.params.clone(), t2.state.bnstats.clone(), t2.exp_avg_sq.clone()))
+    same = all(torch.equal(a, b) for f in finals[1:] for a, b in zip(finals[0], f))
+    q.put((rank, bool(in_sync), bool(after), mean_grads.numpy(), [float(v) for v in loss3.cpu()], bool(same)))
     dist.destroy_process_group()
 
 
@@ -360,6 +403,7 @@ def test_dp_step_on_two_gpus_averages_the_shard_gradients():
         assert p.exitcode == 0
     assert all(r[1] for r in res), "parameters not broadcast from rank 0 at construction"
     assert all(r[2] for r in res), "replicas diverged after one step"
+    assert all(r[5] for r in res), "overlapped bucketed all-reduce differs from the single all-reduce"
     assert np.array_equal(res[0][3], res[1][3]), "ranks hold different averaged gradients"
     # oracle: mean over the two shards of the reference's gradients, on rank 0's weights
     sd = O.synthetic_state_dict(5)
