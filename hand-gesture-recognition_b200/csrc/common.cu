@@ -32,7 +32,14 @@ static bool env_flag(const char* name, bool dflt) {
 
 // Retired switches: settings that lost their A/B on B200 are fixed here instead of being read from the environment
 // (DESIGN.md section 5 has the measurements); the code paths they selected stay compiled for the record.
-bool pdl_enabled() { return false; }  // programmatic dependent launch: step 2.6 % slower
+// Programmatic dependent launch.  Inference forward: measured 2.6 % slower, so it stays off there.  The training step
+// (365 launches of 5-25 us at batch 32) can turn it on for its own calls through PdlScope (HGR_TRAIN_PDL=1): measured
+// 4.93 ms against 4.55 ms per step, so it is off there too.
+static thread_local bool g_pdl_scope = false;
+bool pdl_enabled() { return g_pdl_scope; }
+PdlScope::PdlScope(bool on) : prev_(g_pdl_scope) { g_pdl_scope = on; }
+PdlScope::~PdlScope() { g_pdl_scope = prev_; }
+bool train_pdl_enabled() { return env_flag("HGR_TRAIN_PDL", false); }  // read per plan / call, not cached
 
 int prefetch_distance() { return 0; }  // L2 prefetch of later tiles: distances 1, 2, 4 are 1-5 % slower than none
 
@@ -63,6 +70,13 @@ bool stem_fused_enabled() {
 bool gelan_tail_enabled() {
   static const bool on = env_flag("HGR_GELAN_TAIL", true);
   return on;
+}
+
+// read when a training plan is created (not cached: one process can hold plans of both kinds, which is how the
+// parity test compares them)
+int train_fork_mask() {
+  const char* v = getenv("HGR_TRAIN_FORK");
+  return v && *v ? atoi(v) & 7 : 1;
 }
 
 bool stem_chain_enabled() {

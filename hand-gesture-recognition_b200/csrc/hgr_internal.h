@@ -31,6 +31,17 @@ const char* last_error();
 // CTAs of the next grid take the SM slots the persistent kernels' stragglers are about to free and gain nothing
 // back - so it is off (fixed in common.cu; the launchers keep the attribute code).
 bool pdl_enabled();
+// launches made while a PdlScope(true) is alive on this thread carry the programmatic-serialization attribute
+struct PdlScope {
+  explicit PdlScope(bool on);
+  ~PdlScope();
+  PdlScope(const PdlScope&) = delete;
+  PdlScope& operator=(const PdlScope&) = delete;
+
+ private:
+  bool prev_;
+};
+bool train_pdl_enabled();  // HGR_TRAIN_PDL (default off: measured 8 % slower)
 // HGR_ZIGZAG=0 disables the alternating tile order of plan.cu.
 bool zigzag_enabled();
 // HGR_CLUSTER=0 disables the CTA-pair (cta_group::2) mode of the implicit-GEMM kernel.
@@ -164,6 +175,9 @@ int make_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uin
 // w: [64][32] bf16, k = (kh*3+kw)*3 + c, BN scale folded in, k >= 27 zero; shift: [64] fp32.
 // HGR_CONV1_TC=0: the stem convolution falls back from the tcgen05 kernel (conv1_tc.cu) to the mma.sync kernel.
 bool conv1_tc_enabled();
+// HGR_TRAIN_FORK (bit mask, default 1): which parts of the training backward send work to the plan's side stream -
+// 1 the class head beside the pose head, 2 the transformer's weight gradients, 4 the backbone's weight gradients
+int train_fork_mask();
 bool conv1_tc_supported(int S);
 int launch_conv1_tc(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,
                     int S, bool raw, cudaStream_t stream);

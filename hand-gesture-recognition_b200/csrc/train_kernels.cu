@@ -94,7 +94,9 @@ __device__ __forceinline__ void warp_sum_partials(const float* __restrict__ part
 }
 
 int reduce_blocks(long long rows) {
-  long long b = (rows + 127) / 128;  // at least 128 rows per CTA
+  // at least 32 rows per CTA: the 12 x 12 maps of a 32-crop batch have 4608 rows, and at 128 rows per CTA their
+  // reductions ran on 36 CTAs (bn_bwd_partial 28-52 us, as long as on the 96 x 96 maps)
+  long long b = (rows + 31) / 32;
   if (b > 592) b = 592;
   if (b < 1) b = 1;
   return (int)b;
@@ -104,6 +106,8 @@ int reduce_blocks(long long rows) {
 
 __global__ void __launch_bounds__(kThreads)
 bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int C, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   column_partials<2>(rows, C, partial, [&](long long r, int c0, float (&acc)[2][8]) {
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C + c0)), v);
@@ -122,6 +126,8 @@ bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int C, long l
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
                       float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                       float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per channel
   if (c >= C) return;
   double s[2];
@@ -150,6 +156,8 @@ __global__ void __launch_bounds__(kThreads)
 bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int C, const float* __restrict__ scale,
                   const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res, int res_ctot,
                   __nv_bfloat16* __restrict__ y, int y_ctot, int cg_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   // channel groups per row are a power of two (C = 64 .. 512): row / group come from a shift and a mask
   const long long total = rows << cg_log2;
   const int cg_mask = (1 << cg_log2) - 1;
@@ -179,6 +187,8 @@ bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const _
                       long long rows, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ mean, const float* __restrict__ rstd,
                       const __nv_bfloat16* __restrict__ res, int res_ctot, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   column_partials<2>(rows, C, partial, [&](long long r, int c0, float (&acc)[2][8]) {
     float g[8], v[8], rr[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * dy_ctot + c0)), g);
@@ -203,6 +213,8 @@ bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const _
 __global__ void __launch_bounds__(256)
 bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
   double s[2];
@@ -222,6 +234,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const __n
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ c1,
                     const float* __restrict__ c2, const __nv_bfloat16* __restrict__ res, int res_ctot,
                     __nv_bfloat16* __restrict__ dres, int dres_ctot, __nv_bfloat16* __restrict__ dz, int cg_log2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = rows << cg_log2;
   const int cg_mask = (1 << cg_log2) - 1;
 #pragma unroll 2
@@ -256,6 +270,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const __n
 // ------------------------------------------------------------------ GELU ----
 __global__ void __launch_bounds__(kThreads) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             __nv_bfloat16* __restrict__ y, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kThreads) {
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), v);
@@ -268,6 +284,8 @@ __global__ void __launch_bounds__(kThreads) gelu_fwd_kernel(const __nv_bfloat16*
 // dpre = dh * (Phi(x) + x * phi(x))   (exact-erf GELU, transformer.py:35), in place on dh
 __global__ void __launch_bounds__(kThreads) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre,
                                                             __nv_bfloat16* __restrict__ dh, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kThreads) {
     float v[8], g[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(pre) + i), v);
@@ -285,6 +303,8 @@ __global__ void __launch_bounds__(kThreads) gelu_bwd_kernel(const __nv_bfloat16*
 // ------------------------------------------------------------------ bias gradients ----
 __global__ void __launch_bounds__(kThreads)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   column_partials<1>(rows, C, partial, [&](long long r, int c0, float (&acc)[1][8]) {
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(g + r * C + c0)), v);
@@ -297,6 +317,8 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C
 __global__ void __launch_bounds__(256)
 sums_final_kernel(const float* __restrict__ partial, int nblk, int K, int C, float* __restrict__ dst0,
                   float* __restrict__ dst1) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= C) return;
   if (K == 1) {
@@ -321,6 +343,8 @@ __global__ void __launch_bounds__(kThreads)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ g_in, __nv_bfloat16* __restrict__ g_out, long long rows,
               float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[8][2][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long per = (rows + gridDim.x - 1) / gridDim.x;
@@ -401,6 +425,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(kThreads)
 token_bwd_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dfeat, float* __restrict__ dcls, int B,
                  int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int P = T - 1;
   if (blockIdx.x == gridDim.x - 1) {
     const int c = threadIdx.x;
@@ -430,6 +456,8 @@ token_bwd_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict_
 //  mode 5: matrix transpose dst[c][r] = w[r][c]
 __global__ void __launch_bounds__(kThreads)
 pack_jobs_kernel(const PackJob* __restrict__ jobs, const float* __restrict__ params) {
+  pdl_launch_dependents();
+  pdl_wait();
   const PackJob jb = jobs[blockIdx.y];
   const float* __restrict__ w = params + jb.src_off;
   __nv_bfloat16* __restrict__ dst = jb.dst;
@@ -481,6 +509,8 @@ pack_jobs_kernel(const PackJob* __restrict__ jobs, const float* __restrict__ par
 __global__ void __launch_bounds__(kThreads)
 loss_heat_kernel(const float* __restrict__ heat, const float* __restrict__ target, const float* __restrict__ weight,
                  long long n, int hw, float inv_norm, float* __restrict__ dheat, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[kThreads / 32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
@@ -505,6 +535,8 @@ __global__ void __launch_bounds__(kThreads)
 loss_final_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C, float cls_weight,
                   float* __restrict__ dlogits, const float* __restrict__ partial, int nblk, float inv_norm,
                   float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float ce[kThreads];
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += kThreads) {
@@ -541,6 +573,8 @@ __global__ void __launch_bounds__(kThreads)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
              float grad_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
     const float gi = g[i] * grad_scale;
     float pi = p[i];
@@ -555,6 +589,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 }
 
 __global__ void __launch_bounds__(kThreads) zero_f32_kernel(float* __restrict__ p, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads)
     p[i] = 0.f;
 }
@@ -579,9 +615,10 @@ int launch_bn_stats(const __nv_bfloat16* z, long long rows, int C, const float* 
     return -1;
   }
   const int nblk = reduce_blocks(rows);
-  bn_stats_partial_kernel<<<nblk, kThreads, kThreads * 16 * sizeof(float), st>>>(z, rows, C, partial);
-  bn_stats_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, rows, gamma, beta, scale, shift, mean, rstd,
-                                                         running_mean, running_var, momentum);
+  HGR_CHECK_CUDA(launch_pdl(bn_stats_partial_kernel, dim3(nblk), dim3(kThreads), kThreads * 16 * sizeof(float), st,
+                            z, rows, C, partial));
+  HGR_CHECK_CUDA(launch_pdl(bn_stats_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, C, rows,
+                            gamma, beta, scale, shift, mean, rstd, running_mean, running_var, momentum));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -601,13 +638,17 @@ int launch_bn_act_fwd(const __nv_bfloat16* z, long long rows, int C, const float
   }
   const int blocks = ew_blocks(rows * (C / 8));
   if (silu && res)
-    bn_act_fwd_kernel<true, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
+    HGR_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<true, true>, dim3(blocks), dim3(kThreads), 0, st, z, rows, C, scale,
+                              shift, res, res_ctot, y, y_ctot, cgl));
   else if (silu)
-    bn_act_fwd_kernel<true, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
+    HGR_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<true, false>, dim3(blocks), dim3(kThreads), 0, st, z, rows, C, scale,
+                              shift, res, res_ctot, y, y_ctot, cgl));
   else if (res)
-    bn_act_fwd_kernel<false, true><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
+    HGR_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<false, true>, dim3(blocks), dim3(kThreads), 0, st, z, rows, C, scale,
+                              shift, res, res_ctot, y, y_ctot, cgl));
   else
-    bn_act_fwd_kernel<false, false><<<blocks, kThreads, 0, st>>>(z, rows, C, scale, shift, res, res_ctot, y, y_ctot, cgl);
+    HGR_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel<false, false>, dim3(blocks), dim3(kThreads), 0, st, z, rows, C,
+                              scale, shift, res, res_ctot, y, y_ctot, cgl));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -632,11 +673,13 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
   float* c2 = c1c2 + C;
 #define HGR_BN_BWD(S, R)                                                                                           \
   do {                                                                                                             \
-    bn_bwd_partial_kernel<S, R><<<nblk, kThreads, sm, st>>>(dy, dy_ctot, z, rows, C, scale, shift, mean, rstd, res, \
-                                                            res_ctot, partial);                                    \
-    bn_bwd_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, C, rows, dgamma, dbeta, c1, c2);            \
-    bn_bwd_apply_kernel<S, R><<<blocks, kThreads, 0, st>>>(dy, dy_ctot, z, rows, C, scale, shift, mean, rstd, c1,   \
-                                                           c2, res, res_ctot, dres, dres_ctot, dz, cgl);           \
+    HGR_CHECK_CUDA(launch_pdl(bn_bwd_partial_kernel<S, R>, dim3(nblk), dim3(kThreads), sm, st, dy, dy_ctot, z,         \
+                              rows, C, scale, shift, mean, rstd, res, res_ctot, partial));                             \
+    HGR_CHECK_CUDA(launch_pdl(bn_bwd_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, C, rows,        \
+                              dgamma, dbeta, c1, c2));                                                                 \
+    HGR_CHECK_CUDA(launch_pdl(bn_bwd_apply_kernel<S, R>, dim3(blocks), dim3(kThreads), 0, st, dy, dy_ctot, z,          \
+                              rows, C, scale, shift, mean, rstd, c1, c2, res, res_ctot, dres, dres_ctot, dz,           \
+                              cgl));                                                                                   \
   } while (0)
   if (silu && res) HGR_BN_BWD(true, true);
   else if (silu) HGR_BN_BWD(true, false);
@@ -648,13 +691,13 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
 }
 
 int launch_gelu_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, long long n, cudaStream_t st) {
-  gelu_fwd_kernel<<<ew_blocks(n / 8), kThreads, 0, st>>>(x, y, n / 8);
+  HGR_CHECK_CUDA(launch_pdl(gelu_fwd_kernel, dim3(ew_blocks(n / 8)), dim3(kThreads), 0, st, x, y, n / 8));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_gelu_bwd(const __nv_bfloat16* pre, __nv_bfloat16* dh, long long n, cudaStream_t st) {
-  gelu_bwd_kernel<<<ew_blocks(n / 8), kThreads, 0, st>>>(pre, dh, n / 8);
+  HGR_CHECK_CUDA(launch_pdl(gelu_bwd_kernel, dim3(ew_blocks(n / 8)), dim3(kThreads), 0, st, pre, dh, n / 8));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -665,8 +708,10 @@ int launch_colsum(const __nv_bfloat16* g, long long rows, int C, float* dst, flo
     return -1;
   }
   const int nblk = reduce_blocks(rows);
-  colsum_partial_kernel<<<nblk, kThreads, kThreads * 8 * sizeof(float), st>>>(g, rows, C, partial);
-  sums_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, nblk, 1, C, dst, nullptr);
+  HGR_CHECK_CUDA(launch_pdl(colsum_partial_kernel, dim3(nblk), dim3(kThreads), kThreads * 8 * sizeof(float), st, g,
+                            rows, C, partial));
+  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, 1, C, dst,
+                            nullptr));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -674,22 +719,23 @@ int launch_colsum(const __nv_bfloat16* g, long long rows, int C, float* dst, flo
 int launch_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const __nv_bfloat16* g_in,
                   __nv_bfloat16* g_out, long long rows, float* dgamma, float* dbeta, float* partial, cudaStream_t st) {
   const int nblk = reduce_blocks(rows);
-  ln_bwd_kernel<<<nblk, kThreads, 0, st>>>(dy, x, gamma, g_in, g_out, rows, partial);
-  sums_final_kernel<<<32, 256, 0, st>>>(partial, nblk, 2, 256, dgamma, dbeta);
+  HGR_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(nblk), dim3(kThreads), 0, st, dy, x, gamma, g_in, g_out, rows,
+                            partial));
+  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3(32), dim3(256), 0, st, partial, nblk, 2, 256, dgamma, dbeta));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_token_bwd(const __nv_bfloat16* g, __nv_bfloat16* dfeat, float* dcls, int B, int T, cudaStream_t st) {
   const int blocks = ew_blocks((long long)B * (T - 1) * 32) + 1;
-  token_bwd_kernel<<<blocks, kThreads, 0, st>>>(g, dfeat, dcls, B, T);
+  HGR_CHECK_CUDA(launch_pdl(token_bwd_kernel, dim3(blocks), dim3(kThreads), 0, st, g, dfeat, dcls, B, T));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_pack_jobs(const PackJob* d_jobs, int njobs, const float* params, cudaStream_t st) {
   if (njobs <= 0) return 0;
-  pack_jobs_kernel<<<dim3(32, njobs), kThreads, 0, st>>>(d_jobs, params);
+  HGR_CHECK_CUDA(launch_pdl(pack_jobs_kernel, dim3(32, njobs), dim3(kThreads), 0, st, d_jobs, params));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -701,8 +747,10 @@ int launch_loss(const float* logits, const float* heat, const long long* labels,
   const float inv_norm = 1.0f / ((float)B * (float)hw * (float)J);
   int nblk = ew_blocks(n);
   if (nblk > 592) nblk = 592;
-  loss_heat_kernel<<<nblk, kThreads, 0, st>>>(heat, target, weight, n, hw, inv_norm, dheat, partial);
-  loss_final_kernel<<<1, kThreads, 0, st>>>(logits, labels, B, C, cls_weight, dlogits, partial, nblk, inv_norm, out3);
+  HGR_CHECK_CUDA(launch_pdl(loss_heat_kernel, dim3(nblk), dim3(kThreads), 0, st, heat, target, weight, n, hw,
+                            inv_norm, dheat, partial));
+  HGR_CHECK_CUDA(launch_pdl(loss_final_kernel, dim3(1), dim3(kThreads), 0, st, logits, labels, B, C, cls_weight,
+                            dlogits, partial, nblk, inv_norm, out3));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -711,14 +759,15 @@ int launch_adamw(float* p, const float* g, float* m, float* v, long long n, floa
                  float eps, float wd, int step, float grad_scale, cudaStream_t st) {
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
-  adamw_kernel<<<ew_blocks(n), kThreads, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, sqrtf(bc2), grad_scale);
+  HGR_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(ew_blocks(n)), dim3(kThreads), 0, st, p, g, m, v, n, lr, beta1, beta2,
+                            eps, wd, bc1, sqrtf(bc2), grad_scale));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_zero_f32(float* p, long long n, cudaStream_t st) {
   if (n <= 0) return 0;
-  zero_f32_kernel<<<ew_blocks(n), kThreads, 0, st>>>(p, n);
+  HGR_CHECK_CUDA(launch_pdl(zero_f32_kernel, dim3(ew_blocks(n)), dim3(kThreads), 0, st, p, n));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

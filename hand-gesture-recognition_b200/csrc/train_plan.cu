@@ -139,7 +139,7 @@ struct WsBuf {
 };
 
 struct ConvRt {
-  bf16 *z, *w_fwd, *w_dg[4];
+  bf16 *z, *w_fwd, *w_dg[4], *dz;  // dz: one of the plan's two pre-BatchNorm gradient buffers (layer parity)
   float *scale, *shift, *mean, *rstd;
   GemmOp fwd, dg[4];
   int ndg;
@@ -174,6 +174,23 @@ struct hgr_train_plan {
   float *partial, *wpartial, *c1c2;
   PackJob* d_jobs;
   int njobs;
+  // Weight-gradient branch: at batch 32 a backward kernel runs 10-25 us and rarely fills the GPU, so the weight
+  // gradients (wgrad + split reduce, 1.3 ms of kernel time per step) run on a plan-owned side stream beside the
+  // chain that carries the input gradient.  Fork and join are events, so the branch is captured into the
+  // trainer's CUDA graph like any launch.  side == nullptr (HGR_TRAIN_FORK=0): everything on the caller's stream.
+  static constexpr int kEvents = 160;
+  cudaStream_t side = nullptr;
+  int fork_mask = 0;
+  bool pdl = false;  // programmatic dependent launch for the step's kernels (HGR_TRAIN_PDL, read at creation)
+  cudaEvent_t events[kEvents] = {};
+  int next_event = 0;
+  bf16* dz2 = nullptr;
+
+  ~hgr_train_plan() {
+    for (cudaEvent_t e : events)
+      if (e) cudaEventDestroy(e);
+    if (side) cudaStreamDestroy(side);
+  }
 
   size_t poff(const std::string& n) const {
     for (auto& e : playout)
@@ -254,6 +271,7 @@ std::vector<WsBuf> train_workspace(int S, int J, int C, int B, size_t* total) {
     }
   }
   add("dz", zmax);
+  add("dz2", zmax);  // layers alternate, so the side stream's wgrad of layer i reads its dz while layer i - 1 writes the other
   const size_t R = (size_t)B * T;
   for (int l = 0; l <= kDepth; ++l) add("x" + std::to_string(l), R * kDim * 2, B, 1, T, kDim);
   for (int l = 0; l < kDepth; ++l) {
@@ -392,6 +410,19 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
   const int B = batch, T = pl->T, F = pl->F;
   const long long R = (long long)B * T;
   pl->dz = pl->bp("dz");
+  pl->dz2 = pl->bp("dz2");
+  pl->pdl = train_pdl_enabled();
+  pl->fork_mask = train_fork_mask();
+  if (pl->fork_mask) {
+    bool ok = cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (int e = 0; ok && e < hgr_train_plan::kEvents; ++e)
+      ok = cudaEventCreateWithFlags(&pl->events[e], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("train plan: creating the weight-gradient stream and its events failed");
+      delete pl;
+      return -2;
+    }
+  }
   pl->partial = reinterpret_cast<float*>(pl->bp("partial"));
   pl->c1c2 = reinterpret_cast<float*>(pl->bp("c1c2"));
   pl->wpartial = reinterpret_cast<float*>(pl->bp("wpartial"));
@@ -423,6 +454,7 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
     r.mean = bnp + 2 * d.cout;
     r.rstd = bnp + 3 * d.cout;
     r.w_fwd = pl->bp("w." + n);
+    r.dz = (i & 1) ? pl->dz2 : pl->dz;
     r.ndg = 0;
     if (i == 0) {
       job(n + ".conv.weight", r.w_fwd, 3, 64, 3, 3, 0, 0, 64 * 32);
@@ -439,7 +471,7 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
       r.w_dg[0] = pl->bp("wdg." + n);
       job(n + ".conv.weight", r.w_dg[0], 1, d.cout, d.cin, d.k, 0, 0, wn);
       r.ndg = 1;
-      rc = build_conv_op(r.dg[0], pl->dz, B, Ho, Ho, d.cout, 0, d.cout, r.w_dg[0], nullptr, nullptr, d.k, 1, ACT_NONE,
+      rc = build_conv_op(r.dg[0], r.dz, B, Ho, Ho, d.cout, 0, d.cout, r.w_dg[0], nullptr, nullptr, d.k, 1, ACT_NONE,
                          d.dx_acc ? dx : nullptr, d.in_ctot, d.in_coff, dx, d.in_ctot, d.in_coff, d.cin);
     } else {
       r.ndg = 4;
@@ -448,7 +480,7 @@ int hgr_train_plan_create(hgr_train_plan_t** out, int S, int J, int C, int batch
         r.w_dg[q] = pl->bp("wdg" + std::to_string(q) + "." + n);
         job(n + ".conv.weight", r.w_dg[q], 2, d.cout, d.cin, 3, ph, pw,
             (long long)d.cin * (ph ? 2 : 1) * (pw ? 2 : 1) * d.cout);
-        rc = build_dgrad_s2_op(r.dg[q], pl->dz, B, H, H, d.cout, r.w_dg[q], ph, pw, dx, d.cin);
+        rc = build_dgrad_s2_op(r.dg[q], r.dz, B, H, H, d.cout, r.w_dg[q], ph, pw, dx, d.cin);
       }
     }
   }
@@ -571,6 +603,7 @@ int hgr_train_forward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, float*
     return -1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PdlScope pdl(pl->pdl);
   const int B = pl->B, S = pl->S, T = pl->T, F = pl->F;
   const long long R = (long long)B * T;
   if (int rc = launch_pack_jobs(pl->d_jobs, pl->njobs, pl->params, st)) return rc;
@@ -635,19 +668,62 @@ int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, 
     return -1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PdlScope pdl(pl->pdl);
   const int B = pl->B, S = pl->S, T = pl->T, F = pl->F;
   const long long R = (long long)B * T;
+  // fork / join of the weight-gradient branch (see hgr_train_plan::side).  ws = the stream weight gradients go to.
+  const int section = part == 0 ? 2 : 4;  // HGR_TRAIN_FORK bits: 1 class head, 2 transformer, 4 backbone
+  cudaStream_t ws = pl->side && (pl->fork_mask & section) ? pl->side : st;
+  pl->next_event = 0;
+  bool ev_ok = true, forked = false;
+  auto record = [&](cudaStream_t on) -> cudaEvent_t {  // an event marking "everything launched on `on` so far"
+    if (ws == st) return nullptr;
+    if (pl->next_event >= hgr_train_plan::kEvents) {
+      ev_ok = false;
+      return nullptr;
+    }
+    cudaEvent_t e = pl->events[pl->next_event++];
+    ev_ok = ev_ok && cudaEventRecord(e, on) == cudaSuccess;
+    return e;
+  };
+  auto wait = [&](cudaStream_t on, cudaEvent_t e) {
+    if (e) ev_ok = ev_ok && cudaStreamWaitEvent(on, e, 0) == cudaSuccess;
+  };
+  auto fork = [&]() {  // the side stream sees what the chain has produced so far
+    wait(ws, record(st));
+    forked = ws != st;
+  };
+  auto finish = [&]() -> int {  // the call returns with the branch joined
+    if (forked) wait(st, record(ws));
+    if (!ev_ok) {
+      set_error("hgr_train_backward_part: event record / wait failed (%s)", cudaGetErrorString(cudaGetLastError()));
+      return -2;
+    }
+    return 0;
+  };
   if (part == 0) {
-    // heads
+    // heads: the class head (one CTA, token 0 of gA) beside the pose head (tokens 1.. of gA)
+    cudaStream_t ws_layers = ws;
+    ws = pl->side && (pl->fork_mask & 1) ? pl->side : st;
+    fork();
+    if (int rc = launch_cls_head_bwd(pl->x[kDepth], pl->P("decoder.mlp_head.0.weight"), pl->P("decoder.mlp_head.0.bias"),
+                                     pl->P("decoder.mlp_head.1.weight"), d_dlogits, B, T, pl->C, pl->gA,
+                                     pl->G("decoder.mlp_head.0.weight"), pl->G("decoder.mlp_head.0.bias"),
+                                     pl->G("decoder.mlp_head.1.weight"), pl->G("decoder.mlp_head.1.bias"), ws))
+      return rc;
+    cudaEvent_t cls_done = record(ws);
     if (int rc = launch_pose_head_bwd(pl->x[kDepth], pl->P("decoder.simple_decoder.1.weight"), d_dheatmaps, B, F, pl->J,
                                       pl->gA, pl->wpartial, pl->G("decoder.simple_decoder.1.weight"),
                                       pl->G("decoder.simple_decoder.1.bias"), st))
       return rc;
-    if (int rc = launch_cls_head_bwd(pl->x[kDepth], pl->P("decoder.mlp_head.0.weight"), pl->P("decoder.mlp_head.0.bias"),
-                                     pl->P("decoder.mlp_head.1.weight"), d_dlogits, B, T, pl->C, pl->gA,
-                                     pl->G("decoder.mlp_head.0.weight"), pl->G("decoder.mlp_head.0.bias"),
-                                     pl->G("decoder.mlp_head.1.weight"), pl->G("decoder.mlp_head.1.bias"), st))
-      return rc;
+    wait(st, cls_done);
+    ws = ws_layers;
+    // Within a layer the four weight gradients leave for the side stream as soon as their operand exists; the chain
+    // waits for one of them only where it is about to overwrite that operand: gA at the layer's last kernel, dh /
+    // gB / dqkv in the NEXT layer (w_ff1 / w_out / w_qkv below carry those events across the iteration).  wpartial,
+    // the split-reduction scratch of every wgrad, is used by the pose head above on the chain: the first fork
+    // orders the branch after it.
+    cudaEvent_t w_ff2 = nullptr, w_ff1 = nullptr, w_out = nullptr, w_qkv = nullptr;
     // transformer layers, last to first; gA holds d(x[l+1]) on entry and d(x[l]) on exit
     for (int l = kDepth - 1; l >= 0; --l) {
       LayerRt& L = pl->layer[l];
@@ -655,43 +731,59 @@ int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, 
       const std::string f = "decoder.transformer.layers." + std::to_string(l) + ".1.net.";
       // FeedForward: x[l+1] = xmid + W4 gelu(W1 LN2(xmid) + b1) + b4
       if (int rc = launch_colsum(pl->gA, R, kDim, pl->G(f + "4.bias"), pl->partial, st)) return rc;
+      fork();
       if (int rc = launch_wgrad(pl->gA, kDim, L.hact, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                                pl->G(f + "4.weight"), st))
+                                pl->G(f + "4.weight"), ws))
         return rc;
+      w_ff2 = record(ws);
+      wait(st, w_ff1);  // the previous layer's wgrad still reads dh
       if (int rc = run(L.b_dh, st)) return rc;
       if (int rc = launch_gelu_bwd(L.hpre, pl->dh, R * kDim, st)) return rc;
       if (int rc = launch_colsum(pl->dh, R, kDim, pl->G(f + "1.bias"), pl->partial, st)) return rc;
+      fork();
       if (int rc = launch_wgrad(pl->dh, kDim, L.ln2, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                                pl->G(f + "1.weight"), st))
+                                pl->G(f + "1.weight"), ws))
         return rc;
+      w_ff1 = record(ws);
       if (int rc = run(L.b_dln2, st)) return rc;
+      wait(st, w_out);  // ... gB
       if (int rc = launch_ln_bwd(pl->dln, L.xmid, pl->P(f + "0.weight"), pl->gA, pl->gB, R, pl->G(f + "0.weight"),
                                  pl->G(f + "0.bias"), pl->partial, st))
         return rc;
       // Attention: xmid = x[l] + Wo attn(LN1(x[l]))
+      fork();
       if (int rc = launch_wgrad(pl->gB, kDim, L.attn_out, kDim, (int)R, 1, 1, kDim, kDim, 1, 1, pl->wpartial,
-                                pl->G(a + "to_out.weight"), st))
+                                pl->G(a + "to_out.weight"), ws))
         return rc;
+      w_out = record(ws);
       if (int rc = run(L.b_dattn, st)) return rc;
+      wait(st, w_qkv);  // ... dqkv
       if (int rc = launch_attention_bwd(L.qkv, L.probs, probs_pitch(T), L.attn_out, pl->dattn, pl->dqkv, B, T, st)) return rc;
+      fork();
       if (int rc = launch_wgrad(pl->dqkv, 3 * kDim, L.ln1, kDim, (int)R, 1, 1, kDim, 3 * kDim, 1, 1, pl->wpartial,
-                                pl->G(a + "to_qkv.weight"), st))
+                                pl->G(a + "to_qkv.weight"), ws))
         return rc;
+      w_qkv = record(ws);
       if (int rc = run(L.b_dln1, st)) return rc;
+      wait(st, w_ff2);  // this layer's first wgrad reads gA, which the next kernel rewrites
       if (int rc = launch_ln_bwd(pl->dln, pl->x[l], pl->P(a + "norm.weight"), pl->gB, pl->gA, R,
                                  pl->G(a + "norm.weight"), pl->G(a + "norm.bias"), pl->partial, st))
         return rc;
     }
     // token assembly and proj
     if (int rc = launch_token_bwd(pl->gA, pl->dfeat, pl->G("decoder.cls_token"), B, T, st)) return rc;
+    fork();
     if (int rc = launch_wgrad(pl->dfeat, kDim, pl->bp("o3"), 512, B, F, F, 512, kDim, 1, 1, pl->wpartial,
-                              pl->G("proj.weight"), st))
+                              pl->G("proj.weight"), ws))
       return rc;
     if (int rc = run(pl->b_do3, st)) return rc;
-    return 0;
+    return finish();
   }
-  // backbone, last conv to first
+  // backbone, last conv to first.  Layer i's BatchNorm backward writes dz buffer (i & 1); its wgrad reads that buffer
+  // on the side stream while the chain goes on to the input gradient and to layer i - 1 (other buffer), and layer
+  // i - 2 waits for it before it writes the buffer again.
   const int i_hi = part == 1 ? kNumDefs - 1 : kSplitConv - 1, i_lo = part == 1 ? kSplitConv : 0;
+  cudaEvent_t w_done[2] = {nullptr, nullptr};
   for (int i = i_hi; i >= i_lo; --i) {
     const ConvDef& d = kDefs[i];
     ConvRt& r = pl->conv[i];
@@ -701,21 +793,24 @@ int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, 
     const bf16* dy = pl->bp(std::string("d_") + d.out) + d.out_coff;
     const bf16* res = d.res ? pl->bp(d.res) + d.res_coff : nullptr;
     bf16* dres = d.res ? pl->bp(std::string("d_") + d.res) + d.res_coff : nullptr;
+    wait(st, w_done[i & 1]);
     if (int rc = launch_bn_bwd(dy, d.out_ctot, r.z, rows, d.cout, r.scale, r.shift, r.mean, r.rstd, 1, res, d.res_ctot,
                                dres, d.res_ctot, pl->G(n + ".bn.weight"), pl->G(n + ".bn.bias"), pl->c1c2, pl->partial,
-                               pl->dz, st))
+                               r.dz, st))
       return rc;
+    fork();
     if (i == 0) {
-      if (int rc = launch_conv1_wgrad(pl->dz, d_x, x_dtype, B, S, pl->wpartial, pl->G(n + ".conv.weight"), st)) return rc;
+      if (int rc = launch_conv1_wgrad(r.dz, d_x, x_dtype, B, S, pl->wpartial, pl->G(n + ".conv.weight"), ws)) return rc;
       break;
     }
-    if (int rc = launch_wgrad(pl->dz, d.cout, pl->bp(d.in) + d.in_coff, d.in_ctot, B, H, H, d.cin, d.cout, d.k, d.s,
-                              pl->wpartial, pl->G(n + ".conv.weight"), st))
+    if (int rc = launch_wgrad(r.dz, d.cout, pl->bp(d.in) + d.in_coff, d.in_ctot, B, H, H, d.cin, d.cout, d.k, d.s,
+                              pl->wpartial, pl->G(n + ".conv.weight"), ws))
       return rc;
+    w_done[i & 1] = record(ws);
     for (int q = 0; q < r.ndg; ++q)
       if (int rc = run(r.dg[q], st)) return rc;
   }
-  return 0;
+  return finish();
 }
 
 int hgr_train_backward(hgr_train_plan_t* pl, const void* d_x, int x_dtype, const float* d_dlogits,
@@ -734,6 +829,7 @@ int hgr_loss(const float* d_logits, const float* d_heatmaps, const long long* d_
     set_error("hgr_loss: null argument");
     return -1;
   }
+  PdlScope pdl(train_pdl_enabled());
   return launch_loss(d_logits, d_heatmaps, d_labels, d_target, d_target_weight, B, J, C, hw, cls_weight, d_dlogits,
                      d_dheatmaps, d_scratch, d_loss3, static_cast<cudaStream_t>(stream));
 }
@@ -744,6 +840,7 @@ int hgr_adamw_step(float* d_params, const float* d_grads, float* d_exp_avg, floa
     set_error("hgr_adamw_step: bad argument");
     return -1;
   }
+  PdlScope pdl(train_pdl_enabled());
   return launch_adamw(d_params, d_grads, d_exp_avg, d_exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step,
                       grad_scale, static_cast<cudaStream_t>(stream));
 }

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kBThreads)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ probs, int pp,
                      const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                      __nv_bfloat16* __restrict__ dqkv, int T, int Tp, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int spp = Tp + 8;  // staged P pitch (elements)
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(smraw);
@@ -265,6 +267,8 @@ cls_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __res
                     const float* __restrict__ beta, const float* __restrict__ w, const float* __restrict__ dlogits,
                     int B, int T, int NC, __nv_bfloat16* __restrict__ dtokens, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dbias) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float smc[];
   float* sdw = smc;                 // [NC][256]
   float* sdl = sdw + NC * kDim;     // [NC] current image's dlogits
@@ -320,15 +324,20 @@ constexpr int kPhases = 2;  // pixel phases per CTA: thread (c, q) handles outpu
 
 // Shared-memory traffic decides this kernel (42 loads per pixel and channel in the naive form), so the weight
 // column of a thread lives in registers and the dheat row is staged TRANSPOSED ([ox][24 joints]) so that the 21
-// joint values of a pixel arrive as six broadcast 128-bit loads.
+// joint values of a pixel arrive as six broadcast 128-bit loads.  The three token rows a CTA interpolates from
+// (ty - 1, ty, ty + 1) are staged once: four dependent global loads per pixel were the kernel's latency chain
+// (0.31 ms at batch 32 before, one L2 round trip per inner iteration).
 __global__ void __launch_bounds__(256 * kPhases, 1)
 pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __restrict__ w /*[J][256] fp32*/,
                      const float* __restrict__ dheat, int F, int J, __nv_bfloat16* __restrict__ dtokens,
                      float* __restrict__ dw_partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float smp[];
   const int So = 4 * F;
   float* sdx = smp;                       // [kPhases][F][256]  per-phase accumulators of this token row
   float* sdh = sdx + kPhases * F * kDim;  // [So][kMaxJ]        dheat of the current output row, joint-contiguous
+  __nv_bfloat16* stok = reinterpret_cast<__nv_bfloat16*>(sdh + So * kMaxJ);  // [3][F][256] token rows ty-1 .. ty+1
   const int b = blockIdx.y, ty = blockIdx.x;
   const int c = threadIdx.x & 255, q = threadIdx.x >> 8;
   const int T = F * F + 1;
@@ -340,6 +349,12 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
   for (int j = 0; j < kMaxJ; ++j) {
     wr[j] = j < J ? __bfloat162float(__float2bfloat16_rn(w[(size_t)j * kDim + c])) : 0.f;  // the forward used bf16 weights
     dwacc[j] = 0.f;
+  }
+  for (int i = threadIdx.x; i < 3 * F * (kDim / 8); i += 256 * kPhases) {
+    const int r = i / (F * (kDim / 8)), y = ty - 1 + r;
+    if (y >= 0 && y < F)
+      reinterpret_cast<uint4*>(stok)[i] =
+          __ldg(reinterpret_cast<const uint4*>(tok + (size_t)y * F * kDim) + i % (F * (kDim / 8)));
   }
   float* mydx = sdx + q * F * kDim;
   for (int x = 0; x < F; ++x) mydx[x * kDim + c] = 0.f;
@@ -353,6 +368,8 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
     const float l1 = sy - (float)y0, l0 = 1.0f - l1;
     const float wy = (y0 == ty ? l0 : 0.f) + (y1 == ty ? l1 : 0.f);
     const bool owner = y0 == ty;
+    const __nv_bfloat16* r0 = stok + (size_t)(y0 - ty + 1) * F * kDim + c;
+    const __nv_bfloat16* r1 = stok + (size_t)(y1 - ty + 1) * F * kDim + c;
     __syncthreads();
     for (int i = threadIdx.x; i < J * So; i += 256 * kPhases) {
       const int j = i / So, ox = i % So;
@@ -364,10 +381,10 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
       const int x0 = (int)sx;
       const int x1 = x0 + (x0 < F - 1 ? 1 : 0);
       const float m1 = sx - (float)x0, m0 = 1.0f - m1;
-      const float t00 = __bfloat162float(tok[((size_t)y0 * F + x0) * kDim + c]);
-      const float t01 = __bfloat162float(tok[((size_t)y0 * F + x1) * kDim + c]);
-      const float t10 = __bfloat162float(tok[((size_t)y1 * F + x0) * kDim + c]);
-      const float t11 = __bfloat162float(tok[((size_t)y1 * F + x1) * kDim + c]);
+      const float t00 = __bfloat162float(r0[x0 * kDim]);
+      const float t01 = __bfloat162float(r0[x1 * kDim]);
+      const float t10 = __bfloat162float(r1[x0 * kDim]);
+      const float t11 = __bfloat162float(r1[x1 * kDim]);
       const float up = l0 * (m0 * t00 + m1 * t01) + l1 * (m0 * t10 + m1 * t11);
       if (up > 0.f) {
         float dup = 0.f;
@@ -414,6 +431,8 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
 // dbias[j] = sum_{b, pix} dheat[b][j][pix]: one CTA per joint, fixed order
 __global__ void __launch_bounds__(256)
 heat_bias_grad_kernel(const float* __restrict__ dheat, int B, int J, int hw, float* __restrict__ dbias) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[256];
   const int j = blockIdx.x;
   float s = 0.f;
@@ -446,10 +465,12 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, i
   const float scale = 0.17677669529663687f;
   if (with_p <= 227 * 1024) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_p));
-    attention_bwd_kernel<true><<<B * kHeads, kBThreads, with_p, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, scale);
+    HGR_CHECK_CUDA(launch_pdl(attention_bwd_kernel<true>, dim3(B * kHeads), dim3(kBThreads), with_p, st, qkv, probs,
+                              pp, o, d_o, dqkv, T, Tp, scale));
   } else {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base));
-    attention_bwd_kernel<false><<<B * kHeads, kBThreads, base, st>>>(qkv, probs, pp, o, d_o, dqkv, T, Tp, scale);
+    HGR_CHECK_CUDA(launch_pdl(attention_bwd_kernel<false>, dim3(B * kHeads), dim3(kBThreads), base, st, qkv, probs,
+                              pp, o, d_o, dqkv, T, Tp, scale));
   }
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -464,7 +485,8 @@ int launch_cls_head_bwd(const __nv_bfloat16* tokens, const float* gamma, const f
   }
   const size_t smem = ((size_t)NC * kDim + NC) * sizeof(float);
   HGR_CHECK_CUDA(cudaFuncSetAttribute(cls_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cls_head_bwd_kernel<<<1, 256, smem, st>>>(tokens, gamma, beta, w, dlogits, B, T, NC, dtokens, dgamma, dbeta, dw, dbias);
+  HGR_CHECK_CUDA(launch_pdl(cls_head_bwd_kernel, dim3(1), dim3(256), smem, st, tokens, gamma, beta, w, dlogits, B, T,
+                            NC, dtokens, dgamma, dbeta, dw, dbias));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -478,15 +500,16 @@ int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const floa
   const int So = 4 * F;
   size_t accf = (size_t)kPhases * F * kDim;
   if (accf < (size_t)kMaxJ * kDim) accf = (size_t)kMaxJ * kDim;  // the phase fold re-uses this space as [J][256]
-  const size_t smem = (accf + (size_t)kMaxJ * So) * sizeof(float);
+  const size_t smem = (accf + (size_t)kMaxJ * So) * sizeof(float) + (size_t)3 * F * kDim * sizeof(__nv_bfloat16);
   if (smem > 227 * 1024) {
     set_error("pose_head_bwd: feature side %d does not fit shared memory", F);
     return -1;
   }
   HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pose_head_bwd_kernel<<<dim3(F, B), 256 * kPhases, smem, st>>>(tokens, w, dheat, F, J, dtokens, dw_partial);
+  HGR_CHECK_CUDA(launch_pdl(pose_head_bwd_kernel, dim3(F, B), dim3(256 * kPhases), smem, st, tokens, w, dheat, F, J,
+                            dtokens, dw_partial));
   if (int rc = launch_partial_sum(dw_partial, B * F, J * kDim, dw, st)) return rc;
-  heat_bias_grad_kernel<<<J, 256, 0, st>>>(dheat, B, J, So * So, dbias);
+  HGR_CHECK_CUDA(launch_pdl(heat_bias_grad_kernel, dim3(J), dim3(256), 0, st, dheat, B, J, So * So, dbias));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

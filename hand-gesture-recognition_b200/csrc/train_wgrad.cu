@@ -37,6 +37,8 @@ struct WgradParams {
 template <int MT>
 __global__ void __launch_bounds__(kWThreads)
 wgrad_kernel(const WgradParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int BM = 32 * MT;
   constexpr int kGPitch = BM * 2 + 16;  // bytes per staged G row
   constexpr int kGTile = kPix * kGPitch, kXTile = kPix * kXPitch;
@@ -157,41 +159,72 @@ wgrad_kernel(const WgradParams p) {
 }
 
 // dW[(co * Cin + ci) * taps + tap] = sum_chunk partial[chunk][tap][co][ci]   (PyTorch's (Cout, Cin, kh, kw))
+// SPLIT thread groups share an element: group g adds chunks g, g + SPLIT, ... in ascending order and the groups are
+// folded in ascending order through shared memory, so the sum order depends on the shapes only.  The small 1x1
+// weights have few elements and many chunks (128 x 64 elements, 288 chunks: 33 us on 64 CTAs with one thread per
+// element); SPLIT = 8 gives those a grid that fills the GPU and an eighth of the serial chain.
+template <int SPLIT>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int taps, int Cout, int Cin, float* __restrict__ dw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int kPer = 256 / SPLIT;  // elements per CTA and pass
+  __shared__ float fold[SPLIT > 1 ? 256 : 1];
   const long long total = (long long)Cout * Cin * taps;
   const long long slab = (long long)taps * Cout * Cin;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+  const int e = threadIdx.x % kPer, g = threadIdx.x / kPer;
+  for (long long base = (long long)blockIdx.x * kPer; base < total; base += (long long)gridDim.x * kPer) {
     // i walks the partial layout [tap][co][ci] so that the loads are coalesced
-    const int ci = (int)(i % Cin);
-    const int co = (int)((i / Cin) % Cout);
-    const int tap = (int)(i / ((long long)Cin * Cout));
+    const long long i = base + e;
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += partial[c * slab + i];
-    dw[((size_t)co * Cin + ci) * taps + tap] = s;
+    if (i < total)
+      for (int c = g; c < chunks; c += SPLIT) s += partial[c * slab + i];
+    if constexpr (SPLIT > 1) {
+      __syncthreads();
+      fold[threadIdx.x] = s;
+      __syncthreads();
+      if (g != 0) continue;
+      s = fold[e];
+#pragma unroll
+      for (int q = 1; q < SPLIT; ++q) s += fold[q * kPer + e];
+    }
+    if (i < total) {
+      const int ci = (int)(i % Cin);
+      const int co = (int)((i / Cin) % Cout);
+      const int tap = (int)(i / ((long long)Cin * Cout));
+      dw[((size_t)co * Cin + ci) * taps + tap] = s;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // conv1 (3 -> 64, 3x3 s2) weight gradient.  The input is the NCHW crop (fp32 or bf16) and K = 27 per output
-// pixel, so this one runs on the CUDA cores: a CTA owns `rows_per_cta` output rows of one image, stages the
-// dz row (96 x 64 bf16) and the three input rows it touches in shared memory, and thread (co, q) accumulates
-// the 7 (or 6) weights k = q, q + 4, ... of output channel co.  Per-CTA partials, fixed-order reduce.
+// pixel, so this one runs on the CUDA cores: a CTA owns `rows_per_cta` output rows of one image and stages the
+// dz row (96 x 64 bf16) and the three input rows it touches in shared memory.  Thread (cg, q, ph) accumulates the
+// 7 (or 6) weights k = q, q + 4, ... of the FOUR output channels 4 cg .. 4 cg + 3 over the output columns
+// ow = ph (mod 4): one 8-byte dz load and seven input loads feed 28 FMAs (with one channel per thread it was 8
+// loads for 7 FMAs, and the kernel ran at the shared-memory issue rate: 113 us at batch 32).  The four column
+// phases are folded in a fixed order at the end.  Per-CTA partials, fixed-order reduce.
 // ---------------------------------------------------------------------------------------------
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const TIn* __restrict__ x, int S, int rows_per_cta,
                    float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   const int So = S >> 1;
   float* sxin = reinterpret_cast<float*>(smem);  // [3 ci][3 rows][S + 2], padded to a 16-byte multiple
   __nv_bfloat16* sdz = reinterpret_cast<__nv_bfloat16*>(sxin + ((9 * (S + 2) + 3) & ~3));  // [So][64]
+  float* fold = reinterpret_cast<float*>(sdz + (size_t)So * 64);                           // [4 ph][64 co][27]
   const int b = blockIdx.y;
   const int oh0 = blockIdx.x * rows_per_cta;
-  const int co = threadIdx.x & 63, q = threadIdx.x >> 6;
-  float acc[7];
+  const int cg = threadIdx.x & 15, q = (threadIdx.x >> 4) & 3, ph = threadIdx.x >> 6;
+  float acc[7][4];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 7; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
   // the (up to) 7 taps of this thread: k = q + 4 i -> (kh, kw, ci), offset into sxin for ow = 0
   int koff[7];
 #pragma unroll
@@ -223,26 +256,37 @@ conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const TIn* __restrict__
     const uint4* src = reinterpret_cast<const uint4*>(dz + (((size_t)b * So + oh) * So) * 64);
     for (int i = threadIdx.x; i < So * 8; i += 256) reinterpret_cast<uint4*>(sdz)[i] = __ldg(src + i);
     __syncthreads();
-    for (int ow = 0; ow < So; ++ow) {
-      const float gz = __bfloat162float(sdz[ow * 64 + co]);
+    for (int ow = ph; ow < So; ow += 4) {
+      const uint2 gz2 = *reinterpret_cast<const uint2*>(sdz + ow * 64 + 4 * cg);
+      const float gz[4] = {bf16_lo(gz2.x), bf16_hi(gz2.x), bf16_lo(gz2.y), bf16_hi(gz2.y)};
 #pragma unroll
       for (int i = 0; i < 7; ++i)
-        if (koff[i] >= 0) acc[i] = fmaf(gz, sxin[koff[i] + 2 * ow], acc[i]);
+        if (koff[i] >= 0) {
+          const float xv = sxin[koff[i] + 2 * ow];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(gz[c], xv, acc[i][c]);
+        }
     }
   }
-  // partial[cta][co][27]  (27 = ci-major PyTorch order: (ci, kh, kw))
-  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * 27 + co * 27;
+  // fold the four column phases in ascending order; partial[cta][co][27]  (27 = PyTorch order: (ci, kh, kw))
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     const int k = q + 4 * i;
     if (k < 27) {
       const int ci = k % 3, kw = (k / 3) % 3, kh = k / 9;
-      out[ci * 9 + kh * 3 + kw] = acc[i];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) fold[(ph * 64 + 4 * cg + c) * 27 + ci * 9 + kh * 3 + kw] = acc[i][c];
     }
   }
+  __syncthreads();
+  float* out = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 64 * 27;
+  for (int i = threadIdx.x; i < 64 * 27; i += 256)
+    out[i] = ((fold[i] + fold[64 * 27 + i]) + fold[2 * 64 * 27 + i]) + fold[3 * 64 * 27 + i];
 }
 
 __global__ void partial_sum_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -275,7 +319,7 @@ static int launch_wgrad_impl(const WgradParams& p, int chunks, cudaStream_t st) 
     configured = true;
   }
   dim3 grid((p.Cout / BM) * (p.Cin / 64), p.k * p.k, chunks);
-  wgrad_kernel<MT><<<grid, kWThreads, smem, st>>>(p);
+  HGR_CHECK_CUDA(launch_pdl(wgrad_kernel<MT>, dim3(grid), dim3(kWThreads), smem, st, p));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -314,9 +358,16 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
   p.per_chunk = (int)per;
   if (int rc = wgrad_bm(Cout) == 128 ? launch_wgrad_impl<4>(p, chunks, st) : launch_wgrad_impl<2>(p, chunks, st)) return rc;
   const long long total = (long long)Cout * Cin * k * k;
-  int rb = (int)((total + 255) / 256);
+  // elements per CTA: 256, or 32 when that still leaves fewer than four CTAs per SM and there are chunks to share
+  const bool split = total / 256 < 148 * 4 && chunks >= 16;
+  long long rb = (total + (split ? 31 : 255)) / (split ? 32 : 256);
   if (rb > 148 * 8) rb = 148 * 8;
-  wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, chunks, k * k, Cout, Cin, dw);
+  if (split)
+    HGR_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel<8>, dim3((unsigned)rb), dim3(256), 0, st, partial, chunks, k * k, Cout,
+                              Cin, dw));
+  else
+    HGR_CHECK_CUDA(launch_pdl(wgrad_reduce_kernel<1>, dim3((unsigned)rb), dim3(256), 0, st, partial, chunks, k * k, Cout,
+                              Cin, dw));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -332,24 +383,26 @@ int launch_conv1_wgrad(const __nv_bfloat16* dz, const void* x, int x_dtype, int 
   const int So = S / 2;
   const int rows_per_cta = 8;
   dim3 grid((So + rows_per_cta - 1) / rows_per_cta, B);
-  const size_t smem = (size_t)((9 * (S + 2) + 3) & ~3) * sizeof(float) + (size_t)So * 64 * 2;
+  const size_t smem = (size_t)((9 * (S + 2) + 3) & ~3) * sizeof(float) + (size_t)So * 64 * 2 + (size_t)4 * 64 * 27 * 4;
   if (x_dtype == DT_F32) {
     HGR_CHECK_CUDA(cudaFuncSetAttribute(conv1_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_wgrad_kernel<float><<<grid, 256, smem, st>>>(dz, static_cast<const float*>(x), S, rows_per_cta, partial);
+    HGR_CHECK_CUDA(launch_pdl(conv1_wgrad_kernel<float>, dim3(grid), dim3(256), smem, st, dz,
+                              static_cast<const float*>(x), S, rows_per_cta, partial));
   } else {
     HGR_CHECK_CUDA(
         cudaFuncSetAttribute(conv1_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv1_wgrad_kernel<__nv_bfloat16>
-        <<<grid, 256, smem, st>>>(dz, static_cast<const __nv_bfloat16*>(x), S, rows_per_cta, partial);
+    HGR_CHECK_CUDA(launch_pdl(conv1_wgrad_kernel<__nv_bfloat16>, dim3(grid), dim3(256), smem, st, dz,
+                              static_cast<const __nv_bfloat16*>(x), S, rows_per_cta, partial));
   }
   const int nparts = grid.x * grid.y;
-  partial_sum_kernel<<<(64 * 27 + 127) / 128, 128, 0, st>>>(partial, nparts, 64 * 27, dw);
+  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((64 * 27 + 127) / 128), dim3(128), 0, st, partial, nparts,
+                            64 * 27, dw));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_partial_sum(const float* partial, int nparts, int n, float* dst, cudaStream_t st) {
-  partial_sum_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, nparts, n, dst);
+  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((n + 127) / 128), dim3(128), 0, st, partial, nparts, n, dst));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
