@@ -68,7 +68,8 @@ int launch_cls_head_bwd(const __nv_bfloat16* tokens, const float* gamma, const f
                         const float* dlogits, int B, int T, int NC, __nv_bfloat16* dtokens, float* dgamma,
                         float* dbeta, float* dw, float* dbias, cudaStream_t st);
 int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const float* dheat, int B, int F, int J,
-                         __nv_bfloat16* dtokens, float* dw_partial, float* dw, float* dbias, cudaStream_t st);
+                         __nv_bfloat16* dtokens, float* dw_partial, float* dw, cudaStream_t st);
+int launch_heat_bias_grad(const float* dheat, int B, int J, int hw, float* dbias, cudaStream_t st);
 
 // conv1 without BatchNorm / activation (train-mode forward)
 int launch_conv1_raw(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, int B, int S,

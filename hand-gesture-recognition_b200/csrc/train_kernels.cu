@@ -75,22 +75,33 @@ __device__ __forceinline__ void column_partials(long long rows, int C, float* __
   }
 }
 
-// Fixed-order sum of column c over the per-CTA partials: lane l adds partials l, l + 32, ... (ascending), then the
-// 32 lane sums are folded by a butterfly.  The order depends only on nblk, so the result is reproducible.
+// Fixed-order sum of column c over the per-CTA partials by ONE CTA of 128 threads: thread t adds partials t, t + 128,
+// ... (ascending, double), the lane sums are folded by a butterfly and the four warp sums in ascending order, so the
+// order depends only on nblk and the result is reproducible.  True in thread 0, which holds the sums.  (A warp per
+// channel and eight channels per CTA ran the 64-channel layers' 592 partials on 8 CTAs: 10 us per launch.)
+constexpr int kFinalThreads = 128;
 template <int K>
-__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partial, int nblk, int C, int c,
-                                                  double (&out)[K]) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ bool block_sum_partials(const float* __restrict__ partial, int nblk, int C, int c,
+                                                   double (&out)[K]) {
+  __shared__ double fold[kFinalThreads / 32][K];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; ++k) out[k] = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
+  for (int b = threadIdx.x; b < nblk; b += kFinalThreads) {
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] += (double)partial[((size_t)b * K + k) * C + c];
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k)
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) out[k] += __shfl_xor_sync(0xffffffffu, out[k], o);
+    if (lane == 0) fold[w][k] = out[k];
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return false;
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = ((fold[0][k] + fold[1][k]) + fold[2][k]) + fold[3][k];
+  return true;
 }
 
 int reduce_blocks(long long rows) {
@@ -121,18 +132,16 @@ bn_stats_partial_kernel(const __nv_bfloat16* __restrict__ z, long long rows, int
 
 // mean / biased variance of the batch -> scale = gamma * rstd, shift = beta - mean * scale, x-hat parameters
 // (mean, rstd) for the backward pass, and the running statistics (unbiased variance, momentum).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinalThreads)
 bn_stats_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scale,
                       float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                       float* __restrict__ running_mean, float* __restrict__ running_var, float momentum) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);  // one warp per channel
-  if (c >= C) return;
+  const int c = blockIdx.x;  // one CTA per channel
   double s[2];
-  warp_sum_partials<2>(partial, nblk, C, c, s);
-  if ((threadIdx.x & 31) != 0) return;
+  if (!block_sum_partials<2>(partial, nblk, C, c, s)) return;
   const double n = (double)rows;
   const double mean = s[0] / n;
   double var = s[1] / n - mean * mean;
@@ -210,16 +219,14 @@ bn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ dy, int dy_ctot, const _
 }
 
 // d beta = S1, d gamma = S2; c1 = S1 / n, c2 = S2 / n for the apply pass
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinalThreads)
 bn_bwd_final_kernel(const float* __restrict__ partial, int nblk, int C, long long rows, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ c1, float* __restrict__ c2) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  const int c = blockIdx.x;
   double s[2];
-  warp_sum_partials<2>(partial, nblk, C, c, s);
-  if ((threadIdx.x & 31) != 0) return;
+  if (!block_sum_partials<2>(partial, nblk, C, c, s)) return;
   dbeta[c] = (float)s[0];
   dgamma[c] = (float)s[1];
   c1[c] = (float)(s[0] / (double)rows);
@@ -314,21 +321,18 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C
 }
 
 // out_k[c] = sum_b partial[b][k][c]  (k < K <= 2; dst1 may be null)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinalThreads)
 sums_final_kernel(const float* __restrict__ partial, int nblk, int K, int C, float* __restrict__ dst0,
                   float* __restrict__ dst1) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= C) return;
+  const int c = blockIdx.x;
   if (K == 1) {
     double s[1];
-    warp_sum_partials<1>(partial, nblk, C, c, s);
-    if ((threadIdx.x & 31) == 0 && dst0 != nullptr) dst0[c] = (float)s[0];
+    if (block_sum_partials<1>(partial, nblk, C, c, s) && dst0 != nullptr) dst0[c] = (float)s[0];
   } else {
     double s[2];
-    warp_sum_partials<2>(partial, nblk, C, c, s);
-    if ((threadIdx.x & 31) == 0) {
+    if (block_sum_partials<2>(partial, nblk, C, c, s)) {
       if (dst0 != nullptr) dst0[c] = (float)s[0];
       if (dst1 != nullptr) dst1[c] = (float)s[1];
     }
@@ -617,7 +621,7 @@ int launch_bn_stats(const __nv_bfloat16* z, long long rows, int C, const float* 
   const int nblk = reduce_blocks(rows);
   HGR_CHECK_CUDA(launch_pdl(bn_stats_partial_kernel, dim3(nblk), dim3(kThreads), kThreads * 16 * sizeof(float), st,
                             z, rows, C, partial));
-  HGR_CHECK_CUDA(launch_pdl(bn_stats_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, C, rows,
+  HGR_CHECK_CUDA(launch_pdl(bn_stats_final_kernel, dim3(C), dim3(kFinalThreads), 0, st, partial, nblk, C, rows,
                             gamma, beta, scale, shift, mean, rstd, running_mean, running_var, momentum));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -675,7 +679,7 @@ int launch_bn_bwd(const __nv_bfloat16* dy, int dy_ctot, const __nv_bfloat16* z, 
   do {                                                                                                             \
     HGR_CHECK_CUDA(launch_pdl(bn_bwd_partial_kernel<S, R>, dim3(nblk), dim3(kThreads), sm, st, dy, dy_ctot, z,         \
                               rows, C, scale, shift, mean, rstd, res, res_ctot, partial));                             \
-    HGR_CHECK_CUDA(launch_pdl(bn_bwd_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, C, rows,        \
+    HGR_CHECK_CUDA(launch_pdl(bn_bwd_final_kernel, dim3(C), dim3(kFinalThreads), 0, st, partial, nblk, C, rows,        \
                               dgamma, dbeta, c1, c2));                                                                 \
     HGR_CHECK_CUDA(launch_pdl(bn_bwd_apply_kernel<S, R>, dim3(blocks), dim3(kThreads), 0, st, dy, dy_ctot, z,          \
                               rows, C, scale, shift, mean, rstd, c1, c2, res, res_ctot, dres, dres_ctot, dz,           \
@@ -710,7 +714,7 @@ int launch_colsum(const __nv_bfloat16* g, long long rows, int C, float* dst, flo
   const int nblk = reduce_blocks(rows);
   HGR_CHECK_CUDA(launch_pdl(colsum_partial_kernel, dim3(nblk), dim3(kThreads), kThreads * 8 * sizeof(float), st, g,
                             rows, C, partial));
-  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3((C + 7) / 8), dim3(256), 0, st, partial, nblk, 1, C, dst,
+  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3(C), dim3(kFinalThreads), 0, st, partial, nblk, 1, C, dst,
                             nullptr));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -721,7 +725,8 @@ int launch_ln_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* 
   const int nblk = reduce_blocks(rows);
   HGR_CHECK_CUDA(launch_pdl(ln_bwd_kernel, dim3(nblk), dim3(kThreads), 0, st, dy, x, gamma, g_in, g_out, rows,
                             partial));
-  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3(32), dim3(256), 0, st, partial, nblk, 2, 256, dgamma, dbeta));
+  HGR_CHECK_CUDA(launch_pdl(sums_final_kernel, dim3(256), dim3(kFinalThreads), 0, st, partial, nblk, 2, 256, dgamma,
+                            dbeta));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -702,7 +702,8 @@ int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, 
     return 0;
   };
   if (part == 0) {
-    // heads: the class head (one CTA, token 0 of gA) beside the pose head (tokens 1.. of gA)
+    // heads: the class head (one CTA, token 0 of gA) and the pose head's bias gradient beside the pose head
+    // (tokens 1.. of gA)
     cudaStream_t ws_layers = ws;
     ws = pl->side && (pl->fork_mask & 1) ? pl->side : st;
     fork();
@@ -711,10 +712,11 @@ int hgr_train_backward_part(hgr_train_plan_t* pl, const void* d_x, int x_dtype, 
                                      pl->G("decoder.mlp_head.0.weight"), pl->G("decoder.mlp_head.0.bias"),
                                      pl->G("decoder.mlp_head.1.weight"), pl->G("decoder.mlp_head.1.bias"), ws))
       return rc;
+    if (int rc = launch_heat_bias_grad(d_dheatmaps, B, pl->J, 16 * F * F, pl->G("decoder.simple_decoder.1.bias"), ws))
+      return rc;
     cudaEvent_t cls_done = record(ws);
     if (int rc = launch_pose_head_bwd(pl->x[kDepth], pl->P("decoder.simple_decoder.1.weight"), d_dheatmaps, B, F, pl->J,
-                                      pl->gA, pl->wpartial, pl->G("decoder.simple_decoder.1.weight"),
-                                      pl->G("decoder.simple_decoder.1.bias"), st))
+                                      pl->gA, pl->wpartial, pl->G("decoder.simple_decoder.1.weight"), st))
       return rc;
     wait(st, cls_done);
     ws = ws_layers;

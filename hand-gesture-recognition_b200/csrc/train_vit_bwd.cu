@@ -492,7 +492,7 @@ int launch_cls_head_bwd(const __nv_bfloat16* tokens, const float* gamma, const f
 }
 
 int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const float* dheat, int B, int F, int J,
-                         __nv_bfloat16* dtokens, float* dw_partial, float* dw, float* dbias, cudaStream_t st) {
+                         __nv_bfloat16* dtokens, float* dw_partial, float* dw, cudaStream_t st) {
   if (J < 1 || J > kMaxJ) {
     set_error("pose_head_bwd: unsupported J=%d", J);
     return -1;
@@ -508,9 +508,12 @@ int launch_pose_head_bwd(const __nv_bfloat16* tokens, const float* w, const floa
   HGR_CHECK_CUDA(cudaFuncSetAttribute(pose_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HGR_CHECK_CUDA(launch_pdl(pose_head_bwd_kernel, dim3(F, B), dim3(256 * kPhases), smem, st, tokens, w, dheat, F, J,
                             dtokens, dw_partial));
-  if (int rc = launch_partial_sum(dw_partial, B * F, J * kDim, dw, st)) return rc;
-  HGR_CHECK_CUDA(launch_pdl(heat_bias_grad_kernel, dim3(J), dim3(256), 0, st, dheat, B, J, So * So, dbias));
-  HGR_CHECK_CUDA(cudaGetLastError());
+  return launch_partial_sum(dw_partial, B * F, J * kDim, dw, st);
+}
+
+// d bias of the pose head: independent of the kernels above (the trainer's plan runs it beside them)
+int launch_heat_bias_grad(const float* dheat, int B, int J, int hw, float* dbias, cudaStream_t st) {
+  HGR_CHECK_CUDA(launch_pdl(heat_bias_grad_kernel, dim3(J), dim3(256), 0, st, dheat, B, J, hw, dbias));
   return 0;
 }
 

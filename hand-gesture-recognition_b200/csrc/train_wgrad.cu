@@ -284,14 +284,26 @@ conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dz, const TIn* __restrict__
     out[i] = ((fold[i] + fold[64 * 27 + i]) + fold[2 * 64 * 27 + i]) + fold[3 * 64 * 27 + i];
 }
 
-__global__ void partial_sum_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dst) {
+// dst[i] = sum_c partial[c][i].  A CTA covers 32 elements; warp w adds parts w, w + 8, ... in ascending order
+// (double), the eight warp sums are folded in ascending order: with one thread per element the 384 per-CTA
+// partials of the pose head and of conv1 were a serial chain of 384 loads on 42 CTAs (31 us).
+__global__ void __launch_bounds__(256)
+partial_sum_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ dst) {
   pdl_launch_dependents();
   pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ double fold[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int c = 0; c < nparts; ++c) s += (double)partial[(size_t)c * n + i];
-  dst[i] = (float)s;
+  if (i < n)
+    for (int c = w; c < nparts; c += 8) s += (double)partial[(size_t)c * n + i];
+  fold[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < n) {
+#pragma unroll
+    for (int q = 1; q < 8; ++q) s += fold[q][lane];
+    dst[i] = (float)s;
+  }
 }
 
 }  // namespace
@@ -301,7 +313,10 @@ static int wgrad_bm(int Cout) { return Cout % 128 == 0 ? 128 : 64; }
 size_t wgrad_partial_floats(int Cout, int Cin, int k, long long P, int* chunks_out) {
   const int taps = k * k;
   const long long tiles = (long long)(Cout / wgrad_bm(Cout)) * (Cin / 64) * taps;
-  long long chunks = (148 * 4 + tiles - 1) / tiles;
+  // 592 CTAs are two full waves of the 128-channel tile (80 KiB of shared memory: 2 CTAs per SM) and one of the
+  // 64-channel tile (4 per SM).  Rounded DOWN: tiles x chunks just above 592 (594, 612, 648, 720 with the rounding
+  // up this started with) paid a whole extra wave for a handful of CTAs.
+  long long chunks = 148 * 4 / tiles;
   const long long max_chunks = (P + 4 * kPix - 1) / (4 * kPix);  // at least 256 pixels per chunk
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -358,8 +373,10 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
   p.per_chunk = (int)per;
   if (int rc = wgrad_bm(Cout) == 128 ? launch_wgrad_impl<4>(p, chunks, st) : launch_wgrad_impl<2>(p, chunks, st)) return rc;
   const long long total = (long long)Cout * Cin * k * k;
-  // elements per CTA: 256, or 32 when that still leaves fewer than four CTAs per SM and there are chunks to share
-  const bool split = total / 256 < 148 * 4 && chunks >= 16;
+  // elements per CTA: 256, or 32 with the chunks shared by 8 thread groups where the weight is small and the chunks
+  // are many (128 x 64 elements x 288 chunks: 33 -> 12 us; 64 x 64 x 9 x 65: 11 -> 8 us).  With 19-37 chunks the
+  // fold costs more than the shorter chain saves (measured: 6 -> 10 us on the transformer's 256 x 256 weights).
+  const bool split = chunks >= 64 && total < 40000;
   long long rb = (total + (split ? 31 : 255)) / (split ? 32 : 256);
   if (rb > 148 * 8) rb = 148 * 8;
   if (split)
@@ -395,14 +412,14 @@ int launch_conv1_wgrad(const __nv_bfloat16* dz, const void* x, int x_dtype, int 
                               static_cast<const __nv_bfloat16*>(x), S, rows_per_cta, partial));
   }
   const int nparts = grid.x * grid.y;
-  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((64 * 27 + 127) / 128), dim3(128), 0, st, partial, nparts,
-                            64 * 27, dw));
+  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((64 * 27 + 31) / 32), dim3(256), 0, st, partial, nparts, 64 * 27,
+                            dw));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_partial_sum(const float* partial, int nparts, int n, float* dst, cudaStream_t st) {
-  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((n + 127) / 128), dim3(128), 0, st, partial, nparts, n, dst));
+  HGR_CHECK_CUDA(launch_pdl(partial_sum_kernel, dim3((n + 31) / 32), dim3(256), 0, st, partial, nparts, n, dst));
   HGR_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
