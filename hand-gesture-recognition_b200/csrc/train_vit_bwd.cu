@@ -320,7 +320,7 @@ cls_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __res
 // once per pixel (by the CTA with y0 == ty) into a per-CTA partial.  Thread c = channel c.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxJ = 24;
-constexpr int kPhases = 2;  // pixel phases per CTA: thread (c, q) handles output columns ox = q (mod 2)
+constexpr int kPhases = 2;  // pixel phases per CTA: thread (c, q) handles output columns [q So / 2, (q + 1) So / 2)
 
 // Shared-memory traffic decides this kernel (42 loads per pixel and channel in the naive form), so the weight
 // column of a thread lives in registers and the dheat row is staged TRANSPOSED ([ox][24 joints]) so that the 21
@@ -376,16 +376,27 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
       sdh[ox * kMaxJ + j] = dheat[(((size_t)b * J + j) * So + oy) * So + ox];
     }
     __syncthreads();
-    for (int ox = q; ox < So; ox += kPhases) {
+    // Phase q walks the output columns [q So / 2, (q + 1) So / 2) in order: the source column x0 advances by at most
+    // one per pixel (scale < 1), so the two row-interpolated token values around the pixel (a0 at x0, a1 at x0 + 1)
+    // and the gradients pending for those two tokens (g0, g1) live in registers and touch shared memory only when
+    // x0 moves - per pixel that leaves the six dheat loads and the 48 FMAs.
+    const int ox_begin = q * (So / kPhases), ox_end = ox_begin + So / kPhases;
+    auto colval = [&](int x) { return l0 * __bfloat162float(r0[x * kDim]) + l1 * __bfloat162float(r1[x * kDim]); };
+    int cx = (int)(scale * (float)ox_begin);
+    float a0 = colval(cx), a1 = colval(cx + 1 < F ? cx + 1 : F - 1), g0 = 0.f, g1 = 0.f;
+    for (int ox = ox_begin; ox < ox_end; ++ox) {
       const float sx = scale * (float)ox;
       const int x0 = (int)sx;
-      const int x1 = x0 + (x0 < F - 1 ? 1 : 0);
       const float m1 = sx - (float)x0, m0 = 1.0f - m1;
-      const float t00 = __bfloat162float(r0[x0 * kDim]);
-      const float t01 = __bfloat162float(r0[x1 * kDim]);
-      const float t10 = __bfloat162float(r1[x0 * kDim]);
-      const float t11 = __bfloat162float(r1[x1 * kDim]);
-      const float up = l0 * (m0 * t00 + m1 * t01) + l1 * (m0 * t10 + m1 * t11);
+      if (x0 != cx) {
+        mydx[cx * kDim + c] += g0;
+        g0 = g1;
+        g1 = 0.f;
+        a0 = a1;
+        cx = x0;
+        a1 = colval(cx + 1 < F ? cx + 1 : F - 1);  // at the last column m1 is 0
+      }
+      const float up = m0 * a0 + m1 * a1;
       if (up > 0.f) {
         float dup = 0.f;
         const float4* dh4 = reinterpret_cast<const float4*>(sdh + ox * kMaxJ);
@@ -400,10 +411,12 @@ pose_head_bwd_kernel(const __nv_bfloat16* __restrict__ tokens, const float* __re
           }
         }
         const float v = wy * dup;
-        mydx[x0 * kDim + c] = fmaf(m0, v, mydx[x0 * kDim + c]);
-        mydx[x1 * kDim + c] = fmaf(m1, v, mydx[x1 * kDim + c]);
+        g0 = fmaf(m0, v, g0);
+        g1 = fmaf(m1, v, g1);
       }
     }
+    mydx[cx * kDim + c] += g0;
+    if (cx + 1 < F) mydx[(cx + 1) * kDim + c] += g1;
   }
   __syncthreads();
   // fold the phases in a fixed order: token-row gradient, then the weight-gradient partial
