@@ -290,7 +290,9 @@ HGR_API int hgr_train_buffer(hgr_train_plan_t* plan, const char* name, void** d_
  * unbiased variance; momentum < 0 leaves them untouched), fp32 logits (B, C) and heatmaps (B, J, S/4, S/4). */
 HGR_API int hgr_train_forward(hgr_train_plan_t* plan, const void* d_x, int x_dtype, float* d_logits, float* d_heatmaps,
                               float momentum, void* stream);
-/* Backward of the last hgr_train_forward of this plan (same d_x): overwrites the whole gradient block. */
+/* Backward of the last hgr_train_forward of this plan (same d_x): overwrites the whole gradient block.  A few kernels
+ * run on a stream the plan owns, forked from and joined back into `stream` by events inside the call, so the call is
+ * still ordered on `stream` alone and can be captured into a CUDA graph. */
 HGR_API int hgr_train_backward(hgr_train_plan_t* plan, const void* d_x, int x_dtype, const float* d_dlogits,
                                const float* d_dheatmaps, void* stream);
 /* The same backward in three parts, to be called in order 0, 1, 2 (train.py:58-108 under DistributedDataParallel
