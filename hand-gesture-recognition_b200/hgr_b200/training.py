@@ -363,7 +363,7 @@ class DataParallelTrainer:
             static = [torch.empty_like(t) for t in (x, labels, target, target_weight)]
             for s_, t in zip(static, (x, labels, target, target_weight)):
                 s_.copy_(t)
-            self._forward_backward(*static, update_running=False)  # warm-up outside the capture (see below)
+            self._forward_backward(*static, update_running=False)  # warm-up outside the capture, as in _forward_backward_graph
             torch.cuda.synchronize(dev)
             graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
             pool = torch.cuda.graph_pool_handle()
@@ -373,8 +373,9 @@ class DataParallelTrainer:
             for k in (1, 2):
                 with torch.cuda.graph(graphs[k], pool=pool):
                     backward_train(self.state, plan, static[0], dlogits, dheat, k)
-            entry = self._graphs[key] = (graphs, static, loss3)
-        graphs, static, loss3 = entry
+            # the graphs hold raw pointers into the plan's workspace and into the loss gradients: keep their owners
+            entry = self._graphs[key] = (graphs, static, loss3, (plan, dlogits, dheat))
+        graphs, static, loss3, _ = entry
         for s_, t in zip(static, (x, labels, target, target_weight)):
             if s_.data_ptr() != t.data_ptr():
                 s_.copy_(t, non_blocking=True)
