@@ -59,6 +59,29 @@ def test_train_param_layout_follows_state_dict_order():
     assert _lib.load().hgr_train_workspace_bytes(192, 21, 19, 1) == 0  # batch statistics need batch >= 2
 
 
+def test_gradient_buckets_follow_the_order_the_backward_completes_them():
+    """grad_buckets: the three contiguous ranges of the flat gradient block that hgr_train_backward_part 0, 1, 2
+    complete (heads + transformer + proj; down2 + cspelan3; conv1 .. cspelan2), in that order, covering every
+    parameter exactly once - the ranges the data-parallel step may all-reduce while the next part runs."""
+    from hgr_b200 import _lib
+    from hgr_b200.training import grad_buckets
+    lay = _lib.train_param_layout(21, 19)
+    total = lay[-1][1] + lay[-1][2]
+    b = grad_buckets(21, 19)
+    assert len(b) == 3 and b[2][0] == 0 and b[0][1] == total
+    assert b[2][1] == b[1][0] and b[1][1] == b[0][0]
+    owner = {}
+    for k, (lo, hi) in enumerate(b):
+        for name, off, n in lay:
+            if lo <= off < hi:
+                assert off + n <= hi, name
+                owner[name] = k
+    assert len(owner) == len(lay)
+    assert owner["proj.weight"] == 0 and owner["decoder.simple_decoder.1.bias"] == 0 and owner["decoder.cls_token"] == 0
+    assert owner["encoder.down2.conv.weight"] == 1 and owner["encoder.cspelan3.cv4.bn.bias"] == 1
+    assert owner["encoder.conv1.conv.weight"] == 2 and owner["encoder.cspelan2.cv4.bn.bias"] == 2
+
+
 def test_train_mode_refuses_cpu():
     from hgr_b200 import MultiTaskNet
     m = MultiTaskNet(21, 19, [64, 64]).train()
