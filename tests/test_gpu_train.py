@@ -46,6 +46,9 @@ def _stream():
     (256, 128, 1, 1, 8, 5, (0, 0), (64, 64)),
     (128, 128, 3, 1, 12, 2, (0, 0), (128, 0)),
     (256, 768, 1, 1, 1, 290, (0, 0), (0, 0)),   # a Linear: rows = "images" of 1 x 1 pixels
+    # few elements, many chunks: the reduce shares an element's chunks between eight thread groups (65 / 144 chunks)
+    (64, 64, 3, 1, 96, 2, (0, 0), (0, 0)),
+    (64, 128, 1, 1, 96, 4, (64, 0), (0, 0)),
 ])
 def test_wgrad(lib, cin, cout, k, s, h, b, gpad, xpad):
     dev = torch.device("cuda")
