@@ -74,6 +74,9 @@ bool gelan_tail_enabled() {
 
 // read when a training plan is created (not cached: one process can hold plans of both kinds, which is how the
 // parity test compares them)
+// HGR_WGRAD_TC=0: every weight gradient on the mma.sync kernel (read per call: the parity test compares both)
+bool wgrad_tc_enabled() { return env_flag("HGR_WGRAD_TC", true); }
+
 int train_fork_mask() {
   const char* v = getenv("HGR_TRAIN_FORK");
   return v && *v ? atoi(v) & 7 : 1;

@@ -350,28 +350,33 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
     set_error("wgrad: %lld output pixels out of range", P);
     return -1;
   }
-  WgradParams p;
-  p.g = g;
-  p.x = x;
-  p.partial = partial;
-  p.g_ctot = g_ctot;
-  p.x_ctot = x_ctot;
-  p.Cout = Cout;
-  p.Cin = Cin;
-  p.B = B;
-  p.H = H;
-  p.W = W;
-  p.Ho = H / s;
-  p.Wo = W / s;
-  p.k = k;
-  p.s = s;
-  p.P = (int)P;
   int chunks = 1;
-  wgrad_partial_floats(Cout, Cin, k, P, &chunks);
-  long long per = (P + chunks - 1) / chunks;
-  per = (per + kPix - 1) / kPix * kPix;
-  p.per_chunk = (int)per;
-  if (int rc = wgrad_bm(Cout) == 128 ? launch_wgrad_impl<4>(p, chunks, st) : launch_wgrad_impl<2>(p, chunks, st)) return rc;
+  if (wgrad_tc_supported(g_ctot, x_ctot, Cin, Cout, k, s, H, W)) {
+    // tcgen05 path (train_wgrad_tc.cu): same partial layout, never more chunks than the buffer was sized for
+    if (int rc = launch_wgrad_tc(g, g_ctot, x, x_ctot, B, H, W, Cin, Cout, k, s, partial, &chunks, st)) return rc;
+  } else {
+    WgradParams p;
+    p.g = g;
+    p.x = x;
+    p.partial = partial;
+    p.g_ctot = g_ctot;
+    p.x_ctot = x_ctot;
+    p.Cout = Cout;
+    p.Cin = Cin;
+    p.B = B;
+    p.H = H;
+    p.W = W;
+    p.Ho = H / s;
+    p.Wo = W / s;
+    p.k = k;
+    p.s = s;
+    p.P = (int)P;
+    wgrad_partial_floats(Cout, Cin, k, P, &chunks);
+    long long per = (P + chunks - 1) / chunks;
+    per = (per + kPix - 1) / kPix * kPix;
+    p.per_chunk = (int)per;
+    if (int rc = wgrad_bm(Cout) == 128 ? launch_wgrad_impl<4>(p, chunks, st) : launch_wgrad_impl<2>(p, chunks, st)) return rc;
+  }
   const long long total = (long long)Cout * Cin * k * k;
   // elements per CTA: 256, or 32 with the chunks shared by 8 thread groups where the weight is small and the chunks
   // are many (128 x 64 elements x 288 chunks: 33 -> 12 us; 64 x 64 x 9 x 65: 11 -> 8 us).  With 19-37 chunks the
