@@ -178,7 +178,7 @@ bool conv1_tc_enabled();
 // HGR_TRAIN_FORK (bit mask, default 1): which parts of the training backward send work to the plan's side stream -
 // 1 the class head beside the pose head, 2 the transformer's weight gradients, 4 the backbone's weight gradients
 int train_fork_mask();
-// HGR_WGRAD_TC=0: weight gradients of the Cout % 128 == 0 layers on mma.sync instead of tcgen05 (train_wgrad_tc.cu)
+// HGR_WGRAD_TC=0: weight gradients on mma.sync (train_wgrad.cu) instead of tcgen05 (train_wgrad_tc.cu)
 bool wgrad_tc_enabled();
 bool conv1_tc_supported(int S);
 int launch_conv1_tc(const void* x, int x_dtype, __nv_bfloat16* out, const __nv_bfloat16* w, const float* shift, int B,

@@ -67,7 +67,7 @@ int launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* probs, i
 int launch_cls_head_bwd(const __nv_bfloat16* tokens, const float* gamma, const float* beta, const float* w,
                         const float* dlogits, int B, int T, int NC, __nv_bfloat16* dtokens, float* dgamma,
                         float* dbeta, float* dw, float* dbias, cudaStream_t st);
-// tcgen05 weight gradient (train_wgrad_tc.cu): Cout % 128 == 0 layers; partial layout and reduce of launch_wgrad
+// tcgen05 weight gradient (train_wgrad_tc.cu): Cout and Cin multiples of 64; partial layout and reduce of launch_wgrad
 bool wgrad_tc_supported(int g_ctot, int x_ctot, int Cin, int Cout, int k, int s, int H, int W);
 int wgrad_tc_chunks(int Cout, int Cin, int k, long long P);
 int launch_wgrad_tc(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int x_ctot, int B, int H, int W, int Cin,

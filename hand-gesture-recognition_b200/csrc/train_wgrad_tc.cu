@@ -1,5 +1,5 @@
 // Weight gradients on the 5th-gen tensor cores (the autograd backward of every Conv2d / Linear
-// with Cout a multiple of 128 on the path, reference model/gelan.py:18-56, model/transformer.py:29-77):
+// of the path except conv1, reference model/gelan.py:18-56, model/transformer.py:29-77):
 //     dW[co][tap][ci] = sum over output pixels p of  G[p][co] * X[shift_tap(p)][ci]
 // The reduction runs over PIXELS while both operands are stored channel-contiguous (NHWC), so for tcgen05.mma both
 // are MN-major: A = G^T (M = 128 output channels), B = X^T (N = BN input channels), K = 64 pixels per pipeline
@@ -13,8 +13,9 @@
 // the chunks and writes PyTorch's (Cout, Cin, kh, kw).  One CTA per SM (4 x 48 KiB stages at BN = 256), one wave.
 //
 // Why: the mma.sync kernel it replaces is at that path's ceiling on B200 (an HMMA.16816 holds a scheduler's tensor
-// sub-pipe ~22 cycles: ~420 TFLOP/s per GPU; 0.84 ms of the 4.0 ms training step at batch 32).  Layers with
-// Cout = 64 (cspelan1's 3x3 convs, conv1) stay on train_wgrad.cu.
+// sub-pipe ~22 cycles: ~420 TFLOP/s per GPU; 0.84 ms of the 4.0 ms training step at batch 32).  A layer with 64
+// output channels runs the same M = 128 MMA: the second A tile lies beyond the G map's channel extent, TMA fills it
+// with zeros and its 64 accumulator rows are not written.  conv1 (3 input channels) stays on train_wgrad.cu.
 #include <cstring>
 
 #include "hgr_internal.h"
@@ -36,7 +37,6 @@ struct WgradTcParams {
   int tiles_ci;               // Cin / BN
   int tiles_w, tiles_h, tiles_n, bw, bh, bi;  // 64-pixel boxes of the OUTPUT map
   int boxes_per_chunk, nbox;
-  int x_c_off;                // always 0 (the slice offset is in the map's base pointer); kept for the s2 view
   int tap_dc[9], tap_dw[9], tap_p[9], tap_dh[9];  // tap -> coordinate offsets of the X map (as gemm_tcgen05.cu)
 };
 
@@ -125,8 +125,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       const uint32_t b = a + 2 * kTileBytes;
 #pragma unroll
       for (int k = 0; k < kBoxPix / 16; ++k)  // 16 pixel rows = 2048 B per MMA
-        umma_bf16_ss_elect(tmem, desc_mn_sw128(a + k * 2048, kTileBytes, 1024), desc_mn_sw128(b + k * 2048, kTileBytes, 1024),
-                           idesc, (i | k) != 0 ? 1u : 0u);
+        umma_bf16_ss_elect(tmem, desc_mn_sw128(a + k * 2048, kTileBytes, 1024),
+                           desc_mn_sw128(b + k * 2048, kTileBytes, 1024), idesc, (i | k) != 0 ? 1u : 0u);
       umma_commit_elect(&empty[s]);
     }
     if (nk > 0) umma_commit_elect(acc_full);
@@ -149,9 +149,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = 0u;  // an empty chunk still owes its (zero) partial to the reduce
       }
+      if (co0 + row < p.Cout) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<uint4*>(out + c + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<uint4*>(out + c + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+      }
     }
     tc_fence_before();
   }
@@ -189,7 +191,7 @@ int launch_impl(const CUtensorMap& tmG, const CUtensorMap& tmX, const WgradTcPar
 
 bool wgrad_tc_supported(int g_ctot, int x_ctot, int Cin, int Cout, int k, int s, int H, int W) {
   if (!wgrad_tc_enabled()) return false;
-  if (Cout % 128 != 0 || Cin % 64 != 0 || g_ctot % 8 != 0 || x_ctot % 8 != 0) return false;
+  if (Cout % 64 != 0 || Cin % 64 != 0 || g_ctot % 8 != 0 || x_ctot % 8 != 0) return false;
   if (!((k == 1 && s == 1) || (k == 3 && (s == 1 || s == 2)))) return false;
   if (s == 2 && (x_ctot != Cin || (H & 1) || (W & 1))) return false;  // the stride-2 view reads a whole buffer
   return true;
@@ -197,7 +199,7 @@ bool wgrad_tc_supported(int g_ctot, int x_ctot, int Cin, int Cout, int k, int s,
 
 int wgrad_tc_chunks(int Cout, int Cin, int k, long long P) {
   const int taps = k * k;
-  const long long tiles = (long long)(Cout / 128) * (Cin / pick_bn(Cin)) * taps;
+  const long long tiles = (long long)((Cout + 127) / 128) * (Cin / pick_bn(Cin)) * taps;
   long long chunks = 148 / tiles;                   // one CTA per SM, one wave
   const long long cap = (P + 255) / 256;            // the mma.sync path's cap: the partial buffer is sized for it
   if (chunks > cap) chunks = cap;
@@ -262,7 +264,7 @@ int launch_wgrad_tc(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, 
         p.tap_dh[t] = kh == 0 ? -1 : 0;
       }
   }
-  const dim3 grid((Cout / 128) * p.tiles_ci, p.taps, chunks);
+  const dim3 grid(((Cout + 127) / 128) * p.tiles_ci, p.taps, chunks);
   if (BN == 256) return launch_impl<256>(tmG, tmX, p, grid, st);
   if (BN == 128) return launch_impl<128>(tmG, tmX, p, grid, st);
   return launch_impl<64>(tmG, tmX, p, grid, st);
