@@ -50,7 +50,11 @@ def _stream():
     (64, 64, 3, 1, 96, 2, (0, 0), (0, 0)),
     (64, 128, 1, 1, 96, 4, (64, 0), (0, 0)),
 ])
-def test_wgrad(lib, cin, cout, k, s, h, b, gpad, xpad):
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_wgrad(lib, monkeypatch, cin, cout, k, s, h, b, gpad, xpad, tc):
+    """Weight gradient of a Conv2d / Linear against torch's fp32 conv2d_weight: on tcgen05 (train_wgrad_tc.cu, the
+    default) and on the mma.sync kernel it replaced (HGR_WGRAD_TC=0, read per call)."""
+    monkeypatch.setenv("HGR_WGRAD_TC", tc)
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(cin + cout + k)
     x = bf16_round(torch.randn(b, cin, h, h, generator=g))
@@ -72,7 +76,7 @@ def test_wgrad(lib, cin, cout, k, s, h, b, gpad, xpad):
                        partial.data_ptr(), dw.data_ptr(), _stream()), "hgr_wgrad")
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(x, (cout, cin, k, k), dy, stride=s, padding=k // 2)
-    r, _ = report(f"wgrad {cin}->{cout} k{k} s{s}", dw, ref)
+    r, _ = report(f"wgrad {cin}->{cout} k{k} s{s} {'tcgen05' if tc == '1' else 'mma.sync'}", dw, ref)
     assert r <= 6e-3
 
 
