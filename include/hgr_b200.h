@@ -319,8 +319,8 @@ HGR_API int hgr_adamw_step(float* d_params, const float* d_grads, float* d_exp_a
 /* Single kernels of the training step (parity tests).
  * hgr_wgrad: dW (cout, cin, k, k) fp32 = sum over output pixels of g[p, :cout]^T x[shift(p), :cin]; g is the
  *   (B*Ho*Wo, g_ctot) bf16 output gradient, x the (B, H, W, x_ctot) bf16 NHWC input, stride s, padding k/2;
- *   d_partial: hgr_wgrad_partial_floats(...) floats of scratch.  Runs on tcgen05 (MN-major operands, split over pixel
- *   chunks, fixed-order reduce) when cin and cout are multiples of 64, else never (such shapes are refused). */
+ *   d_partial: hgr_wgrad_partial_floats(...) floats of scratch.  cin and cout must be multiples of 64.  Runs on tcgen05
+ *   (MN-major operands, split over pixel chunks, fixed-order reduce); HGR_WGRAD_TC=0 selects the mma.sync kernel. */
 HGR_API int hgr_wgrad(const void* d_g, int g_ctot, const void* d_x, int x_ctot, int B, int H, int W, int cin, int cout,
                       int k, int s, float* d_partial, float* d_dw, void* stream);
 HGR_API size_t hgr_wgrad_partial_floats(int cout, int cin, int k, long long pixels);
