@@ -541,7 +541,6 @@ loss_final_kernel(const float* __restrict__ logits, const long long* __restrict_
                   float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float ce[kThreads];
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += kThreads) {
     const float* row = logits + (size_t)b * C;
@@ -555,13 +554,29 @@ loss_final_kernel(const float* __restrict__ logits, const long long* __restrict_
       for (int c = 0; c < C; ++c)
         dlogits[(size_t)b * C + c] = cls_weight * (expf(row[c] - m) / s - (c == y ? 1.f : 0.f)) / (float)B;
   }
-  ce[threadIdx.x] = acc;
+  // fixed-order block sums of the per-sample CE terms and of the heatmap partials: thread i adds partials i,
+  // i + 256, ..., lanes fold by a butterfly, the eight warp sums in ascending order (one thread walking 256 + 592
+  // values was 21 us on the step's critical path)
+  __shared__ double red[kThreads / 32][2];
+  double t = (double)acc, h = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += kThreads) h += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+    h += __shfl_xor_sync(0xffffffffu, h, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5][0] = t;
+    red[threadIdx.x >> 5][1] = h;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < kThreads; ++i) t += (double)ce[i];
-    double h = 0.0;
-    for (int i = 0; i < nblk; ++i) h += (double)partial[i];
+    t = 0.0;
+    h = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      t += red[w][0];
+      h += red[w][1];
+    }
     const float cl = cls_weight * (float)(t / (double)B);
     const float jl = 0.5f * (float)(h * (double)inv_norm);
     out[0] = cl + jl;
