@@ -351,8 +351,10 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
     return -1;
   }
   int chunks = 1;
-  if (wgrad_tc_supported(g_ctot, x_ctot, Cin, Cout, k, s, H, W)) {
-    // tcgen05 path (train_wgrad_tc.cu): same partial layout, never more chunks than the buffer was sized for
+  wgrad_partial_floats(Cout, Cin, k, P, &chunks);  // the chunk count the caller's partial buffer was sized for
+  if (wgrad_tc_supported(g_ctot, x_ctot, Cin, Cout, k, s, H, W) && wgrad_tc_chunks(Cout, Cin, k, P) <= chunks) {
+    // tcgen05 path (train_wgrad_tc.cu): same partial layout, never more chunks than that (its tiles are at least as
+    // large and its CTA budget a quarter, so the condition holds for every shape; it is checked, not assumed)
     if (int rc = launch_wgrad_tc(g, g_ctot, x, x_ctot, B, H, W, Cin, Cout, k, s, partial, &chunks, st)) return rc;
   } else {
     WgradParams p;
@@ -371,7 +373,6 @@ int launch_wgrad(const __nv_bfloat16* g, int g_ctot, const __nv_bfloat16* x, int
     p.k = k;
     p.s = s;
     p.P = (int)P;
-    wgrad_partial_floats(Cout, Cin, k, P, &chunks);
     long long per = (P + chunks - 1) / chunks;
     per = (per + kPix - 1) / kPix * kPix;
     p.per_chunk = (int)per;
