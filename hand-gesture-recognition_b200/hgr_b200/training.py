@@ -440,3 +440,54 @@ class DataParallelTrainer:
                                                   _stream(x.device)), "hgr_adamw_step")
         self.model._packed = None  # the eval-mode weight pack is stale now (the kernel does not bump tensor versions)
         return loss3
+
+    # ---- checkpoint / resume (train.py:50-51 + Lightning's optimizer_states) ----
+    def state_dict(self):
+        """The optimiser state in torch.optim.AdamW's own state_dict layout (one group, parameters in
+        model.parameters() order, per-parameter step / exp_avg / exp_avg_sq), so that a checkpoint written here
+        resumes under `torch.optim.AdamW(model.parameters())` and the other way round.  The weights and BatchNorm
+        statistics are the module's own state_dict."""
+        group = dict(torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))]).defaults)
+        group.update(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay,
+                     params=list(range(len(self.state.layout))))
+        state = {}
+        if self.steps > 0:
+            for i, (_, off, n, shape) in enumerate(self._param_views()):
+                state[i] = {"step": torch.tensor(float(self.steps)),
+                            "exp_avg": self.exp_avg[off: off + n].view(shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[off: off + n].view(shape).clone()}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Inverse of state_dict(); also accepts torch.optim.AdamW(model.parameters()).state_dict().  Every parameter
+        must carry the same step count (the fused update keeps one)."""
+        groups = sd["param_groups"]
+        views = self._param_views()
+        if len(groups) != 1 or len(groups[0]["params"]) != len(views):
+            raise ValueError("expected ONE parameter group over all of model.parameters()")
+        g = groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        if g.get("amsgrad") or g.get("maximize"):
+            raise ValueError("amsgrad / maximize are not part of the fused AdamW update")
+        state = sd["state"]
+        if not state:
+            self.steps = 0
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            return
+        if sorted(state.keys()) != list(range(len(views))):
+            raise ValueError("optimizer state must cover every parameter")
+        steps = {int(float(state[i]["step"])) for i in state}
+        if len(steps) != 1:
+            raise ValueError(f"parameters carry different step counts: {sorted(steps)}")
+        self.steps = steps.pop()
+        for i, (name, off, n, shape) in enumerate(views):
+            for key, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                t = state[i][key]
+                if tuple(t.shape) != tuple(shape):
+                    raise ValueError(f"{key} of {name}: shape {tuple(t.shape)}, expected {tuple(shape)}")
+                flat[off: off + n].copy_(t.reshape(-1).to(flat.device, torch.float32))
+
+    def _param_views(self):
+        shapes = {name: tuple(p.shape) for name, p in self.model.named_parameters()}
+        return [(name, off, n, shapes[name]) for name, off, n in self.state.layout]

@@ -316,6 +316,56 @@ def test_trainer_cuda_graph_replay_equals_plain_launches(monkeypatch):
     assert int(out[1][2][0]) == 100 + 3  # synthetic_state_dict starts the counters at 100
 
 
+def test_trainer_checkpoint_resumes_bitwise_and_speaks_torch_adamw():
+    """DataParallelTrainer.state_dict() / load_state_dict() (train.py:50-51 + Lightning's optimizer_states): a run
+    resumed from (module state_dict, trainer state_dict) continues bit-identically, and the optimiser state is
+    torch.optim.AdamW's own layout - it loads into torch.optim.AdamW(model.parameters()) and back."""
+    from hgr_b200 import DataParallelTrainer, MultiTaskNet
+    dev = torch.device("cuda")
+    sd = O.synthetic_state_dict(5)
+    xs = [O.synthetic_images(4, 64, 30 + i).to(dev) for i in range(4)]
+    labels, target, weight = (t.to(dev) for t in O.synthetic_targets(4, 64, seed=7))
+
+    def fresh(state=None):
+        net = MultiTaskNet(21, 19, [64, 64])
+        net.load_state_dict(state if state is not None else sd, strict=True)
+        return net.to(dev).train()
+
+    a = DataParallelTrainer(fresh(), lr=1e-3)
+    for x in xs[:2]:
+        a.step(x, labels, target, weight)
+    torch.cuda.synchronize()
+    ck_model = {k: v.detach().cpu().clone() for k, v in a.model.state_dict().items()}
+    ck_opt = a.state_dict()
+    assert len(ck_opt["state"]) == 114 and float(ck_opt["state"][0]["step"]) == 2.0
+    for x in xs[2:]:
+        a.step(x, labels, target, weight)
+    # resume in a new trainer
+    b = DataParallelTrainer(fresh(ck_model), lr=5e-2)
+    b.load_state_dict(ck_opt)
+    assert b.steps == 2 and b.lr == 1e-3
+    for x in xs[2:]:
+        b.step(x, labels, target, weight)
+    torch.cuda.synchronize()
+    assert torch.equal(a.state.params, b.state.params) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+    assert torch.equal(a.state.bnstats, b.state.bnstats)
+    # the same dictionary drives torch's optimiser, and torch's own state_dict comes back
+    net = fresh(ck_model)
+    opt = torch.optim.AdamW(net.parameters(), lr=1.0)
+    opt.load_state_dict(ck_opt)
+    assert opt.param_groups[0]["lr"] == 1e-3 and len(opt.state) == 114
+    c = DataParallelTrainer(fresh(ck_model), lr=1.0)
+    c.load_state_dict(opt.state_dict())
+    assert c.steps == 2 and torch.equal(c.exp_avg.cpu(), b_flat(ck_opt, c, "exp_avg"))
+
+
+def b_flat(opt_sd, trainer, key):
+    flat = torch.zeros_like(trainer.exp_avg, device="cpu")
+    for i, (_, off, n, _) in enumerate(trainer._param_views()):
+        flat[off: off + n] = opt_sd["state"][i][key].reshape(-1).cpu()
+    return flat
+
+
 def test_backward_in_three_parts_equals_the_whole_backward():
     """hgr_train_backward_part 0, 1, 2 (the units the data-parallel step overlaps its all-reduce with) write exactly
     the gradient block of hgr_train_backward, and each part completes the range grad_buckets names: after part k
